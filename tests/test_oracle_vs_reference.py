@@ -1,0 +1,100 @@
+"""Pins the oracle against the LIVE reference (only where /root/reference exists, i.e. the build
+container; skipped on the GPU box).  Fresh seeds, so this is independent of the golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mspl_oracle as O
+from oracle.ref_import import FixedLogitsModel, build_espdnetue, load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+SOURCES = (("camvid", 13), ("cityscapes", 20), ("forest", 5))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = load_reference()
+    yield r
+    torch.autograd.set_detect_anomaly(False)   # the reference loss switches it on globally
+
+
+def _close(a, b, rtol=4e-7, atol=4e-7):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+def test_luts(ref):
+    for name, _ in SOURCES:
+        assert np.array_equal(getattr(ref.greenhouse, "id_%s_to_greenhouse" % name), O.LUTS[name])
+
+
+@pytest.mark.parametrize("policy", [None, "half", "all", 1, 2, 3, "3", 7])
+def test_label_generation_matches_reference(ref, policy):
+    gen = torch.Generator().manual_seed(11)
+    n, h, w = 2, 20, 36
+    mains, auxs = [], []
+    for _, c in SOURCES:
+        m = 3 * torch.randn(n, c, h, w, generator=gen)
+        mains.append(m), auxs.append(m + 1.5 * torch.randn(n, c, h, w, generator=gen))
+    luts = [O.LUTS[s] for s, _ in SOURCES]
+    got, got_ca = O.multi_source_labels(mains, auxs, luts, policy)
+    for i in range(n):
+        per = []
+        for (name, _), m, a in zip(SOURCES, mains, auxs):
+            out, kld = ref.uest.get_output(FixedLogitsModel(m[i:i + 1], a[i:i + 1]), torch.zeros(1), device='cpu')
+            o2, k2 = O.get_output_from_logits(m[i:i + 1], a[i:i + 1])
+            _close(o2, out, atol=0), _close(k2, kld)
+            amax = np.asarray(np.argmax(out.transpose(1, 2, 0), axis=2), dtype=np.uint8)
+            lab_s = getattr(ref.greenhouse, "id_%s_to_greenhouse" % name)[amax]
+            assert np.array_equal(lab_s, O.argmax_to_greenhouse(o2, O.LUTS[name]))
+            assert np.array_equal(ref.uest.transfer_id_to_greenhouse(O.LUTS[name], amax), lab_s)
+            per.append(lab_s)
+        want = ref.uest.merge_outputs(np.array(per), seg_classes=5, thresh=policy)
+        assert want.dtype == np.int64
+        assert np.array_equal(got[i], want)
+        assert np.array_equal(O.merge_outputs(np.array(per), 5, policy), want)
+
+
+def test_loss_matches_reference(ref):
+    gen = torch.Generator().manual_seed(5)
+    b, k, h, w = 3, 5, 12, 20
+    main = 2 * torch.randn(b, k, h, w, generator=gen)
+    aux = main + torch.randn(b, k, h, w, generator=gen)
+    target = torch.randint(0, k, (b, h, w), generator=gen)
+    cw = torch.tensor([0.0, 2.0, 5.0, 1.5, 9.0])
+    crit = ref.seg_loss.UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=4, device='cpu')
+    m, a = main.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+    kld = ref.seg_loss.PixelwiseKLD()(m, a)
+    loss = crit(m + 0.5 * a, target, kld) * 20 + kld.mean()
+    gm, ga = torch.autograd.grad(loss, (m, a))
+    w_o = O.make_class_weights(k, cw.clone(), 4)
+    assert torch.equal(w_o, crit.class_weights)
+    l_o, gm_o, ga_o = O.training_loss_and_grads(main, aux, target, w_o)
+    _close(l_o, loss.detach(), rtol=1e-6), _close(gm_o, gm, rtol=1e-6, atol=1e-10), _close(ga_o, ga, rtol=1e-6, atol=1e-10)
+    # closed-form gradients used by the fused kernel against reference autograd in fp64
+    l64, gm64, ga64 = O.training_loss_and_grads(main, aux, target, w_o, dtype=torch.float64)
+    m64, a64 = main.double().requires_grad_(True), aux.double().requires_grad_(True)
+    crit64 = ref.seg_loss.UncertaintyWeightedSegmentationLoss(k, class_weights=w_o.double(), ignore_idx=4, device='cpu')
+    kld64 = ref.seg_loss.PixelwiseKLD()(m64, a64)
+    loss64 = crit64(m64 + 0.5 * a64, target, kld64) * 20 + kld64.mean()
+    g1, g2 = torch.autograd.grad(loss64, (m64, a64))
+    _close(l64, loss64.detach(), rtol=1e-13, atol=0), _close(gm64, g1, rtol=1e-12, atol=1e-18), _close(ga64, g2, rtol=1e-12, atol=1e-18)
+
+
+def test_config1_full_resolution(ref):
+    """BASELINE config 1 (two of its eight images here to keep the CPU suite short): random-init 20-class
+    ESPDNetUE at 256x480, reference CPU path vs the oracle on the very same logits."""
+    model = build_espdnetue(20, seed=3)
+    gen = torch.Generator().manual_seed(3)
+    lut = ref.greenhouse.id_cityscapes_to_greenhouse
+    with torch.no_grad():
+        for _ in range(2):
+            image = torch.randn(1, 3, 256, 480, generator=gen)
+            main, aux = model(image)
+            out, kld = ref.uest.get_output(model, image, device='cpu')
+            o2, k2 = O.get_output_from_logits(main, aux)
+            _close(o2, out, atol=0), _close(k2, kld)
+            amax = np.asarray(np.argmax(out.transpose(1, 2, 0), axis=2), dtype=np.uint8)
+            want = ref.uest.merge_outputs(np.array([lut[amax]]), seg_classes=5, thresh=None)
+            got, _ = O.multi_source_labels([main], [aux], [O.ID_CITYSCAPES_TO_GREENHOUSE], None)
+            assert np.array_equal(got[0], want)
