@@ -1,0 +1,159 @@
+/*
+ * mspl_b200.h -- C ABI of libmspl_b200.so: the B200 (sm_100a) kernels behind MSPL's multi-source
+ * pseudo-label generation and its uncertainty-weighted loss.
+ *
+ * The reference (ShigemichiMatsuzaki/MSPL) is pure Python and has no FFI/plugin registry; its "API" for
+ * this path is a set of Python callables.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The Python mirror of those callables lives in
+ * mspl_b200/ (uest_seg_multi_os.py, loss_fns/segmentation_loss.py) and binds this library with ctypes.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; every pointer is a DEVICE pointer unless marked HOST.
+ *   - The library never allocates, frees or synchronises: the caller owns all buffers and the stream.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Returns MSPL_OK (0) or a negative mspl_status; never throws, never exits.  mspl_strerror() explains.
+ *   - Logits are fp32, contiguous NCHW: plane (n, c) starts at ((n * C + c) * pixels_per_image) floats.
+ *   - Accumulating outputs (histograms, counters) are ADDED to; the caller zeroes them.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef MSPL_B200_H
+#define MSPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MSPL_API __attribute__((visibility("default")))
+#else
+#define MSPL_API
+#endif
+
+#define MSPL_ABI_VERSION 1
+#define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
+#define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
+#define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14) */
+#define MSPL_RADIX_BINS 2048    /* bins of one radix-select histogram pass (11 bits)                */
+#define MSPL_RADIX_PASSES 3     /* 11 + 11 + 10 bits of the order-preserving fp32 key               */
+
+typedef enum mspl_status {
+    MSPL_OK = 0,
+    MSPL_ERR_BAD_ARG = -1,      /* null pointer, negative size, K/S/C out of range                  */
+    MSPL_ERR_ALIGN = -2,        /* a pointer is not aligned for its element type                    */
+    MSPL_ERR_UNSUPPORTED = -3,  /* valid request this build has no kernel for                       */
+    MSPL_ERR_CUDA = -4,         /* launch failed (cudaPeekAtLastError)                              */
+    MSPL_ERR_WORKSPACE = -5     /* workspace too small                                              */
+} mspl_status;
+
+/* Fusion policy of mspl_fuse_sources. */
+#define MSPL_POLICY_VOTE 0      /* merge_outputs vote with threshold vote_t (reference behaviour)   */
+#define MSPL_POLICY_PROB 1      /* [NEW] argmax of the averaged greenhouse-class probabilities      */
+
+MSPL_API const char* mspl_strerror(int status);
+MSPL_API int mspl_abi_version(void);
+/* Name of the fused kernel variant this build dispatches to (for bench/profiling records). */
+MSPL_API const char* mspl_fuse_variant(void);
+
+/* ---- K0: get_output's device half ---------------------------------------------------------------
+ * Replaces uest_seg_multi_os.py:687-691 (`softmax2d(pred + 0.5*pred_aux)` and `PixelwiseKLD(pred, pred_aux)`).
+ * prob (n, c, pixels) and/or kld (n, pixels) may be NULL to skip that output. */
+MSPL_API int mspl_softmax_kld(const float* main_logits, const float* aux_logits, int64_t n, int c,
+                     int64_t pixels_per_image, float* prob, float* kld, void* stream);
+
+/* ---- K1: fused multi-source pseudo-label generation ---------------------------------------------
+ * Replaces the per-image loop body of generate_pseudo_label_multi_model (uest_seg_multi_os.py:897-921):
+ * get_output (:669-693) -> np.argmax (:904) -> id_*_to_greenhouse gather (:907-912,
+ * data_loader/segmentation/greenhouse.py:15-58) -> merge_outputs (:695-718) -> class_array (:919-921),
+ * plus the KLD the reference computes and discards (:691, loss_fns/segmentation_loss.py:181-189), plus the
+ * [NEW] per-pixel confidence (average over sources of transfer_output_to_greenhouse, :1334-1350) and the
+ * first radix-select histogram pass of the class-balanced thresholds.
+ *
+ *   main_logits/aux_logits  HOST arrays of S device pointers, source s is (num_images, num_classes[s], pixels)
+ *   num_classes, lut        HOST arrays; lut[s] is a HOST table of num_classes[s] bytes with values < K
+ *   policy, vote_t          MSPL_POLICY_VOTE: label = lowest k with the most votes, or `ignore_label` when the
+ *                           winning count < vote_t (vote_t: S//2+1 for 'half', S for 'all');
+ *                           MSPL_POLICY_PROB: label = first argmax_k of F = (sum_s G_s)/S
+ *   label      (num_images*pixels) u8             conf, unc   same shape f32, NULLable
+ *   kld_per_source  HOST array of S device pointers (or NULL; entries may be NULL): per-source KLD maps
+ *   class_hist      K u64, += number of pixels per label (the reference's class_array)
+ *   conf_hist       K*MSPL_RADIX_BINS u64 or NULL, += pass-0 histogram of conf keys per label, restricted to
+ *                   pixels with (pixel_index_in_image % ds_rate) == 0
+ *   marginal_count  u64 or NULL, += pixels where some source's top-2 softmax margin is < 1e-6 (and, for
+ *                   MSPL_POLICY_PROB, the top-2 margin of F): the only pixels whose label may legitimately
+ *                   differ from the reference's argmax-of-softmax */
+MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
+                      const int* num_classes, const uint8_t* const* lut, int64_t num_images,
+                      int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
+                      int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
+                      float* const* kld_per_source, unsigned long long* class_hist,
+                      unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream);
+
+/* ---- merge_outputs on hard labels ----------------------------------------------------------------
+ * Replaces merge_outputs (uest_seg_multi_os.py:695-718; duplicate eval_label.py:76-100).
+ * labels is (num_sources, num_pixels) u8 with values < K. */
+MSPL_API int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,
+                     int vote_t, int ignore_label, uint8_t* merged, void* stream);
+
+/* ---- K2: class-balanced thresholds by radix select ([NEW]; CBST/CRST vestiges at
+ * uest_seg_multi_os.py:88-107, 216-219 -- no reference implementation) --------------------------------
+ * thresh[k] = 1.0 if floor(n_k*portion)==0 else the floor(n_k*portion)-th largest conf among kept pixels
+ * of class k.  Protocol: zero `hist` (K*MSPL_RADIX_BINS u64) and `state`; pass 0 histogram (fused into
+ * mspl_fuse_sources, or mspl_radix_hist_pass(pass=0)); [all-reduce hist over ranks]; mspl_radix_select
+ * (pass=0); then for pass = 1, 2: mspl_radix_hist_pass; [all-reduce]; mspl_radix_select.  After pass 2,
+ * thresh is final.  mspl_radix_select zeroes `hist` for the next pass.  No host synchronisation needed. */
+MSPL_API size_t mspl_radix_state_bytes(int num_target_classes);
+MSPL_API int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int64_t num_pixels,
+                         int64_t pixels_per_image, int num_target_classes, int pass, const void* state,
+                         unsigned long long* hist, int ds_rate, void* stream);
+MSPL_API int mspl_radix_select(unsigned long long* hist, int num_target_classes, int pass, double portion,
+                      void* state, float* thresh, unsigned long long* kept_count, void* stream);
+
+/* ---- K3: thresholding / ignore mask ([NEW]) --------------------------------------------------------
+ * final = label if (label != ignore_label && conf >= thresh[label]) else ignore_label.
+ * ignore_mask (u8, 1 where final == ignore_label) and final_hist (K u64, +=) may be NULL. */
+MSPL_API int mspl_apply_thresholds(const uint8_t* label, const float* conf, const float* thresh,
+                          int64_t num_pixels, int num_target_classes, int ignore_label,
+                          uint8_t* final_label, uint8_t* ignore_mask, unsigned long long* final_hist,
+                          void* stream);
+
+/* ---- K4: fused rectified uncertainty-weighted CE, forward + backward ------------------------------
+ * Replaces the training-loss expression at uest_seg_multi_os.py:1020-1023 (trav_mask_train.py:333-338):
+ *   kld = PixelwiseKLD()(pred, pred_aux); loss = criterion(pred + 0.5*pred_aux, labels, kld) * alpha + kld.mean()
+ * with criterion = UncertaintyWeightedSegmentationLoss (loss_fns/segmentation_loss.py:146-175).
+ *   target         (num_pixels) int64, values in [0,K); anything else contributes like a zero-weight class
+ *   class_weights  K f32 (device)          norm_pixels  the divisor N of the means (global pixel count under DP)
+ *   out3           3 f32: {loss, mean of w*ce*exp(-kld) (un-scaled), mean kld}
+ *   d_main, d_aux  gradients of `loss * grad_scale`, or both NULL for forward only
+ *   workspace      mspl_uw_ce_workspace_bytes() bytes, zeroed once by the caller; left zeroed by each call */
+MSPL_API size_t mspl_uw_ce_workspace_bytes(void);
+MSPL_API int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logits, const int64_t* target,
+                       const float* class_weights, int64_t num_images, int num_classes,
+                       int64_t pixels_per_image, float alpha, double norm_pixels, float grad_scale,
+                       float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* In-place x *= *scale unless *scale == 1 (device scalar); lets autograd apply an upstream gradient
+ * without a host sync. */
+MSPL_API int mspl_scale_inplace(float* x, int64_t count, const float* scale, void* stream);
+
+/* ---- Generic (un-fused) forms behind the reference's two nn.Modules -------------------------------- */
+/* PixelwiseKLD.forward (loss_fns/segmentation_loss.py:181-189) and its vector-Jacobian product. */
+MSPL_API int mspl_kld_fwd(const float* dist1, const float* dist2, int64_t n, int c, int64_t pixels_per_image,
+                 float* kld, void* stream);
+MSPL_API int mspl_kld_bwd(const float* dist1, const float* dist2, const float* grad_kld, int64_t n, int c,
+                 int64_t pixels_per_image, float* grad1, float* grad2, void* stream);
+/* UncertaintyWeightedSegmentationLoss.forward (loss_fns/segmentation_loss.py:155-175) and its backward.
+ * loss is one f32; grad_loss is a device scalar; d_u may be NULL. Workspace as for mspl_uw_ce_fwd_bwd. */
+MSPL_API int mspl_uw_loss_fwd(const float* pred, const int64_t* target, const float* u_weight,
+                     const float* class_weights, int64_t n, int num_classes, int64_t pixels_per_image,
+                     double norm_pixels, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+MSPL_API int mspl_uw_loss_bwd(const float* pred, const int64_t* target, const float* u_weight,
+                     const float* class_weights, const float* grad_loss, int64_t n, int num_classes,
+                     int64_t pixels_per_image, double norm_pixels, float* d_pred, float* d_u, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSPL_B200_H */

@@ -1,0 +1,138 @@
+// Host entry points for K1 (mspl_fuse_sources) and the hard-label vote (mspl_vote_labels).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "fuse_kernel.cuh"
+
+namespace mspl {
+
+#ifndef MSPL_FUSE_CH
+#define MSPL_FUSE_CH 5      // classes per chunk: 13 -> 5+5+3, 20 -> 4x5, 5 -> one exact two-sweep chunk
+#endif
+#ifndef MSPL_FUSE_MINB
+#define MSPL_FUSE_MINB 2    // resident CTAs per SM the register allocator must leave room for
+#endif
+
+template <typename Kern>
+static int launch_fuse(Kern kern, const FuseParams& prm, int P, cudaStream_t stream) {
+    static std::mutex mu;
+    const size_t smem = fuse_smem_bytes(prm.K);
+    int dev = 0, sms = kNumSMs, per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (cudaGetDevice(&dev) != cudaSuccess) return MSPL_ERR_CUDA;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return MSPL_ERR_CUDA;
+        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFuseThreads, smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            return MSPL_ERR_CUDA;
+        }
+    }
+    const int64_t n_groups = prm.n_img * (prm.hw / P);
+    const int64_t n_tiles = (n_groups + kFuseThreads - 1) / kFuseThreads;
+    const int64_t grid = n_tiles < (int64_t)sms * per_sm ? n_tiles : (int64_t)sms * per_sm;   // persistent CTAs
+    kern<<<(unsigned)grid, kFuseThreads, smem, stream>>>(prm);
+    return launch_status();
+}
+
+template <int P, int KT>
+static int dispatch_fuse(const FuseParams& prm, bool gk, cudaStream_t stream) {
+    constexpr int CH = MSPL_FUSE_CH, MB = MSPL_FUSE_MINB;
+    if (gk) return launch_fuse(fuse_sources_kernel<P, CH, KT, true, true, MB>, prm, P, stream);
+    return launch_fuse(fuse_sources_kernel<P, CH, KT, false, true, MB>, prm, P, stream);
+}
+
+// merge_outputs (uest_seg_multi_os.py:695-718) on (S, npix) hard labels.
+__global__ void __launch_bounds__(256) vote_labels_kernel(const uint8_t* __restrict__ labels, int S, int64_t npix, int K,
+                                                          int vote_t, int ignore, uint8_t* __restrict__ merged) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t votes = 0;
+        for (int s = 0; s < S; ++s) {
+            const uint32_t l = labels[s * npix + i];
+            if (l < (uint32_t)K) votes += 1u << (4 * l);   // values outside [0,K) match no class_id, as in the reference
+        }
+        int bk = 0;
+        uint32_t bc = votes & 15u;
+        for (int k = 1; k < K; ++k) {
+            const uint32_t c = (votes >> (4 * k)) & 15u;
+            if (c > bc) { bc = c; bk = k; }
+        }
+        merged[i] = (uint8_t)(((int)bc < vote_t) ? ignore : bk);
+    }
+}
+
+}  // namespace mspl
+
+using namespace mspl;
+
+extern "C" const char* mspl_fuse_variant(void) {
+    static char name[96];
+    snprintf(name, sizeof(name), "direct-ldg128 P=4 CH=%d threads=%d minblocks=%d", MSPL_FUSE_CH, kFuseThreads, MSPL_FUSE_MINB);
+    return name;
+}
+
+extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
+                                 const int* num_classes, const uint8_t* const* lut, int64_t num_images,
+                                 int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
+                                 int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
+                                 float* const* kld_per_source, unsigned long long* class_hist,
+                                 unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream) {
+    const int S = num_sources, K = num_target_classes;
+    if (S < 1 || S > MSPL_MAX_SOURCES || K < 2 || K > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (!main_logits || !aux_logits || !num_classes || !lut || !label || !class_hist) return MSPL_ERR_BAD_ARG;
+    if (num_images < 0 || pixels_per_image < 1 || ds_rate < 1) return MSPL_ERR_BAD_ARG;
+    if (ignore_label < 0 || ignore_label >= K) return MSPL_ERR_BAD_ARG;
+    if (policy != MSPL_POLICY_VOTE && policy != MSPL_POLICY_PROB) return MSPL_ERR_BAD_ARG;
+    if (conf_hist && !conf) return MSPL_ERR_BAD_ARG;
+    if (num_images == 0) return MSPL_OK;
+
+    FuseParams prm;
+    memset(&prm, 0, sizeof(prm));
+    int P = (pixels_per_image % 4 == 0) ? 4 : 1;
+    for (int s = 0; s < S; ++s) {
+        const int C = num_classes[s];
+        if (C < 1 || C > MSPL_MAX_SRC_CLASSES || !main_logits[s] || !aux_logits[s] || !lut[s]) return MSPL_ERR_BAD_ARG;
+        if (!aligned_to(main_logits[s], 4) || !aligned_to(aux_logits[s], 4)) return MSPL_ERR_ALIGN;
+        prm.main[s] = main_logits[s];
+        prm.aux[s] = aux_logits[s];
+        prm.kld[s] = kld_per_source ? kld_per_source[s] : nullptr;
+        prm.C[s] = C;
+        for (int c = 0; c < C; ++c) {
+            if (lut[s][c] >= K) return MSPL_ERR_BAD_ARG;
+            prm.lut[s][c] = lut[s][c];
+        }
+        if (!aligned_to(prm.main[s], 16) || !aligned_to(prm.aux[s], 16) || (prm.kld[s] && !aligned_to(prm.kld[s], 16))) P = 1;
+    }
+    if (!aligned_to(label, 4) || (conf && !aligned_to(conf, 16)) || (unc && !aligned_to(unc, 16))) P = 1;
+    if ((conf && !aligned_to(conf, 4)) || (unc && !aligned_to(unc, 4))) return MSPL_ERR_ALIGN;
+    if (!aligned_to(class_hist, 8) || (conf_hist && !aligned_to(conf_hist, 8)) || (marginal_count && !aligned_to(marginal_count, 8)))
+        return MSPL_ERR_ALIGN;
+
+    prm.S = S; prm.K = K; prm.policy = policy; prm.vote_t = vote_t < 1 ? 1 : vote_t;
+    prm.ignore = ignore_label; prm.ds_rate = ds_rate;
+    prm.n_img = num_images; prm.hw = pixels_per_image;
+    prm.label = label; prm.conf = conf; prm.unc = unc;
+    prm.class_hist = class_hist; prm.conf_hist = conf_hist; prm.marginal = marginal_count;
+
+    // Per-target-class probabilities are only needed when a pixel can win without every source's vote.
+    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (K <= 5) return P == 4 ? dispatch_fuse<4, 5>(prm, gk, st) : dispatch_fuse<1, 5>(prm, gk, st);
+    return P == 4 ? dispatch_fuse<4, 8>(prm, gk, st) : dispatch_fuse<1, 8>(prm, gk, st);
+}
+
+extern "C" int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,
+                                int vote_t, int ignore_label, uint8_t* merged, void* stream) {
+    if (!labels || !merged || num_sources < 1 || num_sources > 15 || num_pixels < 0) return MSPL_ERR_BAD_ARG;
+    if (num_target_classes < 1 || num_target_classes > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (num_pixels == 0) return MSPL_OK;
+    int64_t blocks = (num_pixels + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    vote_labels_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        labels, num_sources, num_pixels, num_target_classes, vote_t, ignore_label, merged);
+    return launch_status();
+}

@@ -1,0 +1,239 @@
+// K2 (class-balanced thresholds by 3-pass radix select over shared-memory histograms) and
+// K3 (threshold / ignore-mask application).  [NEW] stages: the reference only keeps the CBST/CRST flags
+// (uest_seg_multi_os.py:88-107, 216-219); their definition is SURVEY.md section 8 A4'' (restated in DESIGN.md).
+#include "common.cuh"
+
+namespace mspl {
+
+struct RadixState {            // one per target class, caller-zeroed before pass 0
+    unsigned long long rank;   // 1-based rank from the top still to be resolved inside the current prefix
+    unsigned long long count;  // kept pixels of the class (n_k)
+    uint32_t prefix;           // key bits resolved so far
+    uint32_t done;             // 1: threshold already final (floor(n_k*portion) == 0 -> 1.0)
+};
+
+constexpr int kHistThreads = 256;
+
+// Histogram of the `pass`-th digit of the conf keys whose higher bits equal the class's resolved prefix.
+// VEC = 4: uchar4 + float4 loads (5 B/pixel streamed once).
+template <int VEC>
+__global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                                  int64_t npix, int64_t hw, int K, int pass,
+                                                                  const RadixState* __restrict__ state,
+                                                                  unsigned long long* __restrict__ hist, int ds_rate) {
+    extern __shared__ uint32_t s_hist[];
+    __shared__ uint32_t s_prefix[MSPL_MAX_CLASSES];
+    __shared__ uint32_t s_done[MSPL_MAX_CLASSES];
+    const int nbins = K * MSPL_RADIX_BINS;
+    for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
+    if (threadIdx.x < K) {
+        s_prefix[threadIdx.x] = state[threadIdx.x].prefix;
+        s_done[threadIdx.x] = state[threadIdx.x].done;
+    }
+    __syncthreads();
+    const int64_t n_groups = (npix + VEC - 1) / VEC;
+    for (int64_t g = blockIdx.x * (int64_t)kHistThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kHistThreads) {
+        const int64_t i0 = g * VEC;
+        uint8_t l[VEC];
+        float c[VEC];
+        if (VEC == 4) {
+            const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
+            const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
+            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+            c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
+        } else {
+            l[0] = label[i0];
+            c[0] = conf[i0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int64_t i = i0 + v;
+            if (l[v] >= K || s_done[l[v]]) continue;
+            if (ds_rate > 1 && ((i % hw) % ds_rate) != 0) continue;
+            const uint32_t key = float_to_key(c[v]);
+            if (radix_prefix(key, pass) != s_prefix[l[v]]) continue;
+            atomicAdd(&s_hist[l[v] * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += kHistThreads)
+        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+}
+
+// One CTA per class: locate the bin holding the rank-th largest key, extend the prefix, zero the histogram row.
+__global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* __restrict__ hist, int pass, double portion,
+                                                           RadixState* __restrict__ state, float* __restrict__ thresh,
+                                                           unsigned long long* __restrict__ kept_count) {
+    const int k = blockIdx.x;
+    unsigned long long* h = hist + (size_t)k * MSPL_RADIX_BINS;
+    const int nb = pass == 2 ? 1024 : MSPL_RADIX_BINS;
+    const int bits = pass == 2 ? 10 : 11;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = nb / 32;
+        unsigned long long mine = 0;
+        for (int i = 0; i < per; ++i) mine += h[lane * per + i];
+        // above = sum over lanes > lane (suffix sum); total = sum over all lanes
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += t;
+        }
+        const unsigned long long above = incl - mine;
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 0);
+        RadixState st = state[k];
+        if (pass == 0) {
+            st.count = total;
+            unsigned long long j = (unsigned long long)((double)total * portion);   // floor(n_k * p), as int(n*p)
+            if (j > total) j = total;
+            st.rank = j;
+            st.prefix = 0;
+            st.done = (j == 0);
+            if (lane == 0) {
+                if (st.done) thresh[k] = 1.0f;
+                if (kept_count) kept_count[k] = total;
+            }
+        }
+        if (!st.done) {
+            if (above < st.rank && st.rank <= above + mine) {       // exactly one lane
+                unsigned long long acc = above;
+                int d = lane * per + per - 1;
+                for (; d > lane * per; --d) {
+                    if (acc + h[d] >= st.rank) break;
+                    acc += h[d];
+                }
+                st.rank -= acc;
+                st.prefix = (st.prefix << bits) | (uint32_t)d;
+                state[k] = st;
+                if (pass == 2) thresh[k] = key_to_float(st.prefix);
+            }
+        } else if (lane == 0) {
+            state[k] = st;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSPL_RADIX_BINS; i += blockDim.x) h[i] = 0;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                               const float* __restrict__ thresh, int64_t npix, int K, int ignore,
+                                                               uint8_t* __restrict__ final_label, uint8_t* __restrict__ ignore_mask,
+                                                               unsigned long long* __restrict__ final_hist) {
+    __shared__ float s_thresh[MSPL_MAX_CLASSES];
+    __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
+    if (threadIdx.x < MSPL_MAX_CLASSES) {
+        s_thresh[threadIdx.x] = threadIdx.x < K ? thresh[threadIdx.x] : INFINITY;
+        s_cls[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    uint32_t cnt[MSPL_MAX_CLASSES] = {};
+    const int64_t n_groups = (npix + VEC - 1) / VEC;
+    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = g * VEC;
+        uint8_t l[VEC], f[VEC], mk[VEC];
+        float c[VEC];
+        if (VEC == 4) {
+            const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
+            const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
+            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+            c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
+        } else {
+            l[0] = label[i0];
+            c[0] = conf[i0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const bool keep = l[v] < K && l[v] != ignore && c[v] >= s_thresh[l[v]];
+            f[v] = keep ? l[v] : (uint8_t)ignore;
+            mk[v] = keep ? 0 : 1;
+#pragma unroll
+            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (f[v] == k);
+        }
+        if (VEC == 4) {
+            *reinterpret_cast<uchar4*>(final_label + i0) = make_uchar4(f[0], f[1], f[2], f[3]);
+            if (ignore_mask) *reinterpret_cast<uchar4*>(ignore_mask + i0) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
+        } else {
+            final_label[i0] = f[0];
+            if (ignore_mask) ignore_mask[i0] = mk[0];
+        }
+    }
+    if (final_hist) {
+#pragma unroll
+        for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
+            const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[k]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cls[k], w);
+        }
+        __syncthreads();
+        if (threadIdx.x < K && s_cls[threadIdx.x]) atomicAdd(final_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+    }
+}
+
+static int64_t stream_grid(int64_t n_groups, int threads, int per_sm) {
+    int64_t blocks = (n_groups + threads - 1) / threads;
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
+}
+
+}  // namespace mspl
+
+using namespace mspl;
+
+extern "C" size_t mspl_radix_state_bytes(int num_target_classes) {
+    return num_target_classes < 1 ? 0 : sizeof(RadixState) * (size_t)num_target_classes;
+}
+
+extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int64_t num_pixels, int64_t pixels_per_image,
+                                    int num_target_classes, int pass, const void* state, unsigned long long* hist,
+                                    int ds_rate, void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !state || !hist || num_pixels < 0 || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES || ds_rate < 1) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(conf, 4) || !aligned_to(hist, 8) || !aligned_to(state, 8)) return MSPL_ERR_ALIGN;
+    if (num_pixels == 0) return MSPL_OK;
+    const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (num_pixels % 4 == 0) && aligned_to(label, 4) && aligned_to(conf, 16);
+    auto kern = vec ? radix_hist_kernel<4> : radix_hist_kernel<1>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
+    const int64_t grid = stream_grid((num_pixels + (vec ? 3 : 0)) / (vec ? 4 : 1), kHistThreads, 4);
+    kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K, pass,
+                                                     static_cast<const RadixState*>(state), hist, ds_rate);
+    return launch_status();
+}
+
+extern "C" int mspl_radix_select(unsigned long long* hist, int num_target_classes, int pass, double portion, void* state,
+                                 float* thresh, unsigned long long* kept_count, void* stream) {
+    const int K = num_target_classes;
+    if (!hist || !state || !thresh || K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES) return MSPL_ERR_BAD_ARG;
+    if (!(portion >= 0.0)) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
+    radix_select_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, pass, portion, static_cast<RadixState*>(state),
+                                                                          thresh, kept_count);
+    return launch_status();
+}
+
+extern "C" int mspl_apply_thresholds(const uint8_t* label, const float* conf, const float* thresh, int64_t num_pixels,
+                                     int num_target_classes, int ignore_label, uint8_t* final_label, uint8_t* ignore_mask,
+                                     unsigned long long* final_hist, void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !thresh || !final_label || num_pixels < 0) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ignore_label < 0 || ignore_label > 255) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(conf, 4) || !aligned_to(thresh, 4) || (final_hist && !aligned_to(final_hist, 8))) return MSPL_ERR_ALIGN;
+    if (num_pixels == 0) return MSPL_OK;
+    const bool vec = (num_pixels % 4 == 0) && aligned_to(label, 4) && aligned_to(conf, 16) && aligned_to(final_label, 4) &&
+                     (!ignore_mask || aligned_to(ignore_mask, 4));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t grid = stream_grid(vec ? num_pixels / 4 : num_pixels, 256, 8);
+    if (vec)
+        apply_thresholds_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
+                                                                  ignore_mask, final_hist);
+    else
+        apply_thresholds_kernel<1><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
+                                                                  ignore_mask, final_hist);
+    return launch_status();
+}

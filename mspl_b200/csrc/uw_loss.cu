@@ -1,0 +1,451 @@
+// K4 (fused rectified uncertainty-weighted CE forward+backward), K0 (get_output's softmax + KLD maps) and the
+// generic forms behind the reference's two nn.Modules (PixelwiseKLD, UncertaintyWeightedSegmentationLoss).
+//
+// Closed forms (verified against reference autograd in fp64, tests/test_oracle_vs_reference.py):
+//   per pixel  z = m + a/2, q = softmax(z), p1 = softmax(m), p2 = softmax(a), D = sum_k p1_k (log p1_k - log p2_k),
+//              ce = w_t * (-log q_t),  N = number of pixels in the mean
+//   L        = (alpha/N) sum ce e^{-D} + (1/N) sum D                       uest_seg_multi_os.py:1020-1023
+//   dL/dz_k  = (alpha/N) e^{-D} w_t (q_k - [k==t])
+//   g_D      = (1 - alpha ce e^{-D}) / N
+//   dL/dm_k  = dL/dz_k + g_D p1_k (log p1_k - log p2_k - D)
+//   dL/da_k  = dL/dz_k / 2 + g_D (p2_k - p1_k)
+#include "pixel_math.cuh"
+
+namespace mspl {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxLossBlocks = 2048;
+
+struct LossWorkspace {            // caller-zeroed once; every launch leaves `ticket` at 0 again
+    unsigned int ticket;
+    unsigned int pad[3];
+    double partial[kMaxLossBlocks][2];
+};
+
+// Deterministic two-value reduction: per-thread doubles -> warp shuffle -> block -> per-block slot; the last block
+// to finish adds the slots in index order and writes the means.  No floating-point atomics anywhere.
+template <int NOUT>
+MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv_n, float alpha, float* out) {
+    __shared__ double s_part[kLossThreads / 32][2];
+    __shared__ bool s_last;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5][0] = s0; s_part[threadIdx.x >> 5][1] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < kLossThreads / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+        ws->partial[blockIdx.x][0] = a;
+        ws->partial[blockIdx.x][1] = b;
+        __threadfence();
+        s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kLossThreads) {   // fixed assignment -> fixed order
+        a += __ldcg(&ws->partial[i][0]);
+        b += __ldcg(&ws->partial[i][1]);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5][0] = a; s_part[threadIdx.x >> 5][1] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = 0;
+        for (int w = 0; w < kLossThreads / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+        const double ce_mean = a * inv_n, kld_mean = b * inv_n;
+        if (NOUT == 3) {
+            out[0] = (float)((double)alpha * ce_mean + kld_mean);
+            out[1] = (float)ce_mean;
+            out[2] = (float)kld_mean;
+        } else {
+            out[0] = (float)ce_mean;
+        }
+        ws->ticket = 0;
+    }
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------------
+template <int P, int K, bool BWD>
+__global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l,
+                                                                   const int64_t* __restrict__ target, const float* __restrict__ cw,
+                                                                   int64_t n_img, int64_t hw, float alpha, double inv_n, float gscale,
+                                                                   float* __restrict__ out3, float* __restrict__ d_main,
+                                                                   float* __restrict__ d_aux, LossWorkspace* ws) {
+    __shared__ float s_w[K];
+    if (threadIdx.x < K) s_w[threadIdx.x] = cw[threadIdx.x];
+    __syncthreads();
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    const float inv_nf = (float)inv_n;
+    double acc_ce = 0, acc_d = 0;
+    for (int64_t g = blockIdx.x * (int64_t)kLossThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kLossThreads) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const int64_t base = n * K * hw + off;
+        float m[K][P], a[K][P];
+        long long t[P];
+#pragma unroll
+        for (int k = 0; k < K; ++k) PixVec<P>::load(main_l + base + k * hw, m[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) PixVec<P>::load(aux_l + base + k * hw, a[k]);
+        if (P == 4) {
+            const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off));
+            const longlong2 t1 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off) + 1);
+            t[0] = t0.x; t[1] = t0.y; t[P > 2 ? 2 : 0] = t1.x; t[P > 3 ? 3 : 0] = t1.y;
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) t[p] = __ldcs(target + n * hw + off + p);
+        }
+        float gm[K][P], ga[K][P];
+        float ce_sum = 0.f, d_sum = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float z[K], Mm = -INFINITY, Ma = -INFINITY, Mz = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                z[k] = fmaf(0.5f, a[k][p], m[k][p]);
+                Mm = fmaxf(Mm, m[k][p]); Ma = fmaxf(Ma, a[k][p]); Mz = fmaxf(Mz, z[k]);
+            }
+            float em[K], ea[K], ez[K], Sm = 0.f, Sa = 0.f, Sz = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                em[k] = exp_neg(m[k][p] - Mm); ea[k] = exp_neg(a[k][p] - Ma); ez[k] = exp_neg(z[k] - Mz);
+                Sm += em[k]; Sa += ea[k]; Sz += ez[k];
+            }
+            const float lSm = logf(Sm), lSa = logf(Sa), lSz = logf(Sz);
+            const float rSm = 1.0f / Sm, rSa = 1.0f / Sa, rSz = 1.0f / Sz;
+            float dl[K], D = 0.f;                    // dl_k = log p1_k - log p2_k
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                dl[k] = ((m[k][p] - Mm) - lSm) - ((a[k][p] - Ma) - lSa);
+                D = fmaf(em[k] * rSm, dl[k], D);
+            }
+            const int ti = (int)t[p];
+            const bool valid = t[p] >= 0 && t[p] < K;
+            float wt = 0.f, zt = Mz;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                wt = (valid && ti == k) ? s_w[k] : wt;
+                zt = (valid && ti == k) ? z[k] : zt;
+            }
+            const float ce = wt * (lSz - (zt - Mz));
+            const float eD = expf(-D);
+            const float l = ce * eD;
+            ce_sum += l;
+            d_sum += D;
+            if (BWD) {
+                const float coef = gscale * alpha * inv_nf * eD * wt;
+                const float gD = gscale * inv_nf * (1.0f - alpha * l);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float p1 = em[k] * rSm, p2 = ea[k] * rSa, q = ez[k] * rSz;
+                    const float dz = coef * (q - ((valid && ti == k) ? 1.0f : 0.0f));
+                    gm[k][p] = fmaf(gD, p1 * (dl[k] - D), dz);
+                    ga[k][p] = fmaf(gD, p2 - p1, 0.5f * dz);
+                }
+            }
+        }
+        acc_ce += (double)ce_sum;
+        acc_d += (double)d_sum;
+        if (BWD) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) PixVec<P>::store(d_main + base + k * hw, gm[k]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) PixVec<P>::store(d_aux + base + k * hw, ga[k]);
+        }
+    }
+    finish_loss<3>(acc_ce, acc_d, ws, inv_n, alpha, out3);
+}
+
+// ---- generic runtime-C helpers (compat paths; logits are re-read from L1/L2, HBM sees them once) -------------
+// softmax statistics of one logit vector per pixel: M = max, S = sum e^{x-M}
+template <int P>
+MSPL_DEVINL void stats1(const float* __restrict__ px, int C, int64_t hw, float (&M)[P], float (&S)[P]) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) { M[p] = -INFINITY; S[p] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+        float v[P];
+        PixVec<P>::load(px + c * hw, v);
+#pragma unroll
+        for (int p = 0; p < P; ++p) M[p] = fmaxf(M[p], v[p]);
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[P];
+        PixVec<P>::load(px + c * hw, v);
+#pragma unroll
+        for (int p = 0; p < P; ++p) S[p] += exp_neg(v[p] - M[p]);
+    }
+}
+
+// D = KL(softmax(x1) || softmax(x2)) with the pieces the backward needs.
+template <int P>
+struct KldStats { float M1[P], S1[P], M2[P], S2[P], D[P]; };
+
+template <int P>
+MSPL_DEVINL void kld_stats(const float* __restrict__ p1, const float* __restrict__ p2, int C, int64_t hw, KldStats<P>& k) {
+    stats1<P>(p1, C, hw, k.M1, k.S1);
+    stats1<P>(p2, C, hw, k.M2, k.S2);
+    float l1[P], l2[P], r1[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { l1[p] = logf(k.S1[p]); l2[p] = logf(k.S2[p]); r1[p] = 1.0f / k.S1[p]; k.D[p] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+        float x[P], y[P];
+        PixVec<P>::load(p1 + c * hw, x);
+        PixVec<P>::load(p2 + c * hw, y);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float t1 = x[p] - k.M1[p];
+            k.D[p] = fmaf(exp_neg(t1) * r1[p], (t1 - l1[p]) - ((y[p] - k.M2[p]) - l2[p]), k.D[p]);
+        }
+    }
+}
+
+// K0: prob = softmax(main + aux/2), kld = KL(softmax(main)||softmax(aux))        uest_seg_multi_os.py:687-691
+template <int P>
+__global__ void __launch_bounds__(256) softmax_kld_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l, int64_t n_img,
+                                                          int C, int64_t hw, float* __restrict__ prob, float* __restrict__ kld) {
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const float* pm = main_l + n * C * hw + off;
+        const float* pa = aux_l + n * C * hw + off;
+        if (kld) {
+            KldStats<P> ks;
+            kld_stats<P>(pm, pa, C, hw, ks);
+            PixVec<P>::store(kld + n * hw + off, ks.D);
+        }
+        if (prob) {
+            float M[P], S[P], r[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) { M[p] = -INFINITY; S[p] = 0.f; }
+            for (int c = 0; c < C; ++c) {
+                float x[P], y[P];
+                PixVec<P>::load(pm + c * hw, x);
+                PixVec<P>::load(pa + c * hw, y);
+#pragma unroll
+                for (int p = 0; p < P; ++p) M[p] = fmaxf(M[p], fmaf(0.5f, y[p], x[p]));
+            }
+            for (int c = 0; c < C; ++c) {
+                float x[P], y[P];
+                PixVec<P>::load(pm + c * hw, x);
+                PixVec<P>::load(pa + c * hw, y);
+#pragma unroll
+                for (int p = 0; p < P; ++p) S[p] += exp_neg(fmaf(0.5f, y[p], x[p]) - M[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) r[p] = 1.0f / S[p];
+            for (int c = 0; c < C; ++c) {
+                float x[P], y[P], o[P];
+                PixVec<P>::load(pm + c * hw, x);
+                PixVec<P>::load(pa + c * hw, y);
+#pragma unroll
+                for (int p = 0; p < P; ++p) o[p] = exp_neg(fmaf(0.5f, y[p], x[p]) - M[p]) * r[p];
+                PixVec<P>::store(prob + n * C * hw + off + c * hw, o);
+            }
+        }
+    }
+}
+
+// PixelwiseKLD backward: g1_c = g p1_c (log p1_c - log p2_c - D), g2_c = g (p2_c - p1_c)
+template <int P>
+__global__ void __launch_bounds__(256) kld_bwd_kernel(const float* __restrict__ d1, const float* __restrict__ d2, const float* __restrict__ gk,
+                                                      int64_t n_img, int C, int64_t hw, float* __restrict__ g1, float* __restrict__ g2) {
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const int64_t base = n * C * hw + off;
+        KldStats<P> ks;
+        kld_stats<P>(d1 + base, d2 + base, C, hw, ks);
+        float up[P], l1[P], l2[P], r1[P], r2[P];
+        PixVec<P>::load(gk + n * hw + off, up);
+#pragma unroll
+        for (int p = 0; p < P; ++p) { l1[p] = logf(ks.S1[p]); l2[p] = logf(ks.S2[p]); r1[p] = 1.0f / ks.S1[p]; r2[p] = 1.0f / ks.S2[p]; }
+        for (int c = 0; c < C; ++c) {
+            float x[P], y[P], o1[P], o2[P];
+            PixVec<P>::load(d1 + base + c * hw, x);
+            PixVec<P>::load(d2 + base + c * hw, y);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float t1 = x[p] - ks.M1[p], t2 = y[p] - ks.M2[p];
+                const float p1 = exp_neg(t1) * r1[p], p2 = exp_neg(t2) * r2[p];
+                o1[p] = up[p] * p1 * ((t1 - l1[p]) - (t2 - l2[p]) - ks.D[p]);
+                o2[p] = up[p] * (p2 - p1);
+            }
+            PixVec<P>::store(g1 + base + c * hw, o1);
+            PixVec<P>::store(g2 + base + c * hw, o2);
+        }
+    }
+}
+
+// UncertaintyWeightedSegmentationLoss forward / backward (loss_fns/segmentation_loss.py:155-175)
+template <int P, bool BWD>
+__global__ void __launch_bounds__(kLossThreads) uw_loss_kernel(const float* __restrict__ pred, const int64_t* __restrict__ target,
+                                                               const float* __restrict__ u, const float* __restrict__ cw,
+                                                               const float* __restrict__ grad_loss, int64_t n_img, int C, int64_t hw,
+                                                               double inv_n, float* __restrict__ loss, float* __restrict__ d_pred,
+                                                               float* __restrict__ d_u, LossWorkspace* ws) {
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    const float inv_nf = (float)inv_n;
+    const float up = BWD ? grad_loss[0] : 0.f;
+    double acc = 0;
+    for (int64_t g = blockIdx.x * (int64_t)kLossThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kLossThreads) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const float* pp = pred + n * C * hw + off;
+        float M[P], S[P], uu[P], wt[P], l[P], eu[P], r[P];
+        int ti[P];
+        stats1<P>(pp, C, hw, M, S);
+        PixVec<P>::load(u + n * hw + off, uu);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const long long t = target[n * hw + off + p];
+            const bool valid = t >= 0 && t < C;
+            ti[p] = valid ? (int)t : -1;
+            wt[p] = valid ? __ldg(cw + t) : 0.f;
+            const float xt = valid ? __ldg(pp + t * hw + p) : M[p];
+            eu[p] = expf(-uu[p]);
+            l[p] = wt[p] * (logf(S[p]) - (xt - M[p])) * eu[p];
+            r[p] = 1.0f / S[p];
+            acc += (double)l[p];
+        }
+        if (BWD) {
+            for (int c = 0; c < C; ++c) {
+                float x[P], o[P];
+                PixVec<P>::load(pp + c * hw, x);
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    o[p] = up * inv_nf * eu[p] * wt[p] * (exp_neg(x[p] - M[p]) * r[p] - (ti[p] == c ? 1.0f : 0.0f));
+                PixVec<P>::store(d_pred + n * C * hw + off + c * hw, o);
+            }
+            if (d_u) {
+                float o[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p) o[p] = -up * inv_nf * l[p];
+                PixVec<P>::store(d_u + n * hw + off, o);
+            }
+        }
+    }
+    if (!BWD) finish_loss<1>(acc, 0.0, ws, inv_n, 1.0f, loss);
+}
+
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ x, int64_t count, const float* __restrict__ scale) {
+    const float s = scale[0];
+    if (s == 1.0f) return;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) x[i] *= s;
+}
+
+static int64_t persistent_grid(int64_t n_groups, int threads, int per_sm, int64_t cap) {
+    int64_t blocks = (n_groups + threads - 1) / threads;
+    const int64_t lim = (int64_t)kNumSMs * per_sm < cap ? (int64_t)kNumSMs * per_sm : cap;
+    return blocks < 1 ? 1 : (blocks < lim ? blocks : lim);
+}
+
+template <int K>
+static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, int64_t hw,
+                        float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
+    const int64_t grid = persistent_grid(n * (hw / P), kLossThreads, 4, kMaxLossBlocks);
+#define MSPL_UWCE(PP, BB) uw_ce_fused_kernel<PP, K, BB><<<(unsigned)grid, kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws)
+    if (P == 4) { if (bwd) MSPL_UWCE(4, true); else MSPL_UWCE(4, false); }
+    else        { if (bwd) MSPL_UWCE(1, true); else MSPL_UWCE(1, false); }
+#undef MSPL_UWCE
+    return launch_status();
+}
+
+}  // namespace mspl
+
+using namespace mspl;
+
+extern "C" size_t mspl_uw_ce_workspace_bytes(void) { return sizeof(LossWorkspace); }
+
+extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logits, const int64_t* target, const float* class_weights,
+                                  int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
+                                  float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    if (!main_logits || !aux_logits || !target || !class_weights || !out3 || !workspace) return MSPL_ERR_BAD_ARG;
+    if ((d_main == nullptr) != (d_aux == nullptr)) return MSPL_ERR_BAD_ARG;
+    if (num_images < 1 || pixels_per_image < 1 || num_classes < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
+    if (workspace_bytes < sizeof(LossWorkspace)) return MSPL_ERR_WORKSPACE;
+    if (num_classes > MSPL_MAX_CLASSES) return MSPL_ERR_UNSUPPORTED;
+    if (!aligned_to(main_logits, 4) || !aligned_to(aux_logits, 4) || !aligned_to(target, 8) || !aligned_to(workspace, 8)) return MSPL_ERR_ALIGN;
+    const bool bwd = d_main != nullptr;
+    int P = pick_vec(pixels_per_image, {main_logits, aux_logits, d_main, d_aux}) == 4 && aligned_to(target, 16) ? 4 : 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
+    const double inv_n = 1.0 / norm_pixels;
+#define MSPL_CASE(KK) case KK: return launch_uw_ce<KK>(P, bwd, main_logits, aux_logits, target, class_weights, num_images, pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws, st)
+    switch (num_classes) {
+        MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
+    }
+#undef MSPL_CASE
+    return MSPL_ERR_UNSUPPORTED;
+}
+
+extern "C" int mspl_scale_inplace(float* x, int64_t count, const float* scale, void* stream) {
+    if (!x || !scale || count < 0) return MSPL_ERR_BAD_ARG;
+    if (count == 0) return MSPL_OK;
+    const int64_t grid = persistent_grid(count, 256, 8, 1 << 20);
+    scale_inplace_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, count, scale);
+    return launch_status();
+}
+
+static bool bad_planes(const void* a, const void* b, int64_t n, int c, int64_t hw) {
+    return !a || !b || n < 0 || c < 1 || hw < 1;
+}
+
+extern "C" int mspl_softmax_kld(const float* main_logits, const float* aux_logits, int64_t n, int c, int64_t pixels_per_image,
+                                float* prob, float* kld, void* stream) {
+    if (bad_planes(main_logits, aux_logits, n, c, pixels_per_image) || (!prob && !kld)) return MSPL_ERR_BAD_ARG;
+    if (n == 0) return MSPL_OK;
+    const int P = pick_vec(pixels_per_image, {main_logits, aux_logits, prob, kld}) == 4 ? 4 : 1;
+    const int64_t grid = persistent_grid(n * (pixels_per_image / P), 256, 8, 1 << 20);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 4) softmax_kld_kernel<4><<<(unsigned)grid, 256, 0, st>>>(main_logits, aux_logits, n, c, pixels_per_image, prob, kld);
+    else softmax_kld_kernel<1><<<(unsigned)grid, 256, 0, st>>>(main_logits, aux_logits, n, c, pixels_per_image, prob, kld);
+    return launch_status();
+}
+
+extern "C" int mspl_kld_fwd(const float* dist1, const float* dist2, int64_t n, int c, int64_t pixels_per_image, float* kld, void* stream) {
+    if (!kld) return MSPL_ERR_BAD_ARG;
+    return mspl_softmax_kld(dist1, dist2, n, c, pixels_per_image, nullptr, kld, stream);
+}
+
+extern "C" int mspl_kld_bwd(const float* dist1, const float* dist2, const float* grad_kld, int64_t n, int c, int64_t pixels_per_image,
+                            float* grad1, float* grad2, void* stream) {
+    if (bad_planes(dist1, dist2, n, c, pixels_per_image) || !grad_kld || !grad1 || !grad2) return MSPL_ERR_BAD_ARG;
+    if (n == 0) return MSPL_OK;
+    const int P = pick_vec(pixels_per_image, {dist1, dist2, grad_kld, grad1, grad2}) == 4 ? 4 : 1;
+    const int64_t grid = persistent_grid(n * (pixels_per_image / P), 256, 8, 1 << 20);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 4) kld_bwd_kernel<4><<<(unsigned)grid, 256, 0, st>>>(dist1, dist2, grad_kld, n, c, pixels_per_image, grad1, grad2);
+    else kld_bwd_kernel<1><<<(unsigned)grid, 256, 0, st>>>(dist1, dist2, grad_kld, n, c, pixels_per_image, grad1, grad2);
+    return launch_status();
+}
+
+extern "C" int mspl_uw_loss_fwd(const float* pred, const int64_t* target, const float* u_weight, const float* class_weights, int64_t n,
+                                int num_classes, int64_t pixels_per_image, double norm_pixels, float* loss, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    if (!pred || !target || !u_weight || !class_weights || !loss || !workspace) return MSPL_ERR_BAD_ARG;
+    if (n < 1 || num_classes < 1 || pixels_per_image < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
+    if (workspace_bytes < sizeof(LossWorkspace)) return MSPL_ERR_WORKSPACE;
+    const int P = pick_vec(pixels_per_image, {pred, u_weight}) == 4 ? 4 : 1;
+    const int64_t grid = persistent_grid(n * (pixels_per_image / P), kLossThreads, 4, kMaxLossBlocks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
+    if (P == 4) uw_loss_kernel<4, false><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, nullptr, n, num_classes, pixels_per_image, 1.0 / norm_pixels, loss, nullptr, nullptr, ws);
+    else uw_loss_kernel<1, false><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, nullptr, n, num_classes, pixels_per_image, 1.0 / norm_pixels, loss, nullptr, nullptr, ws);
+    return launch_status();
+}
+
+extern "C" int mspl_uw_loss_bwd(const float* pred, const int64_t* target, const float* u_weight, const float* class_weights,
+                                const float* grad_loss, int64_t n, int num_classes, int64_t pixels_per_image, double norm_pixels,
+                                float* d_pred, float* d_u, void* stream) {
+    if (!pred || !target || !u_weight || !class_weights || !grad_loss || !d_pred) return MSPL_ERR_BAD_ARG;
+    if (n < 1 || num_classes < 1 || pixels_per_image < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
+    const int P = pick_vec(pixels_per_image, {pred, u_weight, d_pred, d_u}) == 4 ? 4 : 1;
+    const int64_t grid = persistent_grid(n * (pixels_per_image / P), kLossThreads, 4, 1 << 20);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 4) uw_loss_kernel<4, true><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, grad_loss, n, num_classes, pixels_per_image, 1.0 / norm_pixels, nullptr, d_pred, d_u, nullptr);
+    else uw_loss_kernel<1, true><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, grad_loss, n, num_classes, pixels_per_image, 1.0 / norm_pixels, nullptr, d_pred, d_u, nullptr);
+    return launch_status();
+}

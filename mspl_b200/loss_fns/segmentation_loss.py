@@ -1,0 +1,69 @@
+"""Drop-in replacements for the two hot-path modules of the reference's loss_fns/segmentation_loss.py, backed by
+the CUDA kernels in libmspl_b200.so (same constructor arguments, same forward signature, same values and
+gradients; CUDA tensors only)."""
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class PixelwiseKLD(nn.Module):
+    """loss_fns/segmentation_loss.py:177-189: per-pixel KL(softmax(dist1) || softmax(dist2)), (B,C,H,W)x2 -> (B,H,W),
+    differentiable w.r.t. both inputs."""
+
+    def __init__(self):
+        super(PixelwiseKLD, self).__init__()
+
+    def forward(self, dist1, dist2):
+        return ops.pixelwise_kld(dist1.contiguous(), dist2.contiguous())
+
+
+class UncertaintyWeightedSegmentationLoss(nn.Module):
+    """loss_fns/segmentation_loss.py:146-175.
+
+    Keeps the reference's construction quirk: the tensor passed as ``class_weights`` is stored as is and its
+    ``ignore_idx`` entry is zeroed IN PLACE (callers reuse that tensor afterwards, uest_seg_multi_os.py:505-513).
+    ``forward`` returns the mean over ALL B*H*W pixels of ``w[t] * (-log_softmax(pred)[t]) * exp(-u_weight)``.
+    Unlike the reference it does not switch autograd anomaly mode on (a global, sticky debug switch at :156).
+    """
+
+    def __init__(self, num_classes, class_weights=None, ignore_idx=None, device='cuda'):
+        super(UncertaintyWeightedSegmentationLoss, self).__init__()
+        self.num_classes = num_classes
+        self.class_weights = class_weights if class_weights is not None else torch.ones(self.num_classes).to(device)
+        self.ignore_idx = ignore_idx
+        if self.ignore_idx is not None:
+            self.class_weights[self.ignore_idx] = 0.0
+
+    def forward(self, pred, target, u_weight, epsilon=1e-12):   # epsilon: accepted and unused, as in the reference
+        cw = self.class_weights
+        if cw.dtype != torch.float32 or cw.device != pred.device:
+            cw = cw.to(device=pred.device, dtype=torch.float32)
+        return ops.uw_segmentation_loss(pred.contiguous(), target.contiguous(), u_weight, cw.contiguous())
+
+
+class FusedUncertaintyWeightedLoss(nn.Module):
+    """[NEW] one-launch form of the training loss expression at uest_seg_multi_os.py:1020-1023:
+
+        kld  = PixelwiseKLD()(pred, pred_aux)
+        loss = criterion(pred + 0.5*pred_aux, labels, kld) * alpha + kld.mean()
+
+    ``forward(pred, pred_aux, labels)`` returns that loss; ``last_parts`` holds [loss, mean weighted CE, mean KLD]
+    (the reference logs ``kld.mean()`` separately at :1021)."""
+
+    def __init__(self, num_classes, class_weights=None, ignore_idx=None, device='cuda', alpha=20.0):
+        super(FusedUncertaintyWeightedLoss, self).__init__()
+        self.num_classes = num_classes
+        self.class_weights = class_weights if class_weights is not None else torch.ones(self.num_classes).to(device)
+        self.ignore_idx = ignore_idx
+        self.alpha = alpha
+        self.last_parts = None
+        if self.ignore_idx is not None:
+            self.class_weights[self.ignore_idx] = 0.0
+
+    def forward(self, pred, pred_aux, labels, norm_pixels=None):
+        cw = self.class_weights.to(device=pred.device, dtype=torch.float32).contiguous()
+        loss, parts = ops.uw_ce_loss(pred.contiguous(), pred_aux.contiguous(), labels.contiguous(), cw, self.alpha,
+                                     norm_pixels, return_parts=True)
+        self.last_parts = parts
+        return loss

@@ -1,0 +1,375 @@
+"""Tensor-in / tensor-out entry points over libmspl_b200.so (no NumPy, no host sync, no CPU fallback).
+
+These are the batched fast paths behind the reference-named callables in ``mspl_b200.uest_seg_multi_os`` and
+``mspl_b200.loss_fns.segmentation_loss``.  Every function enqueues on the current CUDA stream of the tensors'
+device and returns device tensors.
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+RADIX_BINS = 2048
+RADIX_PASSES = 3
+MAX_SOURCES = 8
+MAX_CLASSES = 8
+POLICY_VOTE, POLICY_PROB = 0, 1
+
+FuseResult = namedtuple("FuseResult", "label conf unc kld class_hist conf_hist marginal")
+
+
+def _require_cuda(t, name, dtype=None, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (mspl_b200 has no CPU path), got device %s" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def vote_threshold(num_sources, thresh=None):
+    """merge_outputs' threshold rule (uest_seg_multi_os.py:697-705): None/'half'/invalid -> S//2+1,
+    'all' -> S, an int <= S -> itself."""
+    if thresh is None or (isinstance(thresh, str) and thresh == 'half'):
+        return num_sources // 2 + 1
+    if isinstance(thresh, str) and thresh == 'all':
+        return num_sources
+    if isinstance(thresh, int) and not isinstance(thresh, bool) and thresh <= num_sources:
+        return thresh
+    return num_sources // 2 + 1
+
+
+def _lut_bytes(lut, num_src_classes, num_classes):
+    arr = np.asarray(lut.cpu() if isinstance(lut, torch.Tensor) else lut).astype(np.int64).reshape(-1)
+    if arr.size != num_src_classes:
+        raise ValueError("label table has %d entries for a %d-class source" % (arr.size, num_src_classes))
+    if arr.min() < 0 or arr.max() >= num_classes:
+        raise ValueError("label table values must lie in [0, %d)" % num_classes)
+    return (ctypes.c_ubyte * arr.size)(*arr.tolist())
+
+
+def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4, ds_rate=1,
+                 want_conf=True, want_unc=True, want_kld=False, want_conf_hist=True, count_marginal=True,
+                 class_hist=None, conf_hist=None, marginal=None, label_out=None, conf_out=None, unc_out=None):
+    """K1: fused multi-source pseudo-label generation (replaces uest_seg_multi_os.py:897-921).
+
+    mains/auxs: lists (one entry per source) of (N, C_s, H, W) fp32 CUDA logits; luts: per-source tables
+    source class -> target class.  policy: 'half' | 'all' | int (the reference's vote, merge_outputs) or
+    'prob' ([NEW] averaged greenhouse-class probabilities).  Histogram / counter tensors passed in are
+    accumulated into (int64); otherwise fresh zeroed ones are returned.  label_out/conf_out/unc_out: optional
+    preallocated (N,H,W) outputs (e.g. slices of a dataset-wide map).
+    """
+    S = len(mains)
+    if S < 1 or S > MAX_SOURCES or len(auxs) != S or len(luts) != S:
+        raise ValueError("need 1..%d sources with matching mains/auxs/luts" % MAX_SOURCES)
+    if not (2 <= num_classes <= MAX_CLASSES) or not (0 <= ignore_label < num_classes):
+        raise ValueError("num_classes must be in [2,%d] and ignore_label inside it" % MAX_CLASSES)
+    m0 = _require_cuda(mains[0], "mains[0]", torch.float32, 4)
+    n, _, h, w = m0.shape
+    dev = m0.device
+    lut_bufs, cls = [], []
+    for s in range(S):
+        m = _require_cuda(mains[s], "mains[%d]" % s, torch.float32, 4)
+        a = _require_cuda(auxs[s], "auxs[%d]" % s, torch.float32, 4)
+        if m.shape != a.shape or m.shape[0] != n or m.shape[2:] != (h, w) or m.device != dev or a.device != dev:
+            raise ValueError("source %d: main/aux shapes or devices disagree" % s)
+        cls.append(m.shape[1])
+        lut_bufs.append(_lut_bytes(luts[s], m.shape[1], num_classes))
+    if policy == 'prob':
+        pol, vt = POLICY_PROB, 0
+    else:
+        pol, vt = POLICY_VOTE, vote_threshold(S, policy)
+    hw = h * w
+    def _out(t, name, dtype, wanted):
+        if t is not None:
+            if _require_cuda(t, name, dtype).shape != (n, h, w) or t.device != dev:
+                raise ValueError("%s must be a (%d,%d,%d) tensor on %s" % (name, n, h, w, dev))
+            return t
+        return torch.empty((n, h, w), dtype=dtype, device=dev) if wanted else None
+
+    label = _out(label_out, "label_out", torch.uint8, True)
+    conf = _out(conf_out, "conf_out", torch.float32, want_conf or want_conf_hist)
+    unc = _out(unc_out, "unc_out", torch.float32, want_unc)
+    kld = [torch.empty((n, h, w), dtype=torch.float32, device=dev) for _ in range(S)] if want_kld else None
+    if class_hist is None:
+        class_hist = torch.zeros(num_classes, dtype=torch.int64, device=dev)
+    if want_conf_hist and conf_hist is None:
+        conf_hist = torch.zeros((num_classes, RADIX_BINS), dtype=torch.int64, device=dev)
+    if count_marginal and marginal is None:
+        marginal = torch.zeros((), dtype=torch.int64, device=dev)
+    for t, nm in ((class_hist, "class_hist"), (conf_hist, "conf_hist"), (marginal, "marginal")):
+        if t is not None:
+            _require_cuda(t, nm, torch.int64)
+    vp = ctypes.c_void_p
+    main_ptrs = (vp * S)(*[m.data_ptr() for m in mains])
+    aux_ptrs = (vp * S)(*[a.data_ptr() for a in auxs])
+    kld_ptrs = (vp * S)(*[k.data_ptr() for k in kld]) if kld is not None else None
+    ncls = (ctypes.c_int * S)(*cls)
+    lut_ptrs = (vp * S)(*[ctypes.addressof(b) for b in lut_bufs])
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = lib.mspl_fuse_sources(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, n, hw, num_classes, pol, vt,
+                                   ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,
+                                   _ptr(class_hist), _ptr(conf_hist if want_conf_hist else None),
+                                   _ptr(marginal if count_marginal else None), _stream(dev))
+    _lib.check(st, "mspl_fuse_sources")
+    return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
+                      marginal if count_marginal else None)
+
+
+def vote_labels(labels, num_classes=5, thresh=None, ignore_label=4):
+    """merge_outputs on a (S, ...) uint8 CUDA tensor of hard labels -> uint8 tensor of shape labels.shape[1:]."""
+    labels = _require_cuda(labels, "labels", torch.uint8)
+    S = labels.shape[0]
+    out = torch.empty(labels.shape[1:], dtype=torch.uint8, device=labels.device)
+    npix = out.numel()
+    with torch.cuda.device(labels.device):
+        st = _lib.load().mspl_vote_labels(_ptr(labels), S, npix, num_classes, vote_threshold(S, thresh), ignore_label,
+                                          _ptr(out), _stream(labels.device))
+    _lib.check(st, "mspl_vote_labels")
+    return out
+
+
+def softmax_kld(main, aux, want_prob=True, want_kld=True):
+    """K0: (softmax(main + 0.5*aux) over classes, KL(softmax(main)||softmax(aux))) for (N,C,H,W) logits."""
+    main = _require_cuda(main, "main", torch.float32, 4)
+    aux = _require_cuda(aux, "aux", torch.float32, 4)
+    if main.shape != aux.shape:
+        raise ValueError("main/aux shapes differ")
+    n, c, h, w = main.shape
+    prob = torch.empty_like(main) if want_prob else None
+    kld = torch.empty((n, h, w), dtype=torch.float32, device=main.device) if want_kld else None
+    with torch.cuda.device(main.device):
+        st = _lib.load().mspl_softmax_kld(_ptr(main), _ptr(aux), n, c, h * w, _ptr(prob), _ptr(kld), _stream(main.device))
+    _lib.check(st, "mspl_softmax_kld")
+    return prob, kld
+
+
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None):
+    """K2: class-balanced thresholds by 3-pass radix select; exact order statistics, no sort, no host sync.
+
+    label (N,H,W) u8, conf (N,H,W) f32.  conf_hist: the pass-0 histogram already accumulated by fuse_sources
+    (it is consumed: zeroed on return); if None, pass 0 is computed here.  all_reduce: optional callable applied
+    in place to each pass's (K, 2048) int64 histogram (e.g. ``lambda h: dist.all_reduce(h)``) so that every rank
+    selects the same bins -- thresholds are then identical for 1 or N GPUs.
+    Returns (thresh f32 (K,), kept_count int64 (K,)).
+    """
+    label = _require_cuda(label, "label", torch.uint8)
+    conf = _require_cuda(conf, "conf", torch.float32)
+    if label.shape != conf.shape or label.dim() < 2:
+        raise ValueError("label/conf must share a (..., H, W) shape")
+    dev = label.device
+    hw = label.shape[-1] * label.shape[-2]
+    npix = label.numel()
+    lib = _lib.load()
+    K = num_classes
+    state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
+    thresh = torch.empty(K, dtype=torch.float32, device=dev)
+    kept = torch.zeros(K, dtype=torch.int64, device=dev)
+    hist = conf_hist
+    if hist is not None:
+        _require_cuda(hist, "conf_hist", torch.int64)
+    else:
+        hist = torch.zeros((K, RADIX_BINS), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        for p in range(RADIX_PASSES):
+            if p > 0 or conf_hist is None:
+                _lib.check(lib.mspl_radix_hist_pass(_ptr(label), _ptr(conf), npix, hw, K, p, _ptr(state), _ptr(hist),
+                                                    int(ds_rate), st), "mspl_radix_hist_pass")
+            if all_reduce is not None:
+                all_reduce(hist)
+            _lib.check(lib.mspl_radix_select(_ptr(hist), K, p, float(portion), _ptr(state), _ptr(thresh), _ptr(kept), st),
+                       "mspl_radix_select")
+    return thresh, kept
+
+
+def apply_thresholds(label, conf, thresh, ignore_label=4, want_mask=True, final_hist=None):
+    """K3: final = label if (label != ignore and conf >= thresh[label]) else ignore; mask = (final == ignore).
+    Returns (final u8, mask u8 or None, final_hist int64 (K,))."""
+    label = _require_cuda(label, "label", torch.uint8)
+    conf = _require_cuda(conf, "conf", torch.float32)
+    thresh = _require_cuda(thresh, "thresh", torch.float32, 1)
+    dev = label.device
+    K = thresh.numel()
+    final = torch.empty_like(label)
+    mask = torch.empty_like(label) if want_mask else None
+    if final_hist is None:
+        final_hist = torch.zeros(K, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().mspl_apply_thresholds(_ptr(label), _ptr(conf), _ptr(thresh), label.numel(), K, ignore_label,
+                                               _ptr(final), _ptr(mask), _ptr(final_hist), _stream(dev))
+    _lib.check(st, "mspl_apply_thresholds")
+    return final, mask, final_hist
+
+
+# ---- loss ---------------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(dev):
+    """One zeroed reduction workspace per (device, stream): kernels leave it zeroed for the next call."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().mspl_uw_ce_workspace_bytes(), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True):
+    """K4, explicit form: returns (out3, d_main, d_aux) with out3 = [loss, mean w*ce*exp(-kld), mean kld] on device and
+    the gradients of loss*grad_scale (None, None when backward=False)."""
+    main = _require_cuda(main, "main", torch.float32, 4)
+    aux = _require_cuda(aux, "aux", torch.float32, 4)
+    target = _require_cuda(target, "target", torch.int64, 3)
+    cw = _require_cuda(class_weights, "class_weights", torch.float32, 1)
+    n, k, h, w = main.shape
+    if aux.shape != main.shape or target.shape != (n, h, w) or cw.numel() != k:
+        raise ValueError("shape mismatch: main %s aux %s target %s class_weights %s" %
+                         (tuple(main.shape), tuple(aux.shape), tuple(target.shape), tuple(cw.shape)))
+    if k > MAX_CLASSES:
+        raise NotImplementedError("fused loss supports up to %d classes; use PixelwiseKLD + "
+                                  "UncertaintyWeightedSegmentationLoss modules for %d" % (MAX_CLASSES, k))
+    dev = main.device
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    d_main = torch.empty_like(main) if backward else None
+    d_aux = torch.empty_like(aux) if backward else None
+    ws = _workspace(dev)
+    norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
+    with torch.cuda.device(dev):
+        st = _lib.load().mspl_uw_ce_fwd_bwd(_ptr(main), _ptr(aux), _ptr(target), _ptr(cw), n, k, h * w, float(alpha), norm,
+                                            float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux), _ptr(ws), ws.numel(),
+                                            _stream(dev))
+    _lib.check(st, "mspl_uw_ce_fwd_bwd")
+    return out3, d_main, d_aux
+
+
+class _UwCeLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, main, aux, target, class_weights, alpha, norm_pixels):
+        need = main.requires_grad or aux.requires_grad
+        out3, d_main, d_aux = uw_ce_fwd_bwd(main.detach(), aux.detach(), target, class_weights.detach(), alpha, norm_pixels,
+                                            1.0, backward=need)
+        ctx.grads = (d_main, d_aux)
+        ctx.mark_non_differentiable(out3)
+        return out3[0].clone(), out3
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_parts):
+        d_main, d_aux = ctx.grads
+        ctx.grads = None
+        if d_main is None:
+            return None, None, None, None, None, None
+        # upstream gradient applied on device, skipped inside the kernel when it is exactly 1 (loss.backward())
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(d_main.device):
+            st = _stream(d_main.device)
+            _lib.check(lib.mspl_scale_inplace(_ptr(d_main), d_main.numel(), _ptr(g), st), "mspl_scale_inplace")
+            _lib.check(lib.mspl_scale_inplace(_ptr(d_aux), d_aux.numel(), _ptr(g), st), "mspl_scale_inplace")
+        return d_main, d_aux, None, None, None, None
+
+
+def uw_ce_loss(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, return_parts=False):
+    """K4 with autograd: the value of ``criterion(main + 0.5*aux, target, kld) * alpha + kld.mean()`` with
+    ``kld = PixelwiseKLD()(main, aux)`` (uest_seg_multi_os.py:1020-1023), forward and backward in ONE kernel launch.
+    norm_pixels overrides the divisor of the means (global pixel count under data parallelism)."""
+    loss, parts = _UwCeLoss.apply(main, aux, target, class_weights, alpha, norm_pixels)
+    return (loss, parts) if return_parts else loss
+
+
+def kld_fwd(d1, d2):
+    return softmax_kld(d1, d2, want_prob=False, want_kld=True)[1]
+
+
+class _PixelwiseKLD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d1, d2):
+        d1c, d2c = d1.detach().contiguous(), d2.detach().contiguous()
+        ctx.save_for_backward(d1c, d2c)
+        return kld_fwd(d1c, d2c)
+
+    @staticmethod
+    def backward(ctx, grad_kld):
+        d1, d2 = ctx.saved_tensors
+        g = grad_kld.detach().to(torch.float32).contiguous()
+        g1, g2 = torch.empty_like(d1), torch.empty_like(d2)
+        n, c, h, w = d1.shape
+        with torch.cuda.device(d1.device):
+            st = _lib.load().mspl_kld_bwd(_ptr(d1), _ptr(d2), _ptr(g), n, c, h * w, _ptr(g1), _ptr(g2), _stream(d1.device))
+        _lib.check(st, "mspl_kld_bwd")
+        return g1, g2
+
+
+def pixelwise_kld(d1, d2):
+    """PixelwiseKLD.forward (loss_fns/segmentation_loss.py:181-189), differentiable w.r.t. both inputs."""
+    _require_cuda(d1, "dist1", torch.float32, 4)
+    _require_cuda(d2, "dist2", torch.float32, 4)
+    if d1.shape != d2.shape:
+        raise ValueError("dist1/dist2 shapes differ")
+    return _PixelwiseKLD.apply(d1, d2)
+
+
+class _UwLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, u, cw, norm_pixels):
+        pred_c, u_c = pred.detach().contiguous(), u.detach().contiguous()
+        n, k, h, w = pred_c.shape
+        dev = pred_c.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = _workspace(dev)
+        norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
+        with torch.cuda.device(dev):
+            st = _lib.load().mspl_uw_loss_fwd(_ptr(pred_c), _ptr(target), _ptr(u_c), _ptr(cw), n, k, h * w, norm, _ptr(loss),
+                                              _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(st, "mspl_uw_loss_fwd")
+        ctx.save_for_backward(pred_c, target, u_c, cw)
+        ctx.norm = norm
+        ctx.u_shape = u.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        pred, target, u, cw = ctx.saved_tensors
+        n, k, h, w = pred.shape
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        d_pred = torch.empty_like(pred)
+        d_u = torch.empty_like(u) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(pred.device):
+            st = _lib.load().mspl_uw_loss_bwd(_ptr(pred), _ptr(target), _ptr(u), _ptr(cw), _ptr(g), n, k, h * w, ctx.norm,
+                                              _ptr(d_pred), _ptr(d_u), _stream(pred.device))
+        _lib.check(st, "mspl_uw_loss_bwd")
+        return d_pred, None, (d_u.reshape(ctx.u_shape) if d_u is not None else None), None, None
+
+
+def uw_segmentation_loss(pred, target, u_weight, class_weights, norm_pixels=None):
+    """UncertaintyWeightedSegmentationLoss.forward (loss_fns/segmentation_loss.py:155-175): mean over ALL pixels of
+    w[t] * (-log_softmax(pred)[t]) * exp(-u); differentiable w.r.t. pred and u_weight."""
+    _require_cuda(pred, "pred", torch.float32, 4)
+    n, k, h, w = pred.shape
+    target = _require_cuda(target, "target", torch.int64)
+    if target.numel() != n * h * w:
+        raise ValueError("target must hold one class index per pixel")
+    if not u_weight.is_cuda or u_weight.dtype != torch.float32 or u_weight.numel() != n * h * w:
+        raise ValueError("u_weight must be a CUDA fp32 tensor with one value per pixel")
+    cw = _require_cuda(class_weights, "class_weights", torch.float32, 1)
+    if cw.numel() != k:
+        raise ValueError("class_weights must have %d entries" % k)
+    return _UwLoss.apply(pred, target, u_weight, cw, norm_pixels)

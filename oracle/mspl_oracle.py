@@ -196,8 +196,8 @@ def fuse_sources(mains, auxs, luts, policy='half', seg_classes=NUM_GREENHOUSE_CL
       policy 'prob'               : label = first-argmax_k F ;  conf = max_k F
     Returns dict(label u8 (N,H,W), conf f32, unc f32, kld list of (N,H,W) f32, class_hist int64 (K,),
     marginal bool (N,H,W)).  ``marginal`` flags pixels where a different-but-legitimate fp32 rounding
-    may change the label: some source's top-2 softmax margin < 1e-6 with the two classes mapping to
-    different greenhouse ids, or (policy 'prob') the top-2 margin of F < 1e-6.
+    may change the label: some source's top-2 softmax margin < 1e-6, or (policy 'prob') the top-2 margin
+    of F < 1e-6.
     """
     S = len(mains)
     K = seg_classes
@@ -222,10 +222,8 @@ def fuse_sources(mains, auxs, luts, policy='half', seg_classes=NUM_GREENHOUSE_CL
                 G[:, k] = P[:, sel].max(dim=1).values
         Fsum = Fsum + G
         if P.shape[1] > 1:
-            top2 = torch.topk(P, 2, dim=1)
-            near = (top2.values[:, 0] - top2.values[:, 1]) < NEAR_TIE_MARGIN
-            differ = lut_t[top2.indices[:, 0]] != lut_t[top2.indices[:, 1]]
-            marginal |= near & differ
+            top2 = torch.topk(P, 2, dim=1).values
+            marginal |= (top2[:, 0] - top2[:, 1]) < NEAR_TIE_MARGIN
     Fm = Fsum / S
     U = Usum / S
     if policy == 'prob':

@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads and exports exactly the symbols include/mspl_b200.h declares; the product package
+never touches the oracle."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mspl_b200.h")).read()
+    return sorted(set(re.findall(r"^MSPL_API\s+[\w\s\*]+?\b(mspl_\w+)\s*\(", text, flags=re.M)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mspl_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def test_header_declares_entry_points():
+    names = _declared()
+    assert len(names) >= 17 and "mspl_fuse_sources" in names and "mspl_uw_ce_fwd_bwd" in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from mspl_b200 import _lib
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r"\sT\s+(mspl_\w+)", out))
+    assert set(_declared()) <= exported, sorted(set(_declared()) - exported)
+    assert exported == set(_declared()), "exported but undeclared: %s" % sorted(exported - set(_declared()))
+    assert set(_lib.SIGNATURES) == set(_declared())
+    for name in _declared():
+        assert getattr(lib, name) is not None
+
+
+def test_host_only_entry_points(lib):
+    assert lib.mspl_abi_version() == 1
+    assert lib.mspl_strerror(0) == b"ok" and b"misaligned" in lib.mspl_strerror(-2)
+    assert lib.mspl_radix_state_bytes(5) == 5 * 24
+    assert lib.mspl_uw_ce_workspace_bytes() >= 16 + 2 * 8 * 148
+    assert b"CH=" in lib.mspl_fuse_variant()
+
+
+def test_sass_is_sm100a():
+    from mspl_b200 import _lib
+    out = subprocess.check_output(["cuobjdump", "-lelf", _lib.LIB_PATH], text=True)
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mspl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+                assert "mspl_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from mspl_b200 import ops
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.softmax_kld(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.pixelwise_kld(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
+    assert ops.vote_threshold(3, None) == 2 and ops.vote_threshold(3, 'all') == 3 and ops.vote_threshold(3, 1) == 1
+    assert ops.vote_threshold(3, 7) == 2 and ops.vote_threshold(3, '3') == 2 and ops.vote_threshold(2, 'half') == 2

@@ -1,0 +1,399 @@
+"""-m gpu: CUDA kernels (through the C ABI) against the CPU oracle and the golden fixtures from the live reference.
+
+Tolerances (BASELINE.json north_star): label maps / masks / histograms bit-exact except at pixels the oracle flags
+as near-ties (top-2 probability margin < 1e-6), which are counted; confidences, uncertainties, thresholds and losses
+within 1e-5 relative.  KLD-type quantities are differences of O(1) log terms, so they additionally get an absolute
+floor of 2e-6 (the fp32 cancellation floor of the reference's own p1*logp1 - p1*logp2 sum)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mspl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SOURCES = (("camvid", 13), ("cityscapes", 20), ("forest", 5))
+RTOL = 1e-5
+KLD_ATOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mspl_b200 import ops as _ops
+    return _ops
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _golden_sources(g, prefix=""):
+    mains = [_t(g["%smain_%s" % (prefix, n)]) for n, _ in SOURCES]
+    auxs = [_t(g["%saux_%s" % (prefix, n)]) for n, _ in SOURCES]
+    return mains, auxs, [O.LUTS[n] for n, _ in SOURCES]
+
+
+def _fuse(ops, dev, mains, auxs, luts, policy, **kw):
+    return ops.fuse_sources([m.to(dev) for m in mains], [a.to(dev) for a in auxs], luts, policy=policy, **kw)
+
+
+def _check_against_oracle(r, ref, policy):
+    lab = r.label.cpu()
+    diff = lab != ref["label"]
+    n_diff, n_marg = int(diff.sum()), int(ref["marginal"].sum())
+    assert not bool((diff & ~ref["marginal"]).any()), "%d label mismatches outside the %d near-tie pixels" % (n_diff, n_marg)
+    ok = ~diff
+    torch.testing.assert_close(r.conf.cpu()[ok], ref["conf"][ok], rtol=RTOL, atol=1e-7)
+    torch.testing.assert_close(r.unc.cpu(), ref["unc"], rtol=RTOL, atol=KLD_ATOL)
+    if r.kld is not None:
+        for got, want in zip(r.kld, ref["kld"]):
+            torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=KLD_ATOL)
+    if n_diff == 0:
+        assert torch.equal(r.class_hist.cpu(), ref["class_hist"])
+    assert abs(int(r.marginal.item()) - n_marg) <= max(2, n_marg // 10)
+    return n_diff
+
+
+@pytest.mark.parametrize("policy", ["half", "all", 1, 2, 3, "prob"])
+def test_fuse_golden_3src(ops, dev, golden, policy):
+    g = golden("multi_source_3src.npz")
+    mains, auxs, luts = _golden_sources(g)
+    r = _fuse(ops, dev, mains, auxs, luts, policy, want_kld=True)
+    ref = O.fuse_sources(mains, auxs, luts, policy)
+    n_diff = _check_against_oracle(r, ref, policy)
+    if policy != "prob":     # labels straight from the LIVE reference (merge_outputs on its own argmax/LUT)
+        want = _t(g["label_%s" % policy])
+        assert int((r.label.cpu() != want).sum()) == n_diff
+        if n_diff == 0:
+            assert np.array_equal(r.class_hist.cpu().numpy().astype(np.float64), g["class_array_%s" % policy])
+    for s, (n, _) in enumerate(SOURCES):
+        torch.testing.assert_close(r.kld[s].cpu(), _t(g["kld_" + n]), rtol=RTOL, atol=KLD_ATOL)
+
+
+def test_fuse_subsets_s1_s2(ops, dev, golden):
+    g = golden("multi_source_3src.npz")
+    mains, auxs, luts = _golden_sources(g)
+    r = _fuse(ops, dev, mains[:1], auxs[:1], luts[:1], None)
+    assert torch.equal(r.label.cpu(), _t(g["label_s1"]))
+    r = _fuse(ops, dev, mains[:2], auxs[:2], luts[:2], "half")
+    assert torch.equal(r.label.cpu(), _t(g["label_s2_half"]))
+    assert np.array_equal(r.class_hist.cpu().numpy().astype(np.float64), g["class_array_s2_half"])
+
+
+@pytest.mark.parametrize("tag", ["ties", "big", "onehot"])
+def test_fuse_adversarial(ops, dev, golden, tag):
+    """All-equal logits (pure tie-break), +-80 logits (overflow guard), one-hot +-30 (conf -> 1)."""
+    g = golden("adversarial.npz")
+    mains, auxs, luts = _golden_sources(g, tag + "_")
+    for policy in ("half", "all"):
+        r = _fuse(ops, dev, mains, auxs, luts, policy, want_kld=True)
+        want = _t(g["%s_label_%s" % (tag, policy)])
+        ref = O.fuse_sources(mains, auxs, luts, policy)
+        if tag == "ties":
+            # exact ties in z: the reference's argmax-of-softmax and our argmax-of-z both take the lowest class index
+            assert torch.equal(r.label.cpu(), want)
+        else:
+            assert not bool(((r.label.cpu() != want) & ~ref["marginal"]).any())
+        assert torch.isfinite(r.conf).all() and torch.isfinite(r.unc).all()
+        for s, (n, _) in enumerate(SOURCES):
+            torch.testing.assert_close(r.kld[s].cpu(), _t(g["%s_kld_%s" % (tag, n)]), rtol=RTOL, atol=2e-5 if tag == "big" else KLD_ATOL)
+
+
+def test_softmax_kld_and_get_output(ops, dev, golden):
+    from mspl_b200 import uest_seg_multi_os as U
+    g = golden("multi_source_3src.npz")
+    for n, _ in SOURCES:
+        m, a = _t(g["main_" + n]), _t(g["aux_" + n])
+        prob, kld = ops.softmax_kld(m.to(dev), a.to(dev))
+        torch.testing.assert_close(prob.cpu(), _t(g["softmax_" + n]), rtol=RTOL, atol=1e-9)
+        torch.testing.assert_close(kld.cpu(), _t(g["kld_" + n]), rtol=RTOL, atol=KLD_ATOL)
+        out, k = U.get_output(lambda x: (m[1:2].to(dev), a[1:2].to(dev)), torch.zeros(1, 3, 4, 4), device=dev)
+        assert out.dtype == np.float32 and out.shape == g["softmax_" + n][1].shape and k.shape == g["kld_" + n][1].shape
+        np.testing.assert_allclose(out, g["softmax_" + n][1], rtol=RTOL, atol=1e-9)
+    od = {"out": m[:1].to(dev), "aux": a[:1].to(dev)}
+    out2, _ = U.get_output(lambda x: od, torch.zeros(1, 3, 4, 4), model_name="deeplabv3", device=dev)
+    np.testing.assert_allclose(out2, g["softmax_forest"][0], rtol=RTOL, atol=1e-9)
+
+
+def test_config1_crop(ops, dev, golden):
+    """BASELINE config 1 fixture: random-init 20-class ESPDNetUE logits (near-uniform softmax: many near-ties)."""
+    g = golden("config1_espdnetue_crop.npz")
+    m, a = _t(g["main"]), _t(g["aux"])
+    r = _fuse(ops, dev, [m], [a], [O.ID_CITYSCAPES_TO_GREENHOUSE], None, want_kld=True)
+    ref = O.fuse_sources([m], [a], [O.ID_CITYSCAPES_TO_GREENHOUSE], None)
+    want = _t(g["label"])
+    diff = r.label.cpu() != want
+    assert not bool((diff & ~ref["marginal"]).any())
+    torch.testing.assert_close(r.kld[0].cpu(), _t(g["kld"]), rtol=RTOL, atol=KLD_ATOL)
+    prob, _ = ops.softmax_kld(m.to(dev), a.to(dev))
+    torch.testing.assert_close(prob.cpu(), _t(g["softmax"]), rtol=RTOL, atol=0)
+
+
+def test_merge_outputs_and_helpers(dev, golden):
+    from mspl_b200 import uest_seg_multi_os as U
+    g = golden("multi_source_3src.npz")
+    per = []
+    for n, _ in SOURCES:
+        amax = np.argmax(g["softmax_" + n][0], axis=0).astype(np.uint8)
+        lab = U.transfer_id_to_greenhouse(O.LUTS[n], amax)
+        assert np.array_equal(lab, O.LUTS[n][amax])
+        per.append(lab)
+        got = U.transfer_output_to_greenhouse(O.LUTS[n], g["softmax_" + n][0])
+        assert got.dtype == np.float64 and np.array_equal(got, g["gh_prob_" + n][0])
+    stack = np.array(per)
+    for pol in (None, "half", "all", 1, 2, 3, "3", 7):
+        got = U.merge_outputs(stack, 5, pol)
+        assert got.dtype == np.int64 and np.array_equal(got, O.merge_outputs(stack, 5, pol))
+    for pol in ("half", "all", 1, 2, 3):
+        assert np.array_equal(U.merge_outputs(stack, 5, pol), g["label_%s" % pol][0])
+    t = U.merge_outputs(torch.from_numpy(stack).to(dev), 5, "all")
+    assert t.is_cuda and t.dtype == torch.int64
+
+
+@pytest.mark.parametrize("shape", [(1, 7, 9), (2, 5, 6), (3, 16, 20)])
+def test_ragged_shapes_scalar_path(ops, dev, shape):
+    """H*W not a multiple of 4 -> scalar (P=1) kernels; tiny and odd sizes."""
+    n, h, w = shape
+    mains, auxs = [], []
+    for i, (nm, c) in enumerate(SOURCES):
+        m, a = O.synthetic_logits(n, c, h, w, seed=20 + i)
+        mains.append(m), auxs.append(a)
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    for policy in ("half", "all", "prob"):
+        r = _fuse(ops, dev, mains, auxs, luts, policy, want_kld=True)
+        _check_against_oracle(r, O.fuse_sources(mains, auxs, luts, policy), policy)
+
+
+def test_misaligned_views_fall_back_to_scalar(ops, dev):
+    n, h, w = 2, 8, 12
+    m, a = O.synthetic_logits(n, 5, h, w, seed=4)
+    buf_m = torch.zeros(m.numel() + 1, device=dev)
+    buf_a = torch.zeros(a.numel() + 1, device=dev)
+    buf_m[1:] = m.reshape(-1).to(dev)
+    buf_a[1:] = a.reshape(-1).to(dev)
+    mv, av = buf_m[1:].view(n, 5, h, w), buf_a[1:].view(n, 5, h, w)       # 4-byte aligned only
+    r = ops.fuse_sources([mv], [av], [O.ID_FOREST_TO_GREENHOUSE], policy=None)
+    ref = O.fuse_sources([m], [a], [O.ID_FOREST_TO_GREENHOUSE], None)
+    assert not bool(((r.label.cpu() != ref["label"]) & ~ref["marginal"]).any())
+
+
+def test_empty_batch(ops, dev):
+    m = torch.zeros(0, 5, 8, 8, device=dev)
+    r = ops.fuse_sources([m], [m.clone()], [O.ID_FOREST_TO_GREENHOUSE])
+    assert r.label.shape == (0, 8, 8) and int(r.class_hist.sum()) == 0
+
+
+def test_rejects_cpu_tensors_and_bad_tables(ops, dev):
+    m = torch.zeros(1, 5, 8, 8)
+    with pytest.raises(ValueError):
+        ops.fuse_sources([m], [m], [O.ID_FOREST_TO_GREENHOUSE])
+    with pytest.raises(ValueError):
+        ops.fuse_sources([m.to(dev)], [m.to(dev)], [[0, 1, 2, 3, 9]])
+    with pytest.raises(ValueError):
+        ops.fuse_sources([m.to(dev)], [m.to(dev)], [[0, 1, 2]])
+
+
+@pytest.mark.parametrize("portion,ds_rate", [(0.2, 1), (0.5, 1), (0.05, 4), (1.0, 1), (0.0, 1), (1e-4, 3)])
+def test_cb_thresholds_exact(ops, dev, portion, ds_rate):
+    """Radix select == sort-based order statistic, bit for bit, on the very same conf values."""
+    n, h, w = 3, 40, 52
+    mains, auxs = [], []
+    for i, (nm, c) in enumerate(SOURCES):
+        m, a = O.synthetic_logits(n, c, h, w, seed=40 + i)
+        mains.append(m), auxs.append(a)
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    for policy in ("half", "prob"):
+        r = _fuse(ops, dev, mains, auxs, luts, policy, ds_rate=ds_rate)
+        th_ref, kept_ref = O.cb_thresholds(r.label.cpu(), r.conf.cpu(), portion, ds_rate)
+        th_a, kept_a = ops.cb_thresholds(r.label, r.conf, portion, ds_rate)                  # pass 0 computed standalone
+        th_b, kept_b = ops.cb_thresholds(r.label, r.conf, portion, ds_rate, conf_hist=r.conf_hist)   # pass 0 fused in K1
+        assert torch.equal(th_a.cpu(), th_ref) and torch.equal(kept_a.cpu(), kept_ref)
+        assert torch.equal(th_b.cpu(), th_ref) and torch.equal(kept_b.cpu(), kept_ref)
+        final, mask, fh = ops.apply_thresholds(r.label, r.conf, th_a)
+        f_ref, m_ref = O.apply_thresholds(r.label.cpu(), r.conf.cpu(), th_ref)
+        assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+        assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=5))
+
+
+def test_cb_thresholds_duplicates_and_extremes(ops, dev):
+    """Heavy duplicates, zeros, ones, denormals and negative values order exactly like torch.sort."""
+    gen = torch.Generator().manual_seed(9)
+    label = torch.randint(0, 5, (2, 31, 33), generator=gen).to(torch.uint8)
+    pool = torch.tensor([0.0, 1.0, 0.5, 0.5, 0.25, 1e-40, 3e-39, -0.25, 0.99999994, 0.33333334])
+    conf = pool[torch.randint(0, pool.numel(), (2, 31, 33), generator=gen)]
+    for p in (0.1, 0.37, 0.9):
+        th, kept = ops.cb_thresholds(label.to(dev), conf.to(dev), p)
+        th_ref, kept_ref = O.cb_thresholds(label, conf, p)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+
+
+def test_thresholds_vs_oracle_conf(ops, dev):
+    """End to end against the oracle's own conf: thresholds within 1e-5 relative; final labels equal except at
+    near-tie pixels and pixels whose conf sits within 1e-5 relative of its class threshold."""
+    n, h, w = 4, 64, 96
+    mains, auxs = [], []
+    for i, (nm, c) in enumerate(SOURCES):
+        m, a = O.synthetic_logits(n, c, h, w, seed=60 + i)
+        mains.append(m), auxs.append(a)
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    r = _fuse(ops, dev, mains, auxs, luts, "half")
+    ref = O.fuse_sources(mains, auxs, luts, "half")
+    th, _ = ops.cb_thresholds(r.label, r.conf, 0.2, conf_hist=r.conf_hist)
+    th_ref, _ = O.cb_thresholds(ref["label"], ref["conf"], 0.2)
+    torch.testing.assert_close(th.cpu(), th_ref, rtol=RTOL, atol=0)
+    final, _, _ = ops.apply_thresholds(r.label, r.conf, th)
+    f_ref, _ = O.apply_thresholds(ref["label"], ref["conf"], th_ref)
+    near_thresh = (ref["conf"] - th_ref[ref["label"].long()]).abs() <= 2e-5 * th_ref[ref["label"].long()]
+    bad = (final.cpu() != f_ref) & ~ref["marginal"] & ~near_thresh
+    assert not bool(bad.any())
+
+
+@pytest.mark.parametrize("tag", ["flat", "normal"])
+def test_fused_loss_golden(ops, dev, golden, tag):
+    g = golden("loss_k5.npz")
+    main, aux, target, cw = _t(g["main"]), _t(g["aux"]), _t(g["target"]), _t(g["cw_" + tag])
+    md, ad = main.to(dev).requires_grad_(True), aux.to(dev).requires_grad_(True)
+    loss, parts = ops.uw_ce_loss(md, ad, target.to(dev), cw.to(dev), return_parts=True)
+    loss.backward()
+    want = float(g["loss_" + tag])
+    assert abs(loss.item() - want) <= RTOL * abs(want)
+    assert abs(parts[0].item() - (20 * parts[1].item() + parts[2].item())) <= 1e-5 * abs(want)
+    scale = float(np.abs(g["grad_main_" + tag]).max())
+    torch.testing.assert_close(md.grad.cpu(), _t(g["grad_main_" + tag]), rtol=1e-4, atol=1e-5 * scale)
+    torch.testing.assert_close(ad.grad.cpu(), _t(g["grad_aux_" + tag]), rtol=1e-4, atol=1e-5 * scale)
+    # upstream gradient != 1 goes through the on-device scale kernel
+    md2, ad2 = main.to(dev).requires_grad_(True), aux.to(dev).requires_grad_(True)
+    (ops.uw_ce_loss(md2, ad2, target.to(dev), cw.to(dev)) * 0.25).backward()
+    torch.testing.assert_close(md2.grad, md.grad * 0.25, rtol=1e-6, atol=0)
+    torch.testing.assert_close(ad2.grad, ad.grad * 0.25, rtol=1e-6, atol=0)
+
+
+def test_fused_loss_fp64_oracle_and_determinism(ops, dev):
+    """Gradients against the fp64 oracle (tighter than fp32-vs-fp32) and bitwise run-to-run determinism."""
+    b, k, h, w = 4, 5, 36, 44
+    main, aux = O.synthetic_logits(b, k, h, w, seed=77)
+    target = torch.randint(0, k, (b, h, w), generator=torch.Generator().manual_seed(1))
+    cw = torch.tensor([0.0, 2.5, 1.0, 4.0, 0.0])
+    l64, gm64, ga64 = O.training_loss_and_grads(main, aux, target, cw, dtype=torch.float64)
+    out3, dm, da = ops.uw_ce_fwd_bwd(main.to(dev), aux.to(dev), target.to(dev), cw.to(dev))
+    assert abs(out3[0].item() - l64.item()) <= RTOL * abs(l64.item())
+    scale = float(gm64.abs().max())
+    torch.testing.assert_close(dm.cpu().double(), gm64, rtol=2e-5, atol=2e-6 * scale)
+    torch.testing.assert_close(da.cpu().double(), ga64, rtol=2e-5, atol=2e-6 * scale)
+    out3b, dmb, dab = ops.uw_ce_fwd_bwd(main.to(dev), aux.to(dev), target.to(dev), cw.to(dev))
+    assert torch.equal(out3, out3b) and torch.equal(dm, dmb) and torch.equal(da, dab)
+    out3f, none_m, none_a = ops.uw_ce_fwd_bwd(main.to(dev), aux.to(dev), target.to(dev), cw.to(dev), backward=False)
+    assert none_m is None and none_a is None and torch.equal(out3f, out3)
+    # data-parallel form: two half-batches with the GLOBAL pixel count sum to the full-batch loss and grads
+    norm = b * h * w
+    o_a, dm_a, _ = ops.uw_ce_fwd_bwd(main[:2].to(dev), aux[:2].to(dev), target[:2].to(dev), cw.to(dev), norm_pixels=norm)
+    o_b, dm_b, _ = ops.uw_ce_fwd_bwd(main[2:].to(dev), aux[2:].to(dev), target[2:].to(dev), cw.to(dev), norm_pixels=norm)
+    assert abs((o_a[0] + o_b[0]).item() - out3[0].item()) <= 1e-6 * abs(out3[0].item())
+    torch.testing.assert_close(torch.cat([dm_a, dm_b]), dm, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("tag", ["flat", "normal"])
+def test_reference_named_modules(dev, golden, tag):
+    """PixelwiseKLD / UncertaintyWeightedSegmentationLoss used exactly as uest_seg_multi_os.py:1020-1023 uses them."""
+    from mspl_b200.loss_fns.segmentation_loss import (FusedUncertaintyWeightedLoss, PixelwiseKLD,
+                                                      UncertaintyWeightedSegmentationLoss)
+    g = golden("loss_k5.npz")
+    main, aux, target = _t(g["main"]).to(dev), _t(g["aux"]).to(dev), _t(g["target"]).to(dev)
+    cw_in = torch.ones(5, device=dev) if tag == "flat" else torch.tensor([0.0, 3.1, 7.7, 2.2, 9.0], device=dev)
+    criterion = UncertaintyWeightedSegmentationLoss(5, class_weights=cw_in, ignore_idx=4, device=dev)
+    assert criterion.class_weights is cw_in and cw_in[4].item() == 0.0          # in-place zeroing quirk kept
+    pred, pred_aux = main.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+    kld = PixelwiseKLD()(pred, pred_aux)
+    loss = criterion(pred + 0.5 * pred_aux, target, kld) * 20 + kld.mean()
+    loss.backward()
+    want = float(g["loss_" + tag])
+    assert abs(loss.item() - want) <= RTOL * abs(want)
+    scale = float(np.abs(g["grad_main_" + tag]).max())
+    torch.testing.assert_close(pred.grad.cpu(), _t(g["grad_main_" + tag]), rtol=1e-4, atol=1e-5 * scale)
+    torch.testing.assert_close(pred_aux.grad.cpu(), _t(g["grad_aux_" + tag]), rtol=1e-4, atol=1e-5 * scale)
+    # the two modules on their own, with independent inputs
+    p = main.clone().requires_grad_(True)
+    u = _t(g["uw_u_" + tag]).to(dev).requires_grad_(True)
+    l2 = criterion(p, target, u)
+    l2.backward()
+    assert abs(l2.item() - float(g["uw_loss_" + tag])) <= RTOL * abs(float(g["uw_loss_" + tag]))
+    s2 = float(np.abs(g["uw_grad_pred_" + tag]).max())
+    torch.testing.assert_close(p.grad.cpu(), _t(g["uw_grad_pred_" + tag]), rtol=1e-4, atol=1e-5 * s2)
+    torch.testing.assert_close(u.grad.cpu(), _t(g["uw_grad_u_" + tag]), rtol=1e-4, atol=1e-5 * float(np.abs(g["uw_grad_u_" + tag]).max()))
+    d1, d2 = main.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+    kl = PixelwiseKLD()(d1, d2)
+    kl.backward(_t(g["kld_upstream"]).to(dev))
+    torch.testing.assert_close(kl.detach().cpu(), _t(g["kld"]), rtol=RTOL, atol=KLD_ATOL)
+    torch.testing.assert_close(d1.grad.cpu(), _t(g["kld_grad1"]), rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(d2.grad.cpu(), _t(g["kld_grad2"]), rtol=1e-4, atol=2e-6)
+    fused = FusedUncertaintyWeightedLoss(5, class_weights=cw_in.clone(), ignore_idx=4, device=dev)
+    lf = fused(main.clone().requires_grad_(True), aux.clone(), target)
+    assert abs(lf.item() - want) <= RTOL * abs(want)
+
+
+def test_full_size_properties(ops, dev):
+    """480x256 images at full resolution (too slow for the CPU oracle in bulk): size-independent properties --
+    sharding invariance (two halves == whole, histograms add up exactly), class_hist == bincount(label),
+    conf_hist row sums == kept counts, thresholded labels only ever move to the ignore class, and a spot check of
+    one image against the oracle."""
+    n, h, w = 6, 256, 480
+    gen = torch.Generator(device=dev).manual_seed(3)
+    mains, auxs = [], []
+    for nm, c in SOURCES:
+        m = 3 * torch.randn(n, c, h, w, generator=gen, device=dev)
+        mains.append(m), auxs.append(m + 1.5 * torch.randn(n, c, h, w, generator=gen, device=dev))
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    for policy in ("all", "half"):
+        r = ops.fuse_sources(mains, auxs, luts, policy=policy)
+        ra = ops.fuse_sources([m[:3] for m in mains], [a[:3] for a in auxs], luts, policy=policy)
+        rb = ops.fuse_sources([m[3:] for m in mains], [a[3:] for a in auxs], luts, policy=policy)
+        assert torch.equal(torch.cat([ra.label, rb.label]), r.label)
+        assert torch.equal(torch.cat([ra.conf, rb.conf]), r.conf) and torch.equal(torch.cat([ra.unc, rb.unc]), r.unc)
+        assert torch.equal(ra.class_hist + rb.class_hist, r.class_hist)
+        assert torch.equal(ra.conf_hist + rb.conf_hist, r.conf_hist)
+        assert torch.equal(r.class_hist, torch.bincount(r.label.reshape(-1).long(), minlength=5))
+        assert torch.equal(r.conf_hist.sum(dim=1), r.class_hist)
+        assert int(r.class_hist.sum()) == n * h * w
+        th, kept = ops.cb_thresholds(r.label, r.conf, 0.2, conf_hist=r.conf_hist.clone())
+        # 2-way "sharded" thresholds: histograms of the two halves are summed before each select
+        halves = [(ra.label, ra.conf), (rb.label, rb.conf)]
+        th2 = _sharded_thresholds(ops, halves, 0.2)
+        assert torch.equal(th, th2)
+        th_ref, _ = O.cb_thresholds(r.label.cpu(), r.conf.cpu(), 0.2)
+        assert torch.equal(th.cpu(), th_ref)
+        final, mask, fh = ops.apply_thresholds(r.label, r.conf, th)
+        assert bool(((final == r.label) | (final == 4)).all()) and torch.equal(mask == 1, final == 4)
+        assert torch.equal(fh, torch.bincount(final.reshape(-1).long(), minlength=5))
+        for k in range(1, 4):            # about `portion` of each class survives
+            nk = int((r.label == k).sum())
+            if nk > 100:
+                assert abs(int((final == k).sum()) - int(nk * 0.2)) <= max(3, nk // 1000)
+        ref = O.fuse_sources([m[:1].cpu() for m in mains], [a[:1].cpu() for a in auxs], luts, policy)
+        assert not bool(((r.label[:1].cpu() != ref["label"]) & ~ref["marginal"]).any())
+        torch.testing.assert_close(r.unc[:1].cpu(), ref["unc"], rtol=RTOL, atol=KLD_ATOL)
+
+
+def _sharded_thresholds(ops, shards, portion):
+    """Emulates N ranks on one GPU: per-pass histograms of all shards are summed (the all-reduce) before the select."""
+    from mspl_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    dev = shards[0][0].device
+    K = 5
+    state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
+    thresh = torch.empty(K, dtype=torch.float32, device=dev)
+    hist = torch.zeros((K, 2048), dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for ps in range(3):
+        for lab, conf in shards:
+            hw = lab.shape[-1] * lab.shape[-2]
+            _lib.check(lib.mspl_radix_hist_pass(p(lab), p(conf), lab.numel(), hw, K, ps, p(state), p(hist), 1, st), "hist")
+        _lib.check(lib.mspl_radix_select(p(hist), K, ps, portion, p(state), p(thresh), None, st), "select")
+    return thresh
