@@ -1,9 +1,16 @@
-// K1 -- fused multi-source pseudo-label generation (direct-load variant).
+// K1 -- fused multi-source pseudo-label generation.
 //
-// One pass over HBM: every (main, aux) logit of every source is read exactly once with 128-bit streaming
-// loads; per pixel the kernel produces the voted / fused label (u8), its confidence, the mean main-vs-aux KLD,
-// and accumulates the class histogram plus radix pass 0 of the per-class confidence histogram in shared
-// memory.  Replaces uest_seg_multi_os.py:897-921 (+ :669-718) -- see include/mspl_b200.h.
+// One pass over HBM: every (main, aux) logit of every source is read exactly once; per pixel the kernel produces the
+// voted / fused label (u8), its confidence, the mean main-vs-aux KLD, and accumulates the class histogram plus radix
+// pass 0 of the per-class confidence histogram in shared memory.  Replaces uest_seg_multi_os.py:897-921 (+ :669-718)
+// -- see include/mspl_b200.h.
+//
+// Two load mechanisms share all the per-pixel math below:
+//   fuse_sources_direct_kernel : every thread streams its own pixels with 128-bit ld.global.nc (any shape/alignment
+//                                when P=1; needs hw % 4 == 0 and 16-byte bases when P=4)
+//   fuse_sources_tma_kernel    : a producer warp stages [classes-chunk x tile-of-pixels] boxes into a shared-memory
+//                                ring with bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
+//                                consumer warps compute from shared memory; bytes in flight no longer cost registers
 #pragma once
 #include "pixel_math.cuh"
 
@@ -25,131 +32,62 @@ struct FuseParams {
     unsigned long long* marginal;
 };
 
-constexpr int kFuseThreads = 256;
-
-// Dynamic shared memory: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B class tables]
-inline size_t fuse_smem_bytes(int K) {
-    return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 8) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES;
+// Shared-memory bookkeeping common to both kernels: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B tables]
+inline size_t fuse_tally_smem_bytes(int K) {
+    return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 8) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;   // +16: padded-class table reads
 }
 
-// Per-thread class counters packed 8 bits per class, spilled to full counters before they can overflow.
-template <int K>
-struct ClassCounter {
-    unsigned long long packed = 0;
-    uint32_t full[K] = {};
-    int pending = 0;
-    MSPL_DEVINL void add(int label, bool on) { packed += (unsigned long long)on << (8 * label); }
-    MSPL_DEVINL void spill() {
-#pragma unroll
-        for (int k = 0; k < K; ++k) full[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
-        packed = 0;
-        pending = 0;
-    }
-    template <int P> MSPL_DEVINL void tick() { if ((pending += P) > 255 - P) spill(); }
-};
+// ---- per-pixel accumulation across sources --------------------------------------------------------------------------
+// GK: per-target-class probabilities needed (policy 'prob', or a vote threshold below S); otherwise every source voted
+// for the winning label and G_s[label] is simply that source's max probability.
+template <int P, int K, bool GK, bool TOP2>
+struct PixelFusion {
+    float usum[P], csum[P], Fk[GK ? K : 1][P];
+    uint32_t votes[P];
+    bool marg[P];
 
-// P: pixels per thread (vector width), CH: classes per chunk, KT: compile-time bound on the target classes
-// (prm.K <= KT; classes in [prm.K, KT) simply never receive votes or probability),
-// GK: per-target-class probabilities needed (policy 'prob', or a vote threshold below S),
-// TOP2: near-tie accounting.
-template <int P, int CH, int KT, bool GK, bool TOP2, int MINB>
-__global__ void __launch_bounds__(kFuseThreads, MINB) fuse_sources_kernel(const __grid_constant__ FuseParams prm) {
-    constexpr int K = KT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nbins = prm.K * MSPL_RADIX_BINS;
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_cls = s_hist + nbins;
-    uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_cls + 8);
-
-    const bool want_hist = prm.conf_hist != nullptr;
-    if (want_hist)
-        for (int i = threadIdx.x; i < nbins; i += kFuseThreads) s_hist[i] = 0;
-    if (threadIdx.x < 8) s_cls[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += kFuseThreads)
-        s_lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
-    __syncthreads();
-
-    const int S = prm.S;
-    const float fS = (float)S;
-    const int64_t hw = prm.hw;
-    const int64_t gpi = hw / P;                       // pixel groups per image
-    const int64_t n_groups = prm.n_img * gpi;
-    const int64_t n_tiles = (n_groups + kFuseThreads - 1) / kFuseThreads;
-    const bool prob_policy = prm.policy == MSPL_POLICY_PROB;
-    const int ignore = prm.ignore;
-
-    ClassCounter<K> cls;
-    uint32_t n_marginal = 0, n_ignore_zero = 0;
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int64_t g = tile * kFuseThreads + threadIdx.x;
-        const bool active = g < n_groups;
-        g = active ? g : n_groups - 1;
-        const int64_t n = g / gpi;
-        const int64_t off = (g - n * gpi) * P;       // first pixel of the group inside its image
-
-        float usum[P], csum[P], Fk[K][P];
-        uint32_t votes[P];
-        bool marg[P];
+    MSPL_DEVINL void reset() {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             usum[p] = csum[p] = 0.f;
             votes[p] = 0;
             marg[p] = false;
 #pragma unroll
-            for (int k = 0; k < K; ++k) Fk[k][p] = 0.f;
+            for (int k = 0; k < (GK ? K : 1); ++k) Fk[k][p] = 0.f;
         }
+    }
 
-        for (int s = 0; s < S; ++s) {
-            const int C = prm.C[s];
-            const float* pm = prm.main[s] + (n * C) * hw + off;
-            const float* pa = prm.aux[s] + (n * C) * hw + off;
-            SourceStats<P> st;
-            st.reset();
-            float zk[K][P];
+    // fold one finished source in; d receives its KLD map values
+    MSPL_DEVINL void add_source(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P]) {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
+        for (int p = 0; p < P; ++p) {
+            d[p] = kld_of<P>(st, p);
+            usum[p] += d[p];
+            const float pmax = 1.0f / st.Sz[p];
+            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * pmax < kNearTieMargin;
+            const int lab = s_lut_s[st.amax[p]];
+            votes[p] += 1u << (4 * lab);
+            if (GK) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) zk[k][p] = -INFINITY;
-
-            for (int c0 = 0; c0 < C; c0 += CH) {
-                const int cn = min(CH, C - c0);
-                float m[CH][P], a[CH][P];
-                load_chunk<P, CH>(pm + c0 * hw, pa + c0 * hw, hw, cn, m, a);
-                fold_chunk<P, CH, TOP2, GK, K>(st, m, a, c0, cn, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
+                    Fk[k][p] += exp_neg(zk[k][p] - st.Mz[p]) * pmax;
+            } else {
+                csum[p] += pmax;
             }
-
-            float d[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                d[p] = kld_of<P>(st, p);
-                usum[p] += d[p];
-                const float pmax = 1.0f / st.Sz[p];
-                if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * pmax < kNearTieMargin;
-                const int lab = s_lut[s * MSPL_MAX_SRC_CLASSES + st.amax[p]];
-                votes[p] += 1u << (4 * lab);
-                if (GK) {
-#pragma unroll
-                    for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (:1340)
-                        Fk[k][p] += exp_neg(zk[k][p] - st.Mz[p]) * pmax;
-                } else {
-                    csum[p] += pmax;                 // every source voted for the label: G_s[label] = max prob
-                }
-            }
-            if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
         }
+    }
 
-        int label[P];
-        float conf[P], unc[P];
+    MSPL_DEVINL void finish(const FuseParams& prm, float fS, int (&label)[P], float (&conf)[P], float (&unc)[P]) {
+        const int ignore = prm.ignore;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             unc[p] = usum[p] / fS;
-            if (prob_policy) {
+            if (prm.policy == MSPL_POLICY_PROB) {
                 float best = -1.f, second = -1.f;
                 int bk = 0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float f = GK ? Fk[k][p] / fS : 0.f;
+                    const float f = GK ? Fk[GK ? k : 0][p] / fS : 0.f;
                     second = fmaxf(second, fminf(best, f));
                     bk = (f > best) ? k : bk;
                     best = fmaxf(best, f);
@@ -161,61 +99,334 @@ __global__ void __launch_bounds__(kFuseThreads, MINB) fuse_sources_kernel(const 
                 int bk = 0;
                 uint32_t bc = votes[p] & 15u;
 #pragma unroll
-                for (int k = 1; k < K; ++k) {
+                for (int k = 1; k < K; ++k) {        // merge_outputs: most votes, lowest class on ties (:713)
                     const uint32_t c = (votes[p] >> (4 * k)) & 15u;
                     if (c > bc) { bc = c; bk = k; }
                 }
-                label[p] = ((int)bc < prm.vote_t) ? ignore : bk;
+                label[p] = ((int)bc < prm.vote_t) ? ignore : bk;     // (:716)
                 float f = csum[p];
                 if (GK) {
                     f = 0.f;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) f = (label[p] == k) ? Fk[k][p] : f;
+                    for (int k = 0; k < K; ++k) f = (label[p] == k) ? Fk[GK ? k : 0][p] : f;
                 }
                 conf[p] = (label[p] == ignore) ? 0.f : f / fS;
             }
         }
+    }
+};
 
+// ---- per-thread tallies: class counts (packed 8 bits per class, spilled before overflow), near-ties, histogram ----------
+template <int K>
+struct Tally {
+    unsigned long long packed = 0;
+    uint32_t full[K] = {};
+    uint32_t n_marginal = 0, n_ignore_zero = 0;
+    int pending = 0;
+
+    MSPL_DEVINL void spill() {
+#pragma unroll
+        for (int k = 0; k < K; ++k) full[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+        packed = 0;
+        pending = 0;
+    }
+
+    template <int P>
+    MSPL_DEVINL void add(const FuseParams& prm, uint32_t* s_hist, const int (&label)[P], const float (&conf)[P],
+                         const bool (&marg)[P], int64_t off, bool active) {
+        const bool want_hist = prm.conf_hist != nullptr;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            packed += (unsigned long long)active << (8 * label[p]);
+            n_marginal += (marg[p] && active);
+            if (want_hist) {
+                const bool keep = active && (prm.ds_rate <= 1 || ((off + p) % prm.ds_rate) == 0);
+                // vote policies give ignore-labelled pixels conf == 0: one known bin, counted without atomics
+                if (prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore) n_ignore_zero += keep;
+                else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + (float_to_key(conf[p]) >> 21)], 1u);
+            }
+        }
+        if ((pending += P) > 255 - P) spill();
+    }
+
+    // whole CTA must call this (it syncs); nthreads = blockDim.x
+    MSPL_DEVINL void flush(const FuseParams& prm, uint32_t* s_hist, uint32_t* s_cls, int nthreads) {
+        spill();
+        const bool leader = (threadIdx.x & 31) == 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t w = __reduce_add_sync(0xffffffffu, full[k]);
+            if (leader && w) atomicAdd(&s_cls[k], w);
+        }
+        const uint32_t wz = __reduce_add_sync(0xffffffffu, n_ignore_zero);
+        if (leader && wz) atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
+        const uint32_t wm = __reduce_add_sync(0xffffffffu, n_marginal);
+        if (leader && wm && prm.marginal) atomicAdd(prm.marginal, (unsigned long long)wm);
+        __syncthreads();
+        if ((int)threadIdx.x < prm.K && s_cls[threadIdx.x]) atomicAdd(prm.class_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+        if (prm.conf_hist)
+            for (int i = threadIdx.x; i < prm.K * MSPL_RADIX_BINS; i += nthreads)
+                if (s_hist[i]) atomicAdd(prm.conf_hist + i, (unsigned long long)s_hist[i]);
+    }
+};
+
+MSPL_DEVINL void tally_smem_init(const FuseParams& prm, unsigned char* smem, uint32_t*& s_hist, uint32_t*& s_cls, uint8_t*& s_lut,
+                                 int nthreads) {
+    const int nbins = prm.K * MSPL_RADIX_BINS;
+    s_hist = reinterpret_cast<uint32_t*>(smem);
+    s_cls = s_hist + nbins;
+    s_lut = reinterpret_cast<uint8_t*>(s_cls + 8);
+    for (int i = threadIdx.x; i < nbins; i += nthreads) s_hist[i] = 0;
+    if (threadIdx.x < 8) s_cls[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += nthreads)
+        s_lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
+}
+
+template <int K, int P>
+MSPL_DEVINL void reset_zk(float (&zk)[K][P]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int p = 0; p < P; ++p) zk[k][p] = -INFINITY;
+}
+
+// ======================================================================================================================
+// Direct-load kernel.  P: pixels per thread (vector width), CH: classes per chunk, KT: compile-time bound on the target
+// classes (prm.K <= KT; classes in [prm.K, KT) never receive votes or probability).
+// ======================================================================================================================
+template <int P, int CH, int KT, bool GK, bool TOP2, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(const __grid_constant__ FuseParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_hist, *s_cls;
+    uint8_t* s_lut;
+    tally_smem_init(prm, smem_raw, s_hist, s_cls, s_lut, THREADS);
+    __syncthreads();
+
+    const int S = prm.S;
+    const float fS = (float)S;
+    const int64_t hw = prm.hw;
+    const int64_t gpi = hw / P;                       // pixel groups per image
+    const int64_t n_groups = prm.n_img * gpi;
+    const int64_t n_tiles = (n_groups + THREADS - 1) / THREADS;
+    Tally<KT> tally;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t g = tile * THREADS + threadIdx.x;
+        const bool active = g < n_groups;
+        g = active ? g : n_groups - 1;
+        const int64_t n = g / gpi;
+        const int64_t off = (g - n * gpi) * P;       // first pixel of the group inside its image
+
+        PixelFusion<P, KT, GK, TOP2> fus;
+        fus.reset();
+        for (int s = 0; s < S; ++s) {
+            const int C = prm.C[s];
+            const float* pm = prm.main[s] + (n * C) * hw + off;
+            const float* pa = prm.aux[s] + (n * C) * hw + off;
+            SourceStats<P> st;
+            st.reset();
+            float zk[KT][P];
+            reset_zk<KT, P>(zk);
+            for (int c0 = 0; c0 < C; c0 += CH) {
+                const int cn = min(CH, C - c0);
+                float m[CH][P], a[CH][P];
+                load_chunk<P, CH>(pm + c0 * hw, pa + c0 * hw, hw, cn, m, a);
+                fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+            }
+            float d[P];
+            fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
+            if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+        }
+        int label[P];
+        float conf[P], unc[P];
+        fus.finish(prm, fS, label, conf, unc);
         if (active) {
             const int64_t o = n * hw + off;
             store_labels<P>(prm.label + o, label);
             if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
             if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
         }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            cls.add(label[p], active);
-            if (TOP2) n_marginal += (marg[p] && active);
-            if (want_hist) {
-                const bool keep = active && (prm.ds_rate <= 1 || ((off + p) % prm.ds_rate) == 0);
-                if (!prob_policy && label[p] == ignore) n_ignore_zero += keep;   // conf == 0: one known bin
-                else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + (float_to_key(conf[p]) >> 21)], 1u);
-            }
-        }
-        cls.template tick<P>();
+        tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
     }
+    tally.flush(prm, s_hist, s_cls, THREADS);
+}
 
-    // ---- flush per-thread counters -> shared -> global ------------------------------------------------
-    cls.spill();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const uint32_t w = __reduce_add_sync(0xffffffffu, cls.full[k]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cls[k], w);
-    }
-    if (want_hist) {
-        const uint32_t w = __reduce_add_sync(0xffffffffu, n_ignore_zero);
-        if ((threadIdx.x & 31) == 0 && w)
-            atomicAdd(&s_hist[ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], w);
-    }
-    if (TOP2 && prm.marginal) {
-        const uint32_t w = __reduce_add_sync(0xffffffffu, n_marginal);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(prm.marginal, (unsigned long long)w);
+// ======================================================================================================================
+// TMA (bulk async copy) staged kernel.
+//   CTA = NCW consumer warps + 1 producer warp.  A tile is TP = NCW*32*P consecutive pixels of one image (hw % TP == 0).
+//   A stage holds one chunk of up to CH classes of both heads for the tile: [2][CH][TP] floats; the producer fills stages
+//   in the order (tile, source, chunk) with one cp.async.bulk per class row, completion signalled on the stage's "full"
+//   mbarrier (complete_tx::bytes); a consumer warp copies its pixels' values to registers, releases the stage ("empty"
+//   mbarrier, one arrival per consumer warp) and only then does the math, so the ring turns over at load speed.
+// ======================================================================================================================
+namespace tma {
+
+MSPL_DEVINL uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+MSPL_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+MSPL_DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+MSPL_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+MSPL_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streaming data: L2 evict-first hint
+MSPL_DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+MSPL_DEVINL uint64_t evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+template <int P> MSPL_DEVINL void lds(const float* p, float (&v)[P]);
+template <> MSPL_DEVINL void lds<1>(const float* p, float (&v)[1]) { v[0] = *p; }
+template <> MSPL_DEVINL void lds<2>(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <> MSPL_DEVINL void lds<4>(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+}  // namespace tma
+
+template <int NCW, int P, int CH, int NSTAGE>
+struct TmaCfg {
+    static constexpr int kThreads = (NCW + 1) * 32;
+    static constexpr int kTilePix = NCW * 32 * P;
+    static constexpr int kStageFloats = 2 * CH * kTilePix;
+    static constexpr size_t kRingBytes = sizeof(float) * (size_t)kStageFloats * NSTAGE;
+    static size_t smem_bytes(int K) { return kRingBytes + 2 * NSTAGE * sizeof(uint64_t) + fuse_tally_smem_bytes(K) + 128; }
+};
+
+template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(const __grid_constant__ FuseParams prm) {
+    using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
+    constexpr int TP = Cfg::kTilePix;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kRingBytes);
+    uint64_t* empty = full + NSTAGE;
+    uint32_t *s_hist, *s_cls;
+    uint8_t* s_lut;
+    tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, Cfg::kThreads);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x < prm.K && s_cls[threadIdx.x]) atomicAdd(prm.class_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
-    if (want_hist)
-        for (int i = threadIdx.x; i < nbins; i += kFuseThreads)
-            if (s_hist[i]) atomicAdd(prm.conf_hist + i, (unsigned long long)s_hist[i]);
+
+    const int S = prm.S;
+    const int64_t hw = prm.hw;
+    const int64_t tpi = hw / TP;                       // tiles per image
+    const int64_t n_tiles = prm.n_img * tpi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Tally<KT> tally;
+
+    if (warp == NCW) {
+        // ------------------------------- producer warp -------------------------------
+        const uint64_t policy = tma::evict_first_policy();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t n = tile / tpi;
+            const int64_t off = (tile - n * tpi) * TP;
+            for (int s = 0; s < S; ++s) {
+                const int C = prm.C[s];
+                const float* pm = prm.main[s] + (n * C) * hw + off;
+                const float* pa = prm.aux[s] + (n * C) * hw + off;
+                for (int c0 = 0; c0 < C; c0 += CH) {
+                    const int cn = min(CH, C - c0);
+                    tma::mbar_wait(&empty[stage], phase ^ 1);          // all consumers released this slot
+                    float* dst = ring + (size_t)stage * Cfg::kStageFloats;
+                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 * cn * TP * sizeof(float)));
+                    __syncwarp();
+                    for (int j = lane; j < 2 * cn; j += 32) {
+                        const int head = j >= cn, c = head ? j - cn : j;
+                        const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
+                        tma::bulk_g2s(dst + (head * CH + c) * TP, src, TP * sizeof(float), &full[stage], policy);
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps -------------------------------
+        const float fS = (float)S;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int px = (warp * 32 + lane) * P;          // this thread's first pixel inside the tile
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t n = tile / tpi;
+            const int64_t off = (tile - n * tpi) * TP + px;
+            PixelFusion<P, KT, GK, TOP2> fus;
+            fus.reset();
+            for (int s = 0; s < S; ++s) {
+                const int C = prm.C[s];
+                SourceStats<P> st;
+                st.reset();
+                float zk[KT][P];
+                reset_zk<KT, P>(zk);
+                for (int c0 = 0; c0 < C; c0 += CH) {
+                    const int cn = min(CH, C - c0);
+                    float m[CH][P], a[CH][P];
+                    tma::mbar_wait(&full[stage], phase);
+                    const float* src = ring + (size_t)stage * Cfg::kStageFloats + px;
+                    if (cn == CH) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) tma::lds<P>(src + j * TP, m[j]);
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) tma::lds<P>(src + (CH + j) * TP, a[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (j < cn) { tma::lds<P>(src + j * TP, m[j]); tma::lds<P>(src + (CH + j) * TP, a[j]); }
+                            else { fill_pad<P>(m[j]); fill_pad<P>(a[j]); }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) tma::mbar_arrive(&empty[stage]);    // values are in registers: hand the slot back
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                }
+                float d[P];
+                fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
+                if (prm.kld[s] != nullptr) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+            }
+            int label[P];
+            float conf[P], unc[P];
+            fus.finish(prm, fS, label, conf, unc);
+            const int64_t o = n * hw + off;
+            store_labels<P>(prm.label + o, label);
+            if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
+            if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
+            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, true);
+        }
+    }
+    tally.flush(prm, s_hist, s_cls, Cfg::kThreads);
 }
 
 }  // namespace mspl

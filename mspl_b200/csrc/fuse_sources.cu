@@ -1,49 +1,52 @@
 // Host entry points for K1 (mspl_fuse_sources) and the hard-label vote (mspl_vote_labels).
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 
-#include "fuse_kernel.cuh"
+#include "fuse_launch.cuh"
 
 namespace mspl {
 
+// Build-time choice of the K1 variants (picked from the tools/k1_sweep measurements on B200, see profiles/).
 #ifndef MSPL_FUSE_CH
-#define MSPL_FUSE_CH 5      // classes per chunk: 13 -> 5+5+3, 20 -> 4x5, 5 -> one exact two-sweep chunk
+#define MSPL_FUSE_CH 5        // classes per chunk: 13 -> 5+5+3, 20 -> 4x5, 5 -> one exact two-sweep chunk
 #endif
 #ifndef MSPL_FUSE_MINB
-#define MSPL_FUSE_MINB 2    // resident CTAs per SM the register allocator must leave room for
+#define MSPL_FUSE_MINB 2      // direct kernel: resident CTAs per SM the register allocator must leave room for
+#endif
+#ifndef MSPL_TMA_NCW
+#define MSPL_TMA_NCW 8        // TMA kernel: consumer warps per CTA
+#endif
+#ifndef MSPL_TMA_P
+#define MSPL_TMA_P 4          // TMA kernel: pixels per consumer thread
+#endif
+#ifndef MSPL_TMA_STAGES
+#define MSPL_TMA_STAGES 4     // TMA kernel: ring depth
+#endif
+#ifndef MSPL_USE_TMA
+#define MSPL_USE_TMA 1
 #endif
 
-template <typename Kern>
-static int launch_fuse(Kern kern, const FuseParams& prm, int P, cudaStream_t stream) {
-    static std::mutex mu;
-    const size_t smem = fuse_smem_bytes(prm.K);
-    int dev = 0, sms = kNumSMs, per_sm = 1;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (cudaGetDevice(&dev) != cudaSuccess) return MSPL_ERR_CUDA;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return MSPL_ERR_CUDA;
-        }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFuseThreads, smem) != cudaSuccess || per_sm < 1) {
-            cudaGetLastError();
-            return MSPL_ERR_CUDA;
-        }
-    }
-    const int64_t n_groups = prm.n_img * (prm.hw / P);
-    const int64_t n_tiles = (n_groups + kFuseThreads - 1) / kFuseThreads;
-    const int64_t grid = n_tiles < (int64_t)sms * per_sm ? n_tiles : (int64_t)sms * per_sm;   // persistent CTAs
-    kern<<<(unsigned)grid, kFuseThreads, smem, stream>>>(prm);
-    return launch_status();
-}
+constexpr int kDirectThreads = 256;
 
 template <int P, int KT>
-static int dispatch_fuse(const FuseParams& prm, bool gk, cudaStream_t stream) {
+static int dispatch_direct(const FuseParams& prm, bool gk, cudaStream_t stream) {
     constexpr int CH = MSPL_FUSE_CH, MB = MSPL_FUSE_MINB;
-    if (gk) return launch_fuse(fuse_sources_kernel<P, CH, KT, true, true, MB>, prm, P, stream);
-    return launch_fuse(fuse_sources_kernel<P, CH, KT, false, true, MB>, prm, P, stream);
+    if (gk) return launch_fuse_direct<P, kDirectThreads>(fuse_sources_direct_kernel<P, CH, KT, true, true, kDirectThreads, 1>, prm, stream);
+    return launch_fuse_direct<P, kDirectThreads>(fuse_sources_direct_kernel<P, CH, KT, false, true, kDirectThreads, MB>, prm, stream);
+}
+
+template <int KT>
+static int dispatch_tma(const FuseParams& prm, bool gk, cudaStream_t stream) {
+    using Cfg = TmaCfg<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES>;
+    if (gk) return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, KT, true, true>, prm, stream);
+    return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, KT, false, true>, prm, stream);
+}
+
+template <int KT>
+static int dispatch_fuse(const FuseParams& prm, int P, bool gk, cudaStream_t stream) {
+    using Cfg = TmaCfg<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES>;
+    if (MSPL_USE_TMA && P == 4 && tma_eligible<Cfg>(prm)) return dispatch_tma<KT>(prm, gk, stream);
+    return P == 4 ? dispatch_direct<4, KT>(prm, gk, stream) : dispatch_direct<1, KT>(prm, gk, stream);
 }
 
 // merge_outputs (uest_seg_multi_os.py:695-718) on (S, npix) hard labels.
@@ -70,8 +73,12 @@ __global__ void __launch_bounds__(256) vote_labels_kernel(const uint8_t* __restr
 using namespace mspl;
 
 extern "C" const char* mspl_fuse_variant(void) {
-    static char name[96];
-    snprintf(name, sizeof(name), "direct-ldg128 P=4 CH=%d threads=%d minblocks=%d", MSPL_FUSE_CH, kFuseThreads, MSPL_FUSE_MINB);
+    static char name[192];
+    if (MSPL_USE_TMA)
+        snprintf(name, sizeof(name), "tma-bulk ring: consumer warps=%d P=%d CH=%d stages=%d (direct-ldg fallback: P=4|1 CH=%d minblocks=%d)",
+                 MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, MSPL_FUSE_CH, MSPL_FUSE_MINB);
+    else
+        snprintf(name, sizeof(name), "direct-ldg128 P=4 CH=%d threads=%d minblocks=%d", MSPL_FUSE_CH, kDirectThreads, MSPL_FUSE_MINB);
     return name;
 }
 
@@ -121,8 +128,7 @@ extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logit
     // Per-target-class probabilities are only needed when a pixel can win without every source's vote.
     const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (K <= 5) return P == 4 ? dispatch_fuse<4, 5>(prm, gk, st) : dispatch_fuse<1, 5>(prm, gk, st);
-    return P == 4 ? dispatch_fuse<4, 8>(prm, gk, st) : dispatch_fuse<1, 8>(prm, gk, st);
+    return K <= 5 ? dispatch_fuse<5>(prm, P, gk, st) : dispatch_fuse<8>(prm, P, gk, st);
 }
 
 extern "C" int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,

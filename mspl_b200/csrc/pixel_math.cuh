@@ -38,12 +38,16 @@ struct SourceStats {
     }
 };
 
-// Fold classes [c0, c0+cn) (1 <= cn <= CH, warp-uniform) into the running stats.  m/a hold the chunk's logits.
-// `first` (warp-uniform): nothing accumulated yet, skip the rescale.
+// Value loaded in place of the classes a tail chunk does not have: hugely negative but finite, so that it never wins a
+// max, its exponentials are exactly 0 and (m - Mm) - (a - Ma) stays finite (0) -- the math below needs no predicates.
+constexpr float kPadLogit = -1.0e30f;
+
+// Fold classes [c0, c0+CH) into the running stats.  m/a hold the chunk's logits; entries past the source's last class
+// are kPadLogit (see load_chunk).  `first` (warp-uniform): nothing accumulated yet, skip the rescale.
 // TOP2: also track the runner-up z (needed only for the near-tie report).
 // GK: also track zk[k][p], the running max of z over the classes that `lut` maps to target class k.
 template <int P, int CH, bool TOP2, bool GK, int K>
-MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const float (&a)[CH][P], int c0, int cn,
+MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const float (&a)[CH][P], int c0,
                             bool first, const uint8_t* __restrict__ lut, float (&zk)[K][P]) {
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -53,16 +57,14 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const f
         int i1 = st.amax[p];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            if (j < cn) {
-                // z exactly as the reference forms it: 0.5*a is exact in fp32, so the fused multiply-add
-                // rounds once, just like `pred + 0.5 * pred_aux`.
-                z[j] = fmaf(0.5f, a[j][p], m[j][p]);
-                cm = fmaxf(cm, m[j][p]);
-                ca = fmaxf(ca, a[j][p]);
-                if (TOP2) zr = fmaxf(zr, fminf(z1, z[j]));
-                i1 = (z[j] > z1) ? (c0 + j) : i1;      // strict >: lowest index wins ties, as np.argmax
-                z1 = fmaxf(z1, z[j]);
-            }
+            // z exactly as the reference forms it: 0.5*a is exact in fp32, so the fused multiply-add
+            // rounds once, just like `pred + 0.5 * pred_aux`.
+            z[j] = fmaf(0.5f, a[j][p], m[j][p]);
+            cm = fmaxf(cm, m[j][p]);
+            ca = fmaxf(ca, a[j][p]);
+            if (TOP2) zr = fmaxf(zr, fminf(z1, z[j]));
+            i1 = (z[j] > z1) ? (c0 + j) : i1;      // strict >: lowest index wins ties, as np.argmax
+            z1 = fmaxf(z1, z[j]);
         }
         const float nMm = fmaxf(st.Mm[p], cm), nMa = fmaxf(st.Ma[p], ca);
         float sm = 0.f, sa = 0.f, sz = 0.f, t = 0.f;
@@ -76,24 +78,19 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const f
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            if (j < cn) {
-                const float tm = m[j][p] - nMm, ta = a[j][p] - nMa;
-                const float em = exp_neg(tm);
-                sm += em;
-                t = fmaf(em, tm - ta, t);
-                sa += exp_neg(ta);
-                sz += exp_neg(z[j] - z1);
-            }
+            const float tm = m[j][p] - nMm, ta = a[j][p] - nMa;
+            const float em = exp_neg(tm);
+            sm += em;
+            t = fmaf(em, tm - ta, t);
+            sa += exp_neg(ta);
+            sz += exp_neg(z[j] - z1);
         }
         if (GK) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-                if (j < cn) {
-                    const int l = lut[c0 + j];          // warp-uniform
+                const int l = lut[c0 + j];          // warp-uniform; padded classes read table slack and carry kPadLogit
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        if (l == k) zk[k][p] = fmaxf(zk[k][p], z[j]);
-                }
+                for (int k = 1; k < K; ++k) zk[k][p] = fmaxf(zk[k][p], l == k ? z[j] : -INFINITY);
             }
         }
         st.Mm[p] = nMm; st.Ma[p] = nMa; st.Mz[p] = z1; st.z2[p] = zr; st.amax[p] = i1;
@@ -108,16 +105,29 @@ MSPL_DEVINL float kld_of(const SourceStats<P>& st, int p) {
     return st.T[p] / st.Sm[p] - logf(st.Sm[p]) + logf(st.Sa[p]);
 }
 
-// Load P pixels of CH class planes of both heads (classes c0..c0+cn-1; cn warp-uniform).
+template <int P>
+MSPL_DEVINL void fill_pad(float (&v)[P]) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) v[p] = kPadLogit;
+}
+
+// Load P pixels of CH class planes of both heads (classes c0..c0+cn-1; cn warp-uniform); a tail chunk (cn < CH) is
+// padded with kPadLogit.  Full chunks take the predicate-free path.
 template <int P, int CH>
 MSPL_DEVINL void load_chunk(const float* __restrict__ pm, const float* __restrict__ pa, int64_t hw, int cn,
                             float (&m)[CH][P], float (&a)[CH][P]) {
+    if (cn == CH) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-        if (j < cn) PixVec<P>::load(pm + j * hw, m[j]);
+        for (int j = 0; j < CH; ++j) PixVec<P>::load(pm + j * hw, m[j]);
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-        if (j < cn) PixVec<P>::load(pa + j * hw, a[j]);
+        for (int j = 0; j < CH; ++j) PixVec<P>::load(pa + j * hw, a[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            if (j < cn) { PixVec<P>::load(pm + j * hw, m[j]); PixVec<P>::load(pa + j * hw, a[j]); }
+            else { fill_pad<P>(m[j]); fill_pad<P>(a[j]); }
+        }
+    }
 }
 
 }  // namespace mspl

@@ -123,6 +123,9 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
     ncls = (ctypes.c_int * S)(*cls)
     lut_ptrs = (vp * S)(*[ctypes.addressof(b) for b in lut_bufs])
     lib = _lib.load()
+    if n == 0:      # nothing to label: empty maps, untouched histograms
+        return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
+                          marginal if count_marginal else None)
     with torch.cuda.device(dev):
         st = lib.mspl_fuse_sources(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, n, hw, num_classes, pol, vt,
                                    ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,

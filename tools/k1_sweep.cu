@@ -1,0 +1,180 @@
+// tools/k1_sweep -- times variants of the fused K1 kernel (direct-load and TMA-staged) on synthetic logits.
+// Development tool, not part of the library: prints one line per variant with ms, algorithmic GB/s (313 B/pixel for the
+// 13/20/5-class configuration) and a checksum of the outputs so that variants can be compared for equality.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../mspl_b200/csrc/fuse_launch.cuh"
+
+using namespace mspl;
+
+__global__ void fill_logits(float* main_l, float* aux_l, int64_t n, uint32_t seed, int C, int64_t hw) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)(i * 2654435761u) ^ seed;
+        float acc = 0.f, acc2 = 0.f;
+        for (int r = 0; r < 4; ++r) {          // sum of uniforms ~ normal
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+            acc += (x & 0xffff) * (1.0f / 65536.0f) - 0.5f;
+            acc2 += (x >> 16) * (1.0f / 65536.0f) - 0.5f;
+        }
+        const int c = (int)((i / hw) % C);
+        const float m = 3.0f * 1.7320508f * acc + 1.5f * ((c * 7 + 3) % 5 - 2);   // class bias -> non-uniform labels
+        main_l[i] = m;
+        aux_l[i] = m + 1.5f * 1.7320508f * acc2;
+    }
+}
+
+__global__ void checksum_kernel(const uint8_t* label, const float* conf, const float* unc, int64_t n, unsigned long long* out) {
+    unsigned long long a = 0, b = 0, c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        a += label[i] * (unsigned long long)((i % 1021) + 1);
+        b += __float_as_uint(conf[i]) >> 8;
+        c += __float_as_uint(unc[i]) >> 12;
+    }
+    atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c);
+}
+
+struct Bench {
+    FuseParams prm;
+    int64_t npix;
+    unsigned long long* d_stats;   // class_hist[8], marginal, conf_hist[8*2048], checksum[3]
+    int reps;
+};
+
+template <typename F>
+static void run_variant(const char* name, Bench& b, F launch) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const size_t stats_bytes = sizeof(unsigned long long) * (8 + 8 + 8 * 2048 + 8);
+    cudaMemset(b.d_stats, 0, stats_bytes);
+    int rc = launch();
+    cudaError_t err = cudaDeviceSynchronize();
+    if (rc != 0 || err != cudaSuccess) {
+        printf("%-44s FAILED rc=%d cuda=%s\n", name, rc, cudaGetErrorString(err));
+        cudaGetLastError();
+        return;
+    }
+    unsigned long long h[16];
+    checksum_kernel<<<592, 256>>>(b.prm.label, b.prm.conf, b.prm.unc, b.npix, b.d_stats + 16 + 8 * 2048);
+    cudaMemcpy(h, b.d_stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
+    unsigned long long cs[3];
+    cudaMemcpy(cs, b.d_stats + 16 + 8 * 2048, sizeof(cs), cudaMemcpyDeviceToHost);
+    launch();
+    float best = 1e30f, sum = 0.f;
+    for (int r = 0; r < b.reps; ++r) {
+        cudaEventRecord(e0);
+        launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+        sum += ms;
+    }
+    const double bytes = (double)b.npix * 313.0;
+    printf("%-44s min %8.3f ms  mean %8.3f ms  %7.1f GB/s (min)  frac6455 %.3f  | hist %llu %llu %llu %llu %llu marg %llu cs %llx %llx %llx\n", name, best,
+           sum / b.reps, bytes / 1e6 / best, bytes / 1e6 / best / 6455.6, h[0], h[1], h[2], h[3], h[4], h[8], cs[0], cs[1], cs[2]);
+    fflush(stdout);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+#define DIRECT(P, CH, THREADS, MINB, GK, TOP2)                                                                                   \
+    if (want(#P "," #CH "," #THREADS "," #MINB, "direct"))                                                                      \
+    run_variant("direct P=" #P " CH=" #CH " thr=" #THREADS " minb=" #MINB " gk=" #GK " top2=" #TOP2, b, [&] {                  \
+        return launch_fuse_direct<P, THREADS>(fuse_sources_direct_kernel<P, CH, 5, GK, TOP2, THREADS, MINB>, b.prm, 0);         \
+    })
+#define TMA(NCW, P, CH, NST, GK, TOP2)                                                                                           \
+    if (want(#NCW "," #P "," #CH "," #NST, "tma")) {                                                                             \
+        using Cfg = TmaCfg<NCW, P, CH, NST>;                                                                                     \
+        if (tma_eligible<Cfg>(b.prm))                                                                                            \
+            run_variant("tma ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST " gk=" #GK " top2=" #TOP2, b, [&] {                \
+                return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<NCW, P, CH, NST, 5, GK, TOP2>, b.prm, 0);                   \
+            });                                                                                                                  \
+    }
+
+static const char* g_filter = nullptr;
+static bool want(const char* key, const char* family) {
+    if (!g_filter) return true;
+    return strstr(g_filter, family) != nullptr || strstr(g_filter, key) != nullptr;
+}
+
+int main(int argc, char** argv) {
+    int64_t n_img = 400, H = 256, W = 480;
+    int reps = 5, vote_t = 3, policy = MSPL_POLICY_VOTE;
+    bool hist = true;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--images")) n_img = atoll(argv[++i]);
+        else if (!strcmp(argv[i], "--reps")) reps = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--hw")) { H = atoll(argv[++i]); W = atoll(argv[++i]); }
+        else if (!strcmp(argv[i], "--vote")) vote_t = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--prob")) policy = MSPL_POLICY_PROB;
+        else if (!strcmp(argv[i], "--nohist")) hist = false;
+        else if (!strcmp(argv[i], "--only")) g_filter = argv[++i];
+    }
+    const int C[3] = {13, 20, 5};
+    const uint8_t luts[3][20] = {{4, 2, 2, 3, 3, 1, 2, 2, 2, 4, 4, 2, 4},
+                                 {3, 3, 2, 2, 2, 2, 2, 2, 1, 3, 4, 4, 4, 2, 2, 2, 2, 2, 2, 4},
+                                 {3, 1, 1, 2, 2}};
+    const int64_t hw = H * W, npix = n_img * hw;
+    Bench b;
+    memset(&b.prm, 0, sizeof(b.prm));
+    b.npix = npix;
+    b.reps = reps;
+    for (int s = 0; s < 3; ++s) {
+        float *m, *a;
+        const int64_t cnt = npix * C[s];
+        if (cudaMalloc(&m, cnt * 4) != cudaSuccess || cudaMalloc(&a, cnt * 4) != cudaSuccess) { printf("alloc failed\n"); return 1; }
+        fill_logits<<<148 * 8, 256>>>(m, a, cnt, 0x9e3779b9u * (s + 1), C[s], hw);
+        b.prm.main[s] = m; b.prm.aux[s] = a; b.prm.C[s] = C[s];
+        memcpy(b.prm.lut[s], luts[s], C[s]);
+    }
+    cudaMalloc(&b.prm.label, npix);
+    cudaMalloc(&b.prm.conf, npix * 4);
+    cudaMalloc(&b.prm.unc, npix * 4);
+    cudaMalloc(&b.d_stats, sizeof(unsigned long long) * (8 + 8 + 8 * 2048 + 8));
+    b.prm.S = 3; b.prm.K = 5; b.prm.policy = policy; b.prm.vote_t = vote_t; b.prm.ignore = 4; b.prm.ds_rate = 1;
+    b.prm.n_img = n_img; b.prm.hw = hw;
+    b.prm.class_hist = b.d_stats; b.prm.marginal = b.d_stats + 8; b.prm.conf_hist = hist ? b.d_stats + 16 : nullptr;
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("init failed\n"); return 1; }
+    const bool gk = policy == MSPL_POLICY_PROB || vote_t < 3;
+    printf("# k1_sweep: %lld images %lldx%lld, 3 sources 13/20/5, policy=%d vote_t=%d gk=%d hist=%d, %.2f GB of logits\n", (long long)n_img,
+           (long long)W, (long long)H, policy, vote_t, (int)gk, (int)hist, npix * 304.0 / 1e9);
+    if (!gk) {
+        DIRECT(4, 5, 256, 2, false, true);
+        DIRECT(4, 5, 256, 1, false, true);
+        DIRECT(4, 5, 128, 4, false, true);
+        DIRECT(4, 4, 256, 2, false, true);
+        DIRECT(2, 5, 256, 3, false, true);
+        DIRECT(2, 5, 256, 4, false, true);
+        DIRECT(2, 10, 256, 2, false, true);
+        DIRECT(1, 5, 256, 4, false, true);
+        DIRECT(1, 10, 256, 4, false, true);
+        DIRECT(4, 5, 256, 2, false, false);
+        TMA(8, 4, 5, 4, false, true);
+        TMA(8, 2, 5, 8, false, true);
+        TMA(16, 2, 5, 4, false, true);
+        TMA(16, 1, 5, 8, false, true);
+        TMA(12, 2, 5, 5, false, true);
+        TMA(8, 4, 4, 5, false, true);
+        TMA(16, 2, 4, 5, false, true);
+        TMA(8, 4, 10, 2, false, true);
+        TMA(16, 2, 10, 2, false, true);
+        TMA(20, 2, 5, 3, false, true);
+        TMA(24, 2, 5, 2, false, true);
+        TMA(24, 1, 5, 5, false, true);
+        TMA(30, 1, 5, 4, false, true);
+        TMA(16, 2, 5, 4, false, false);
+        TMA(8, 4, 5, 4, false, false);
+    } else {
+        DIRECT(4, 5, 256, 1, true, true);
+        DIRECT(2, 5, 256, 2, true, true);
+        DIRECT(1, 5, 256, 3, true, true);
+        TMA(8, 4, 5, 4, true, true);
+        TMA(16, 2, 5, 4, true, true);
+        TMA(16, 1, 5, 8, true, true);
+    }
+    return 0;
+}
