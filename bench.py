@@ -78,7 +78,8 @@ def make_logits_host(torch, n, h, w, seed, pin):
 
 # ---- clocks during the timed region (B200_PROFILING.md) ---------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from process start; stop(t0, t1) keeps the samples taken inside the timed region."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -87,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -98,30 +99,37 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:      # very short timed region: widen to the neighbouring samples and say so
+            inside = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.1]
+            window = "timed region +-0.25 s (region shorter than 3 samples)"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({nm for r in inside for nm in r[4]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "power_w_max": max((r[3] for r in inside), default=None), "samples": len(inside), "window": window,
+                "reasons": reasons}
 
 
 def hbm_peak():
@@ -222,6 +230,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     n, h, w = args.images_per_gpu, args.height, args.width
     pix_local = n * h * w
     luts = [SOURCE_TABLES[s] for s, _ in SOURCES]
@@ -260,16 +271,15 @@ def main():
     barrier()
     k1_events.clear()
     launches0 = gen.launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     t0.record()
     for _ in range(args.steps):
         job = gen.run(mains, auxs)
     t1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     k1_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k1_events) / max(1, len(k1_events))], device=dev)
     if world > 1:

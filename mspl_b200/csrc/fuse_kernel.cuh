@@ -57,37 +57,45 @@ struct PixelFusion {
         }
     }
 
-    // fold one finished source in; d receives its KLD map values
-    MSPL_DEVINL void add_source(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P]) {
+    // fold one finished source in; d receives its KLD map values.  gm/ga: this thread's first pixel, class 0, of the
+    // source's two heads in global memory (only touched on the degenerate slow path).
+    MSPL_DEVINL void add_source(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P],
+                                const float* __restrict__ gm, const float* __restrict__ ga, int C, int64_t hw) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            d[p] = kld_of<P>(st, p);
-            usum[p] += d[p];
-            const float pmax = 1.0f / st.Sz[p];
-            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * pmax < kNearTieMargin;
+            SourceResult r = finish_source<P>(st, p);
+            if (r.degenerate) {
+                r.rz = st.Mz[p];
+                r.inv_sz = r.pmax = recompute_pmax(gm + p, ga + p, C, hw, st.Mz[p]);
+            }
+            d[p] = r.kld;
+            usum[p] += r.kld;
+            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
             const int lab = s_lut_s[st.amax[p]];
             votes[p] += 1u << (4 * lab);
             if (GK) {
 #pragma unroll
                 for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
-                    Fk[k][p] += exp_neg(zk[k][p] - st.Mz[p]) * pmax;
+                    Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
             } else {
-                csum[p] += pmax;
+                csum[p] += r.pmax;
             }
         }
     }
 
-    MSPL_DEVINL void finish(const FuseParams& prm, float fS, int (&label)[P], float (&conf)[P], float (&unc)[P]) {
+    // inv_s = 1/S: the averages over sources are formed as sum * (1/S) (one rounding away from the sum / S the
+    // definition states; far inside the 1e-5 tolerance) to keep IEEE division sequences out of the hot loop
+    MSPL_DEVINL void finish(const FuseParams& prm, float inv_s, int (&label)[P], float (&conf)[P], float (&unc)[P]) {
         const int ignore = prm.ignore;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            unc[p] = usum[p] / fS;
+            unc[p] = usum[p] * inv_s;
             if (prm.policy == MSPL_POLICY_PROB) {
                 float best = -1.f, second = -1.f;
                 int bk = 0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float f = GK ? Fk[GK ? k : 0][p] / fS : 0.f;
+                    const float f = GK ? Fk[GK ? k : 0][p] * inv_s : 0.f;
                     second = fmaxf(second, fminf(best, f));
                     bk = (f > best) ? k : bk;
                     best = fmaxf(best, f);
@@ -110,7 +118,7 @@ struct PixelFusion {
 #pragma unroll
                     for (int k = 0; k < K; ++k) f = (label[p] == k) ? Fk[GK ? k : 0][p] : f;
                 }
-                conf[p] = (label[p] == ignore) ? 0.f : f / fS;
+                conf[p] = (label[p] == ignore) ? 0.f : f * inv_s;
             }
         }
     }
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(cons
     __syncthreads();
 
     const int S = prm.S;
-    const float fS = (float)S;
+    const float fS = 1.0f / (float)S;
     const int64_t hw = prm.hw;
     const int64_t gpi = hw / P;                       // pixel groups per image
     const int64_t n_groups = prm.n_img * gpi;
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(cons
                 fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
             }
             float d[P];
-            fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
+            fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d, pm, pa, C, hw);
             if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
         }
         int label[P];
@@ -253,7 +261,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(cons
 
 // ======================================================================================================================
 // TMA (bulk async copy) staged kernel.
-//   CTA = NCW consumer warps + 1 producer warp.  A tile is TP = NCW*32*P consecutive pixels of one image (hw % TP == 0).
+//   CTA = NCW consumer warps + 1 producer warp.  A tile is up to TP = NCW*32*P consecutive pixels of one image (the
+//   last tile of an image may be shorter; hw % 4 == 0 keeps every row copy a multiple of 16 bytes).
 //   A stage holds one chunk of up to CH classes of both heads for the tile: [2][CH][TP] floats; the producer fills stages
 //   in the order (tile, source, chunk) with one cp.async.bulk per class row, completion signalled on the stage's "full"
 //   mbarrier (complete_tx::bytes); a consumer warp copies its pixels' values to registers, releases the stage ("empty"
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
 
     const int S = prm.S;
     const int64_t hw = prm.hw;
-    const int64_t tpi = hw / TP;                       // tiles per image
+    const int64_t tpi = (hw + TP - 1) / TP;            // tiles per image (the last one may be partial)
     const int64_t n_tiles = prm.n_img * tpi;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Tally<KT> tally;
@@ -354,6 +363,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t n = tile / tpi;
             const int64_t off = (tile - n * tpi) * TP;
+            const uint32_t row_bytes = (uint32_t)((hw - off < TP ? hw - off : TP) * sizeof(float));
             for (int s = 0; s < S; ++s) {
                 const int C = prm.C[s];
                 const float* pm = prm.main[s] + (n * C) * hw + off;
@@ -362,12 +372,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                     const int cn = min(CH, C - c0);
                     tma::mbar_wait(&empty[stage], phase ^ 1);          // all consumers released this slot
                     float* dst = ring + (size_t)stage * Cfg::kStageFloats;
-                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 * cn * TP * sizeof(float)));
+                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);
                     __syncwarp();
                     for (int j = lane; j < 2 * cn; j += 32) {
                         const int head = j >= cn, c = head ? j - cn : j;
                         const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
-                        tma::bulk_g2s(dst + (head * CH + c) * TP, src, TP * sizeof(float), &full[stage], policy);
+                        tma::bulk_g2s(dst + (head * CH + c) * TP, src, row_bytes, &full[stage], policy);
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -375,13 +385,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
         }
     } else {
         // ------------------------------- consumer warps -------------------------------
-        const float fS = (float)S;
+        const float fS = 1.0f / (float)S;
         int stage = 0;
         uint32_t phase = 0;
         const int px = (warp * 32 + lane) * P;          // this thread's first pixel inside the tile
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t n = tile / tpi;
             const int64_t off = (tile - n * tpi) * TP + px;
+            const bool active = off < hw;                 // partial last tile: the ring holds stale values past the image
             PixelFusion<P, KT, GK, TOP2> fus;
             fus.reset();
             for (int s = 0; s < S; ++s) {
@@ -413,17 +424,20 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                     fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
                 }
                 float d[P];
-                fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
-                if (prm.kld[s] != nullptr) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+                const int64_t goff = (n * C) * hw + (active ? off : 0);
+                fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d, prm.main[s] + goff, prm.aux[s] + goff, C, hw);
+                if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
             }
             int label[P];
             float conf[P], unc[P];
             fus.finish(prm, fS, label, conf, unc);
-            const int64_t o = n * hw + off;
-            store_labels<P>(prm.label + o, label);
-            if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
-            if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
-            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, true);
+            if (active) {
+                const int64_t o = n * hw + off;
+                store_labels<P>(prm.label + o, label);
+                if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
+                if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
+            }
+            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
         }
     }
     tally.flush(prm, s_hist, s_cls, Cfg::kThreads);

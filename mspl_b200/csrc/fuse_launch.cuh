@@ -45,15 +45,15 @@ int launch_fuse_tma(Kern kern, const FuseParams& prm, cudaStream_t stream) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
-    const int64_t n_tiles = prm.n_img * (prm.hw / Cfg::kTilePix);
+    const int64_t n_tiles = prm.n_img * ((prm.hw + Cfg::kTilePix - 1) / Cfg::kTilePix);
     kern<<<(unsigned)(n_tiles < di.sms ? n_tiles : di.sms), Cfg::kThreads, smem, stream>>>(prm);
     return launch_status();
 }
 
-// The bulk-copy path needs whole tiles and 16-byte aligned rows.
+// The bulk-copy path needs 16-byte aligned class rows (bases 16-byte aligned, pixels_per_image % 4 == 0).
 template <typename Cfg>
 bool tma_eligible(const FuseParams& prm) {
-    if (prm.hw % Cfg::kTilePix != 0) return false;
+    if (prm.hw % 4 != 0) return false;
     for (int s = 0; s < prm.S; ++s)
         if (!aligned_to(prm.main[s], 16) || !aligned_to(prm.aux[s], 16) || (prm.kld[s] && !aligned_to(prm.kld[s], 16))) return false;
     return aligned_to(prm.label, 4) && (!prm.conf || aligned_to(prm.conf, 16)) && (!prm.unc || aligned_to(prm.unc, 16));

@@ -14,13 +14,13 @@ namespace mspl {
 #define MSPL_FUSE_MINB 2      // direct kernel: resident CTAs per SM the register allocator must leave room for
 #endif
 #ifndef MSPL_TMA_NCW
-#define MSPL_TMA_NCW 8        // TMA kernel: consumer warps per CTA
+#define MSPL_TMA_NCW 16       // TMA kernel: consumer warps per CTA
 #endif
 #ifndef MSPL_TMA_P
-#define MSPL_TMA_P 4          // TMA kernel: pixels per consumer thread
+#define MSPL_TMA_P 2          // TMA kernel: pixels per consumer thread
 #endif
 #ifndef MSPL_TMA_STAGES
-#define MSPL_TMA_STAGES 4     // TMA kernel: ring depth
+#define MSPL_TMA_STAGES 4     // TMA kernel: ring depth (stage = 2 heads x CH classes x 1024 pixels x 4 B = 40 KB)
 #endif
 #ifndef MSPL_USE_TMA
 #define MSPL_USE_TMA 1
@@ -46,7 +46,7 @@ template <int KT>
 static int dispatch_fuse(const FuseParams& prm, int P, bool gk, cudaStream_t stream) {
     using Cfg = TmaCfg<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES>;
     if (MSPL_USE_TMA && P == 4 && tma_eligible<Cfg>(prm)) return dispatch_tma<KT>(prm, gk, stream);
-    return P == 4 ? dispatch_direct<4, KT>(prm, gk, stream) : dispatch_direct<1, KT>(prm, gk, stream);
+    return dispatch_direct<1, KT>(prm, gk, stream);   // odd shapes / unaligned views: scalar streaming loads
 }
 
 // merge_outputs (uest_seg_multi_os.py:695-718) on (S, npix) hard labels.
@@ -75,7 +75,7 @@ using namespace mspl;
 extern "C" const char* mspl_fuse_variant(void) {
     static char name[192];
     if (MSPL_USE_TMA)
-        snprintf(name, sizeof(name), "tma-bulk ring: consumer warps=%d P=%d CH=%d stages=%d (direct-ldg fallback: P=4|1 CH=%d minblocks=%d)",
+        snprintf(name, sizeof(name), "tma-bulk ring: consumer warps=%d P=%d CH=%d stages=%d (direct-ldg fallback for unaligned shapes: P=1 CH=%d minblocks=%d)",
                  MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, MSPL_FUSE_CH, MSPL_FUSE_MINB);
     else
         snprintf(name, sizeof(name), "direct-ldg128 P=4 CH=%d threads=%d minblocks=%d", MSPL_FUSE_CH, kDirectThreads, MSPL_FUSE_MINB);

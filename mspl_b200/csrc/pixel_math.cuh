@@ -18,12 +18,40 @@
 namespace mspl {
 
 // e^t for t <= 0 (t already max-subtracted, so the largest term is exactly e^0 = 1): FMUL + MUFU.EX2.
-MSPL_DEVINL float exp_neg(float t) {
+MSPL_DEVINL float ex2_approx(float x) {
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t * kLog2e));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+MSPL_DEVINL float exp_neg(float t) { return ex2_approx(t * kLog2e); }
+MSPL_DEVINL float exp_half_neg(float t) { return ex2_approx(t * (0.5f * kLog2e)); }   // e^{t/2}
+// natural log through MUFU.LG2 (absolute error <= 2^-22.6 * |log2 x| * ln 2: ~5e-7 at worst for the ratios of softmax sums it
+// is used on, inside the 2e-6 KLD floor), instead of the ~20-instruction branchy logf
+MSPL_DEVINL float log_fast(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.6931471805599453f;
+}
+MSPL_DEVINL float max3(float a, float b, float c) {        // FMNMX3 (sm_100+)
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+template <int N>
+MSPL_DEVINL float max_of(const float (&v)[N], float init) {
+    float r = init;
+    int j = 0;
+#pragma unroll
+    for (; j + 1 < N; j += 2) r = max3(r, v[j], v[j + 1]);
+    if (j < N) r = fmaxf(r, v[j]);
     return r;
 }
 
+// Running per-pixel statistics of one source.
+//   Mm, Sm = sum e^{m-Mm}     Ma, Sa = sum e^{a-Ma}     T = sum e^{m-Mm} ((m-Mm) - (a-Ma))
+//   Mz = max z, z2 = runner-up z, amax = first index of the largest z
+//   Sz = sum e^{z - Rz} with the reference point Rz = Mm + Ma/2 (>= Mz): e^{z-Rz} = e^{m-Mm} * e^{(a-Ma)/2}, so the z-softmax
+//        costs no exponential of its own (two MUFU.EX2 per class instead of three).
 template <int P>
 struct SourceStats {
     float Mm[P], Sm[P], Ma[P], Sa[P], Mz[P], Sz[P], T[P], z2[P];
@@ -51,39 +79,38 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const f
                             bool first, const uint8_t* __restrict__ lut, float (&zk)[K][P]) {
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        float z[CH];
-        float cm = -INFINITY, ca = -INFINITY;
+        float z[CH], mv[CH], av[CH];
         float z1 = st.Mz[p], zr = st.z2[p];
         int i1 = st.amax[p];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
+            mv[j] = m[j][p];
+            av[j] = a[j][p];
             // z exactly as the reference forms it: 0.5*a is exact in fp32, so the fused multiply-add
             // rounds once, just like `pred + 0.5 * pred_aux`.
-            z[j] = fmaf(0.5f, a[j][p], m[j][p]);
-            cm = fmaxf(cm, m[j][p]);
-            ca = fmaxf(ca, a[j][p]);
+            z[j] = fmaf(0.5f, av[j], mv[j]);
             if (TOP2) zr = fmaxf(zr, fminf(z1, z[j]));
             i1 = (z[j] > z1) ? (c0 + j) : i1;      // strict >: lowest index wins ties, as np.argmax
             z1 = fmaxf(z1, z[j]);
         }
-        const float nMm = fmaxf(st.Mm[p], cm), nMa = fmaxf(st.Ma[p], ca);
+        const float nMm = max_of<CH>(mv, st.Mm[p]), nMa = max_of<CH>(av, st.Ma[p]);
         float sm = 0.f, sa = 0.f, sz = 0.f, t = 0.f;
-        if (!first) {   // rescale what earlier chunks accumulated to the new maxima (one exp per stream)
+        if (!first) {   // rescale what earlier chunks accumulated to the new maxima
             const float dm = st.Mm[p] - nMm, da = st.Ma[p] - nMa;
-            const float rm = exp_neg(dm);
+            const float rm = exp_neg(dm), rh = exp_half_neg(da);
             sm = st.Sm[p] * rm;
             t = rm * fmaf(st.Sm[p], dm - da, st.T[p]);
-            sa = st.Sa[p] * exp_neg(da);
-            sz = st.Sz[p] * exp_neg(st.Mz[p] - z1);
+            sa = st.Sa[p] * (rh * rh);
+            sz = st.Sz[p] * (rm * rh);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            const float tm = m[j][p] - nMm, ta = a[j][p] - nMa;
-            const float em = exp_neg(tm);
+            const float tm = mv[j] - nMm, ta = av[j] - nMa;
+            const float em = exp_neg(tm), h = exp_half_neg(ta);
             sm += em;
             t = fmaf(em, tm - ta, t);
-            sa += exp_neg(ta);
-            sz += exp_neg(z[j] - z1);
+            sa = fmaf(h, h, sa);
+            sz = fmaf(em, h, sz);
         }
         if (GK) {
 #pragma unroll
@@ -98,11 +125,33 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const f
     }
 }
 
-// KL(softmax(m) || softmax(a)) from the finished stats (IEEE division and accurate logf: the two log terms
-// cancel to O(KLD), so their absolute error is what bounds the 1e-5 relative agreement).
+// What the fusion needs from a finished source, per pixel.
+struct SourceResult {
+    float kld;      // KL(softmax(m) || softmax(a)) = T/Sm - log Sm + log Sa  (= sum_c p1 (logp1 - logp2), log_softmax taken as
+                    // (x - max) - log(sum) like ATen, so no large maxima are ever added back)
+    float rz;       // Rz = Mm + Ma/2, the reference point of Sz
+    float inv_sz;   // 1 / Sz:  softmax(z)_c = e^{z_c - Rz} * inv_sz
+    float pmax;     // probability of the argmax class = e^{Mz - Rz} * inv_sz
+    bool degenerate;  // the two heads disagree by > 64 logit units: Sz may underflow, caller must take the slow path
+};
+
 template <int P>
-MSPL_DEVINL float kld_of(const SourceStats<P>& st, int p) {
-    return st.T[p] / st.Sm[p] - logf(st.Sm[p]) + logf(st.Sa[p]);
+MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
+    SourceResult r;
+    const float inv_sm = __frcp_rn(st.Sm[p]);
+    r.kld = fmaf(st.T[p], inv_sm, log_fast(st.Sa[p] * inv_sm));
+    r.rz = fmaf(0.5f, st.Ma[p], st.Mm[p]);
+    r.inv_sz = __frcp_rn(st.Sz[p]);
+    r.pmax = exp_neg(st.Mz[p] - r.rz) * r.inv_sz;
+    r.degenerate = !(r.rz - st.Mz[p] <= 64.f);      // Sz >= e^-64 otherwise: no underflow, full precision
+    return r;
+}
+
+// Slow path for a degenerate pixel: recompute 1/sum_c e^{z_c - Mz} directly from global memory (rare; divergent).
+MSPL_DEVINL float recompute_pmax(const float* __restrict__ pm, const float* __restrict__ pa, int C, int64_t hw, float Mz) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += exp_neg(fmaf(0.5f, __ldg(pa + c * hw), __ldg(pm + c * hw)) - Mz);
+    return __frcp_rn(s);
 }
 
 template <int P>

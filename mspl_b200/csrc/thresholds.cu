@@ -14,8 +14,51 @@ struct RadixState {            // one per target class, caller-zeroed before pas
 
 constexpr int kHistThreads = 256;
 
+// VEC consecutive (label, conf) pairs: VEC = 16 -> one 16-byte label load + four 16-byte conf loads in flight per thread
+// (80 B/thread/iteration), VEC = 4 -> uchar4 + float4, VEC = 1 -> scalars.
+template <int VEC>
+MSPL_DEVINL void load_label_conf(const uint8_t* __restrict__ label, const float* __restrict__ conf, int64_t i0, uint8_t (&l)[VEC],
+                                 float (&c)[VEC]) {
+    if (VEC == 16) {
+        const uint4 lv = __ldcs(reinterpret_cast<const uint4*>(label + i0));
+        float4 cv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cv[q] = __ldcs(reinterpret_cast<const float4*>(conf + i0) + q);
+        const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) l[(q * 4 + b) % VEC] = (uint8_t)(lw[q] >> (8 * b));
+            c[(q * 4 + 0) % VEC] = cv[q].x; c[(q * 4 + 1) % VEC] = cv[q].y; c[(q * 4 + 2) % VEC] = cv[q].z; c[(q * 4 + 3) % VEC] = cv[q].w;
+        }
+    } else if (VEC == 4) {
+        const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
+        const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
+        l[0] = lv.x; l[1 % VEC] = lv.y; l[2 % VEC] = lv.z; l[3 % VEC] = lv.w;
+        c[0] = cv.x; c[1 % VEC] = cv.y; c[2 % VEC] = cv.z; c[3 % VEC] = cv.w;
+    } else {
+        l[0] = label[i0];
+        c[0] = conf[i0];
+    }
+}
+
+template <int VEC>
+MSPL_DEVINL void store_bytes(uint8_t* __restrict__ dst, int64_t i0, const uint8_t (&v)[VEC]) {
+    if (VEC == 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            w[q] = (uint32_t)v[(q * 4) % VEC] | ((uint32_t)v[(q * 4 + 1) % VEC] << 8) | ((uint32_t)v[(q * 4 + 2) % VEC] << 16) |
+                   ((uint32_t)v[(q * 4 + 3) % VEC] << 24);
+        __stcs(reinterpret_cast<uint4*>(dst + i0), make_uint4(w[0], w[1], w[2], w[3]));
+    } else if (VEC == 4) {
+        *reinterpret_cast<uchar4*>(dst + i0) = make_uchar4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    } else {
+        dst[i0] = v[0];
+    }
+}
+
 // Histogram of the `pass`-th digit of the conf keys whose higher bits equal the class's resolved prefix.
-// VEC = 4: uchar4 + float4 loads (5 B/pixel streamed once).
 template <int VEC>
 __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
                                                                   int64_t npix, int64_t hw, int K, int pass,
@@ -31,20 +74,18 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
         s_done[threadIdx.x] = state[threadIdx.x].done;
     }
     __syncthreads();
+    // conf == +0 is by far the most common duplicate (every ignore-labelled pixel of the vote policies): those are counted
+    // in registers (8 bits per class, spilled before overflow) instead of hammering one shared-memory address
+    const uint32_t zero_key = float_to_key(0.f);
+    unsigned long long zpacked = 0;
+    uint32_t zcnt[MSPL_MAX_CLASSES] = {};
+    int pending = 0;
     const int64_t n_groups = (npix + VEC - 1) / VEC;
     for (int64_t g = blockIdx.x * (int64_t)kHistThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kHistThreads) {
         const int64_t i0 = g * VEC;
         uint8_t l[VEC];
         float c[VEC];
-        if (VEC == 4) {
-            const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
-            const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
-            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
-            c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
-        } else {
-            l[0] = label[i0];
-            c[0] = conf[i0];
-        }
+        load_label_conf<VEC>(label, conf, i0, l, c);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int64_t i = i0 + v;
@@ -52,8 +93,21 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
             if (ds_rate > 1 && ((i % hw) % ds_rate) != 0) continue;
             const uint32_t key = float_to_key(c[v]);
             if (radix_prefix(key, pass) != s_prefix[l[v]]) continue;
-            atomicAdd(&s_hist[l[v] * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
+            if (key == zero_key) zpacked += 1ull << (8 * l[v]);
+            else atomicAdd(&s_hist[l[v] * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
         }
+        if ((pending += VEC) > 255 - VEC) {
+#pragma unroll
+            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) zcnt[k] += (uint32_t)(zpacked >> (8 * k)) & 0xffu;
+            zpacked = 0;
+            pending = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
+        zcnt[k] += (uint32_t)(zpacked >> (8 * k)) & 0xffu;
+        const uint32_t w = __reduce_add_sync(0xffffffffu, zcnt[k]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[k * MSPL_RADIX_BINS + radix_digit(zero_key, pass)], w);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += kHistThreads)
@@ -129,39 +183,34 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
     }
     __syncthreads();
     uint32_t cnt[MSPL_MAX_CLASSES] = {};
+    unsigned long long packed = 0;          // 8 bits per class, spilled into cnt[] before it can overflow
+    int pending = 0;
     const int64_t n_groups = (npix + VEC - 1) / VEC;
     for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
         const int64_t i0 = g * VEC;
         uint8_t l[VEC], f[VEC], mk[VEC];
         float c[VEC];
-        if (VEC == 4) {
-            const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
-            const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
-            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
-            c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
-        } else {
-            l[0] = label[i0];
-            c[0] = conf[i0];
-        }
+        load_label_conf<VEC>(label, conf, i0, l, c);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const bool keep = l[v] < K && l[v] != ignore && c[v] >= s_thresh[l[v]];
             f[v] = keep ? l[v] : (uint8_t)ignore;
             mk[v] = keep ? 0 : 1;
+            packed += 1ull << (8 * f[v]);
+        }
+        if ((pending += VEC) > 255 - VEC) {
 #pragma unroll
-            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (f[v] == k);
+            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+            packed = 0;
+            pending = 0;
         }
-        if (VEC == 4) {
-            *reinterpret_cast<uchar4*>(final_label + i0) = make_uchar4(f[0], f[1], f[2], f[3]);
-            if (ignore_mask) *reinterpret_cast<uchar4*>(ignore_mask + i0) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
-        } else {
-            final_label[i0] = f[0];
-            if (ignore_mask) ignore_mask[i0] = mk[0];
-        }
+        store_bytes<VEC>(final_label, i0, f);
+        if (ignore_mask) store_bytes<VEC>(ignore_mask, i0, mk);
     }
     if (final_hist) {
 #pragma unroll
         for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
+            cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
             const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[k]);
             if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cls[k], w);
         }
@@ -194,13 +243,14 @@ extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int
     if (num_pixels == 0) return MSPL_OK;
     const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool vec = (num_pixels % 4 == 0) && aligned_to(label, 4) && aligned_to(conf, 16);
-    auto kern = vec ? radix_hist_kernel<4> : radix_hist_kernel<1>;
+    const int vec = (num_pixels % 16 == 0 && aligned_to(label, 16) && aligned_to(conf, 16)) ? 16
+                    : (num_pixels % 4 == 0 && aligned_to(label, 4) && aligned_to(conf, 16)) ? 4 : 1;
+    auto kern = vec == 16 ? radix_hist_kernel<16> : vec == 4 ? radix_hist_kernel<4> : radix_hist_kernel<1>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
-    const int64_t grid = stream_grid((num_pixels + (vec ? 3 : 0)) / (vec ? 4 : 1), kHistThreads, 4);
+    const int64_t grid = stream_grid(num_pixels / vec, kHistThreads, 4);
     kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K, pass,
                                                      static_cast<const RadixState*>(state), hist, ds_rate);
     return launch_status();
@@ -222,14 +272,19 @@ extern "C" int mspl_apply_thresholds(const uint8_t* label, const float* conf, co
                                      unsigned long long* final_hist, void* stream) {
     const int K = num_target_classes;
     if (!label || !conf || !thresh || !final_label || num_pixels < 0) return MSPL_ERR_BAD_ARG;
-    if (K < 1 || K > MSPL_MAX_CLASSES || ignore_label < 0 || ignore_label > 255) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ignore_label < 0 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
     if (!aligned_to(conf, 4) || !aligned_to(thresh, 4) || (final_hist && !aligned_to(final_hist, 8))) return MSPL_ERR_ALIGN;
     if (num_pixels == 0) return MSPL_OK;
-    const bool vec = (num_pixels % 4 == 0) && aligned_to(label, 4) && aligned_to(conf, 16) && aligned_to(final_label, 4) &&
-                     (!ignore_mask || aligned_to(ignore_mask, 4));
+    auto ok = [&](size_t a) {
+        return aligned_to(label, a) && aligned_to(conf, 16) && aligned_to(final_label, a) && (!ignore_mask || aligned_to(ignore_mask, a));
+    };
+    const int vec = (num_pixels % 16 == 0 && ok(16)) ? 16 : (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t grid = stream_grid(vec ? num_pixels / 4 : num_pixels, 256, 8);
-    if (vec)
+    const int64_t grid = stream_grid(num_pixels / vec, 256, 8);
+    if (vec == 16)
+        apply_thresholds_kernel<16><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
+                                                                   ignore_mask, final_hist);
+    else if (vec == 4)
         apply_thresholds_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
                                                                   ignore_mask, final_hist);
     else

@@ -1,0 +1,90 @@
+"""CPU stand-in for mspl_b200.ops built on the oracle -- lets the host-side sharding / all-reduce logic of
+mspl_b200.pipeline.LabelGenerator run under gloo without a GPU.  Test infrastructure only."""
+import numpy as np
+import torch
+
+from oracle import mspl_oracle as O
+from mspl_b200.ops import FuseResult, vote_threshold  # noqa: F401  (pure-Python helpers, no CUDA needed)
+
+RADIX_BINS = 2048
+
+
+def _keys(conf):
+    b = conf.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (b & 0x80000000) != 0
+    return torch.where(neg, (~b) & 0xFFFFFFFF, b | 0x80000000)
+
+
+def _digit(keys, p):
+    return (keys >> 21) if p == 0 else ((keys >> 10) & 0x7FF) if p == 1 else (keys & 0x3FF)
+
+
+def _prefix(keys, p):
+    return torch.zeros_like(keys) if p == 0 else (keys >> 21) if p == 1 else (keys >> 10)
+
+
+def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4, ds_rate=1, want_conf=True, want_unc=True,
+                 want_kld=False, want_conf_hist=True, count_marginal=True, class_hist=None, conf_hist=None, marginal=None,
+                 label_out=None, conf_out=None, unc_out=None):
+    r = O.fuse_sources(mains, auxs, luts, policy, num_classes, ignore_label)
+    h, w = r["label"].shape[-2:]
+    ch = r["class_hist"].clone() if class_hist is None else class_hist.add_(r["class_hist"])
+    hist = None
+    if want_conf_hist:
+        keep = (torch.arange(h * w) % ds_rate == 0).reshape(h, w).expand(r["label"].shape)
+        idx = r["label"].long()[keep] * RADIX_BINS + _digit(_keys(r["conf"]), 0)[keep]
+        hist = torch.bincount(idx, minlength=num_classes * RADIX_BINS).reshape(num_classes, RADIX_BINS)
+        if conf_hist is not None:
+            hist = conf_hist.add_(hist)
+    marg = r["marginal"].sum()
+    if marginal is not None:
+        marg = marginal.add_(marg)
+    return FuseResult(r["label"], r["conf"], r["unc"], r["kld"] if want_kld else None, ch, hist, marg)
+
+
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None):
+    """3-pass radix select written with torch ops (independent of the CUDA implementation)."""
+    h, w = label.shape[-2:]
+    keep = (torch.arange(h * w) % ds_rate == 0).reshape(h, w).expand(label.shape)
+    keys, lab = _keys(conf)[keep], label.long()[keep]
+    K = num_classes
+    rank = torch.zeros(K, dtype=torch.int64)
+    prefix = torch.zeros(K, dtype=torch.int64)
+    done = torch.zeros(K, dtype=torch.bool)
+    thresh = torch.ones(K, dtype=torch.float32)
+    kept = torch.zeros(K, dtype=torch.int64)
+    for p in range(3):
+        if p == 0 and conf_hist is not None:
+            hist = conf_hist
+        else:
+            sel = (_prefix(keys, p) == prefix[lab]) & ~done[lab]
+            hist = torch.bincount(lab[sel] * RADIX_BINS + _digit(keys, p)[sel], minlength=K * RADIX_BINS).reshape(K, RADIX_BINS)
+        if all_reduce is not None:
+            all_reduce(hist)
+        for k in range(K):
+            if p == 0:
+                kept[k] = hist[k].sum()
+                rank[k] = int(int(kept[k]) * float(portion))
+                done[k] = rank[k] == 0
+            if done[k]:
+                continue
+            above = torch.flip(torch.cumsum(torch.flip(hist[k], [0]), 0), [0])      # above[d] = sum_{i >= d}
+            d = int((above >= rank[k]).nonzero().max())
+            rank[k] -= int(above[d]) - int(hist[k][d])
+            prefix[k] = (prefix[k] << (10 if p == 2 else 11)) | d
+            if p == 2:
+                key = int(prefix[k])
+                bits = (key & 0x7FFFFFFF) if key & 0x80000000 else (~key) & 0xFFFFFFFF
+                thresh[k] = torch.tensor([bits], dtype=torch.int64).to(torch.int32).view(torch.float32)[0] if bits < 2 ** 31 else \
+                    torch.tensor([bits - 2 ** 32], dtype=torch.int64).to(torch.int32).view(torch.float32)[0]
+        if hasattr(hist, "zero_"):
+            hist.zero_()
+    return thresh, kept
+
+
+def apply_thresholds(label, conf, thresh, ignore_label=4, want_mask=True, final_hist=None):
+    final, mask = O.apply_thresholds(label, conf, thresh, ignore_label)
+    hist = torch.bincount(final.reshape(-1).long(), minlength=thresh.numel())
+    if final_hist is not None:
+        hist = final_hist.add_(hist)
+    return final, (mask if want_mask else None), hist

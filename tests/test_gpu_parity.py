@@ -183,6 +183,31 @@ def test_misaligned_views_fall_back_to_scalar(ops, dev):
     assert not bool(((r.label.cpu() != ref["label"]) & ~ref["marginal"]).any())
 
 
+def test_extreme_head_disagreement_slow_path(ops, dev):
+    """main and aux heads disagree by ~200 logit units: the shared-exponential form of softmax(z) underflows and the
+    kernel must take its per-pixel recompute path; results still match the oracle."""
+    n, h, w = 2, 16, 40
+    gen = torch.Generator().manual_seed(12)
+    mains, auxs = [], []
+    for nm, c in SOURCES:
+        im = torch.randint(0, c, (n, 1, h, w), generator=gen)
+        ia = torch.randint(0, c, (n, 1, h, w), generator=gen)
+        m = torch.full((n, c, h, w), -100.0).scatter_(1, im, 100.0) + torch.randn(n, c, h, w, generator=gen)
+        a = torch.full((n, c, h, w), -100.0).scatter_(1, ia, 100.0) + torch.randn(n, c, h, w, generator=gen)
+        mains.append(m.contiguous()), auxs.append(a.contiguous())
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    for policy in ("half", "all", "prob"):
+        r = _fuse(ops, dev, mains, auxs, luts, policy, want_kld=True)
+        assert torch.isfinite(r.conf).all() and torch.isfinite(r.unc).all()
+        ref = O.fuse_sources(mains, auxs, luts, policy)
+        lab = r.label.cpu()
+        diff = lab != ref["label"]
+        assert not bool((diff & ~ref["marginal"]).any())
+        torch.testing.assert_close(r.conf.cpu()[~diff], ref["conf"][~diff], rtol=RTOL, atol=1e-7)
+        for got, want in zip(r.kld, ref["kld"]):
+            torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=KLD_ATOL)
+
+
 def test_empty_batch(ops, dev):
     m = torch.zeros(0, 5, 8, 8, device=dev)
     r = ops.fuse_sources([m], [m.clone()], [O.ID_FOREST_TO_GREENHOUSE])
