@@ -14,24 +14,14 @@ struct RadixState {            // one per target class, caller-zeroed before pas
 
 constexpr int kHistThreads = 256;
 
-// VEC consecutive (label, conf) pairs: VEC = 16 -> one 16-byte label load + four 16-byte conf loads in flight per thread
-// (80 B/thread/iteration), VEC = 4 -> uchar4 + float4, VEC = 1 -> scalars.
+// VEC consecutive (label, conf) pairs per load: VEC = 4 -> uchar4 + float4 (a warp reads 128 B of labels and 512 B of conf,
+// both contiguous), VEC = 1 -> scalars.  Kernels keep kUnroll such groups in flight per thread, one block-stride apart.
+constexpr int kUnroll = 4;
+
 template <int VEC>
 MSPL_DEVINL void load_label_conf(const uint8_t* __restrict__ label, const float* __restrict__ conf, int64_t i0, uint8_t (&l)[VEC],
                                  float (&c)[VEC]) {
-    if (VEC == 16) {
-        const uint4 lv = __ldcs(reinterpret_cast<const uint4*>(label + i0));
-        float4 cv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cv[q] = __ldcs(reinterpret_cast<const float4*>(conf + i0) + q);
-        const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) l[(q * 4 + b) % VEC] = (uint8_t)(lw[q] >> (8 * b));
-            c[(q * 4 + 0) % VEC] = cv[q].x; c[(q * 4 + 1) % VEC] = cv[q].y; c[(q * 4 + 2) % VEC] = cv[q].z; c[(q * 4 + 3) % VEC] = cv[q].w;
-        }
-    } else if (VEC == 4) {
+    if (VEC == 4) {
         const uchar4 lv = __ldcs(reinterpret_cast<const uchar4*>(label + i0));
         const float4 cv = __ldcs(reinterpret_cast<const float4*>(conf + i0));
         l[0] = lv.x; l[1 % VEC] = lv.y; l[2 % VEC] = lv.z; l[3 % VEC] = lv.w;
@@ -44,21 +34,10 @@ MSPL_DEVINL void load_label_conf(const uint8_t* __restrict__ label, const float*
 
 template <int VEC>
 MSPL_DEVINL void store_bytes(uint8_t* __restrict__ dst, int64_t i0, const uint8_t (&v)[VEC]) {
-    if (VEC == 16) {
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            w[q] = (uint32_t)v[(q * 4) % VEC] | ((uint32_t)v[(q * 4 + 1) % VEC] << 8) | ((uint32_t)v[(q * 4 + 2) % VEC] << 16) |
-                   ((uint32_t)v[(q * 4 + 3) % VEC] << 24);
-        __stcs(reinterpret_cast<uint4*>(dst + i0), make_uint4(w[0], w[1], w[2], w[3]));
-    } else if (VEC == 4) {
-        *reinterpret_cast<uchar4*>(dst + i0) = make_uchar4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-    } else {
-        dst[i0] = v[0];
-    }
+    if (VEC == 4) *reinterpret_cast<uchar4*>(dst + i0) = make_uchar4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    else dst[i0] = v[0];
 }
 
-// Histogram of the `pass`-th digit of the conf keys whose higher bits equal the class's resolved prefix.
 template <int VEC>
 __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
                                                                   int64_t npix, int64_t hw, int K, int pass,
@@ -81,22 +60,34 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
     uint32_t zcnt[MSPL_MAX_CLASSES] = {};
     int pending = 0;
     const int64_t n_groups = (npix + VEC - 1) / VEC;
-    for (int64_t g = blockIdx.x * (int64_t)kHistThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kHistThreads) {
-        const int64_t i0 = g * VEC;
-        uint8_t l[VEC];
-        float c[VEC];
-        load_label_conf<VEC>(label, conf, i0, l, c);
+    for (int64_t g0 = blockIdx.x * (int64_t)(kHistThreads * kUnroll) + threadIdx.x; g0 < n_groups;
+         g0 += (int64_t)gridDim.x * kHistThreads * kUnroll) {
+        uint8_t l[kUnroll][VEC];
+        float c[kUnroll][VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const int64_t i = i0 + v;
-            if (l[v] >= K || s_done[l[v]]) continue;
-            if (ds_rate > 1 && ((i % hw) % ds_rate) != 0) continue;
-            const uint32_t key = float_to_key(c[v]);
-            if (radix_prefix(key, pass) != s_prefix[l[v]]) continue;
-            if (key == zero_key) zpacked += 1ull << (8 * l[v]);
-            else atomicAdd(&s_hist[l[v] * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * kHistThreads;
+            if (g < n_groups) load_label_conf<VEC>(label, conf, g * VEC, l[u], c[u]);
+            else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) l[u][v] = 255;
+            }
         }
-        if ((pending += VEC) > 255 - VEC) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int64_t i = (g0 + u * kHistThreads) * VEC + v;
+                const uint32_t lab = l[u][v];
+                if (lab >= (uint32_t)K || s_done[lab]) continue;
+                if (ds_rate > 1 && ((i % hw) % ds_rate) != 0) continue;
+                const uint32_t key = float_to_key(c[u][v]);
+                if (radix_prefix(key, pass) != s_prefix[lab]) continue;
+                if (key == zero_key) zpacked += 1ull << (8 * lab);
+                else atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
+            }
+        }
+        if ((pending += VEC * kUnroll) > 255 - VEC * kUnroll) {
 #pragma unroll
             for (int k = 0; k < MSPL_MAX_CLASSES; ++k) zcnt[k] += (uint32_t)(zpacked >> (8 * k)) & 0xffu;
             zpacked = 0;
@@ -186,26 +177,35 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
     unsigned long long packed = 0;          // 8 bits per class, spilled into cnt[] before it can overflow
     int pending = 0;
     const int64_t n_groups = (npix + VEC - 1) / VEC;
-    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
-        const int64_t i0 = g * VEC;
-        uint8_t l[VEC], f[VEC], mk[VEC];
-        float c[VEC];
-        load_label_conf<VEC>(label, conf, i0, l, c);
+    for (int64_t g0 = blockIdx.x * (int64_t)(256 * kUnroll) + threadIdx.x; g0 < n_groups; g0 += (int64_t)gridDim.x * 256 * kUnroll) {
+        uint8_t l[kUnroll][VEC];
+        float c[kUnroll][VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const bool keep = l[v] < K && l[v] != ignore && c[v] >= s_thresh[l[v]];
-            f[v] = keep ? l[v] : (uint8_t)ignore;
-            mk[v] = keep ? 0 : 1;
-            packed += 1ull << (8 * f[v]);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (g < n_groups) load_label_conf<VEC>(label, conf, g * VEC, l[u], c[u]);
         }
-        if ((pending += VEC) > 255 - VEC) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (g >= n_groups) break;
+            uint8_t f[VEC], mk[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const bool keep = l[u][v] < K && l[u][v] != ignore && c[u][v] >= s_thresh[l[u][v]];
+                f[v] = keep ? l[u][v] : (uint8_t)ignore;
+                mk[v] = keep ? 0 : 1;
+                packed += 1ull << (8 * f[v]);
+            }
+            store_bytes<VEC>(final_label, g * VEC, f);
+            if (ignore_mask) store_bytes<VEC>(ignore_mask, g * VEC, mk);
+        }
+        if ((pending += VEC * kUnroll) > 255 - VEC * kUnroll) {
 #pragma unroll
             for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
             packed = 0;
             pending = 0;
         }
-        store_bytes<VEC>(final_label, i0, f);
-        if (ignore_mask) store_bytes<VEC>(ignore_mask, i0, mk);
     }
     if (final_hist) {
 #pragma unroll
@@ -243,14 +243,13 @@ extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int
     if (num_pixels == 0) return MSPL_OK;
     const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int vec = (num_pixels % 16 == 0 && aligned_to(label, 16) && aligned_to(conf, 16)) ? 16
-                    : (num_pixels % 4 == 0 && aligned_to(label, 4) && aligned_to(conf, 16)) ? 4 : 1;
-    auto kern = vec == 16 ? radix_hist_kernel<16> : vec == 4 ? radix_hist_kernel<4> : radix_hist_kernel<1>;
+    const int vec = (num_pixels % 4 == 0 && aligned_to(label, 4) && aligned_to(conf, 16)) ? 4 : 1;
+    auto kern = vec == 4 ? radix_hist_kernel<4> : radix_hist_kernel<1>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
-    const int64_t grid = stream_grid(num_pixels / vec, kHistThreads, 4);
+    const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, kHistThreads, 4);
     kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K, pass,
                                                      static_cast<const RadixState*>(state), hist, ds_rate);
     return launch_status();
@@ -278,13 +277,10 @@ extern "C" int mspl_apply_thresholds(const uint8_t* label, const float* conf, co
     auto ok = [&](size_t a) {
         return aligned_to(label, a) && aligned_to(conf, 16) && aligned_to(final_label, a) && (!ignore_mask || aligned_to(ignore_mask, a));
     };
-    const int vec = (num_pixels % 16 == 0 && ok(16)) ? 16 : (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
+    const int vec = (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t grid = stream_grid(num_pixels / vec, 256, 8);
-    if (vec == 16)
-        apply_thresholds_kernel<16><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
-                                                                   ignore_mask, final_hist);
-    else if (vec == 4)
+    const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, 256, 8);
+    if (vec == 4)
         apply_thresholds_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
                                                                   ignore_mask, final_hist);
     else

@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
             const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off));
             const longlong2 t1 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off) + 1);
             t[0] = t0.x; t[1] = t0.y; t[P > 2 ? 2 : 0] = t1.x; t[P > 3 ? 3 : 0] = t1.y;
+        } else if (P == 2) {
+            const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off));
+            t[0] = t0.x; t[P > 1 ? 1 : 0] = t0.y;
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) t[p] = __ldcs(target + n * hw + off + p);
@@ -114,12 +117,12 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
                 em[k] = exp_neg(m[k][p] - Mm); ea[k] = exp_neg(a[k][p] - Ma); ez[k] = exp_neg(z[k] - Mz);
                 Sm += em[k]; Sa += ea[k]; Sz += ez[k];
             }
-            const float lSm = logf(Sm), lSa = logf(Sa), lSz = logf(Sz);
-            const float rSm = 1.0f / Sm, rSa = 1.0f / Sa, rSz = 1.0f / Sz;
+            const float rSm = __frcp_rn(Sm), rSa = __frcp_rn(Sa), rSz = __frcp_rn(Sz);
+            const float lRatio = log_fast(Sm * rSa), lSz = log_fast(Sz);     // log Sm - log Sa, log Sz
             float dl[K], D = 0.f;                    // dl_k = log p1_k - log p2_k
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                dl[k] = ((m[k][p] - Mm) - lSm) - ((a[k][p] - Ma) - lSa);
+                dl[k] = ((m[k][p] - Mm) - (a[k][p] - Ma)) - lRatio;
                 D = fmaf(em[k] * rSm, dl[k], D);
             }
             const int ti = (int)t[p];
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
                 zt = (valid && ti == k) ? z[k] : zt;
             }
             const float ce = wt * (lSz - (zt - Mz));
-            const float eD = expf(-D);
+            const float eD = exp_neg(-D);
             const float l = ce * eD;
             ce_sum += l;
             d_sum += D;
@@ -341,13 +344,21 @@ static int64_t persistent_grid(int64_t n_groups, int threads, int per_sm, int64_
     return blocks < 1 ? 1 : (blocks < lim ? blocks : lim);
 }
 
+// Pixels per thread when rows are 16-byte aligned, picked on B200 (profiles/r01_loss_variants.txt): the backward keeps
+// 2*K*P gradient registers live, so it wants the narrower P=2 (77% of the measured HBM peak vs 68% at P=4); the
+// forward-only kernel is best at P=4 (76% vs 63%).
+constexpr int kLossCtasPerSm = 4;
+
 template <int K>
 static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, int64_t hw,
                         float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
-    const int64_t grid = persistent_grid(n * (hw / P), kLossThreads, 4, kMaxLossBlocks);
+    const int pv = P == 4 ? (bwd ? 2 : 4) : 1;
+    const int64_t grid = persistent_grid(n * (hw / pv), kLossThreads, kLossCtasPerSm, kMaxLossBlocks);
 #define MSPL_UWCE(PP, BB) uw_ce_fused_kernel<PP, K, BB><<<(unsigned)grid, kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws)
-    if (P == 4) { if (bwd) MSPL_UWCE(4, true); else MSPL_UWCE(4, false); }
-    else        { if (bwd) MSPL_UWCE(1, true); else MSPL_UWCE(1, false); }
+    if (pv == 4) MSPL_UWCE(4, false);
+    else if (pv == 2) MSPL_UWCE(2, true);
+    else if (bwd) MSPL_UWCE(1, true);
+    else MSPL_UWCE(1, false);
 #undef MSPL_UWCE
     return launch_status();
 }

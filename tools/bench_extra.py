@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Secondary measurements (BASELINE.json configs 4 and 5 and the non-headline policies), one JSON line each.
+Not the driver's bench (that is /bench.py); run on a B200:  python tools/bench_extra.py [--quick]
+
+  loss_b64 / loss_b8 : K4 fused uncertainty-weighted CE forward+backward, K=5, 480x256 (config 4: batch 64, and the
+                       8-per-GPU share of it under 8-way data parallelism), 88 algorithmic B/pixel
+  loss_modules_b64   : the same loss through the reference-named modules (PixelwiseKLD + UncertaintyWeighted... + autograd)
+  stress_1024x512    : config 5, 3 sources x 20 classes at 1024x512 (495 B/pixel incl. thresholds), one GPU's share
+  policy_half / prob : K1 with per-class probabilities (vote threshold below S / probability fusion)
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mspl_b200 import ops  # noqa: E402
+from mspl_b200.data_loader.segmentation.greenhouse import SOURCE_TABLES  # noqa: E402
+from mspl_b200.loss_fns.segmentation_loss import PixelwiseKLD, UncertaintyWeightedSegmentationLoss  # noqa: E402
+from mspl_b200.pipeline import LabelGenerator  # noqa: E402
+
+PEAK = 6455.6
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, iters, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()                      # > L2 bytes written between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2], ms[0]
+
+
+def report(name, pix, bytes_per_pix, med, best, **extra):
+    line = {"name": name, "Mpix/s": round(pix / 1e6 / (med / 1e3), 1), "ms_median": round(med, 4), "ms_min": round(best, 4),
+            "GB/s": round(pix * bytes_per_pix / 1e9 / (med / 1e3), 1), "frac_of_measured_hbm_peak": round(pix * bytes_per_pix / 1e9 / (med / 1e3) / PEAK, 4),
+            "algorithmic_bytes_per_pixel": bytes_per_pix}
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def logits(n, c, h, w, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    m = 3 * torch.randn((n, c, h, w), device=dev, generator=g) + 3 * torch.randn((n, c, 1, 1), device=dev, generator=g)
+    a = m + 1.5 * torch.randn((n, c, h, w), device=dev, generator=g)
+    return m, a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress"))
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    iters = 5 if args.quick else 20
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # 256 MB > 126 MB L2
+    h, w, k = 256, 480, 5
+
+    # ---- config 4: loss ------------------------------------------------------------------------------------------
+    for b in ((64, 8) if args.section in ("all", "loss") else ()):
+        main_l, aux_l = logits(b, k, h, w, dev, 11)
+        target = torch.randint(1, 5, (b, h, w), device=dev)
+        cw = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], device=dev)
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw), iters, flush=flush)
+        report("loss_b%d_fused_fwd_bwd" % b, b * h * w, 88, med, best, launches_per_step=1)
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw, backward=False), iters, flush=flush)
+        report("loss_b%d_fused_fwd_only" % b, b * h * w, 48, med, best, launches_per_step=1)
+        if b == 64 and args.section == "all":
+            crit = UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=4, device=dev)
+            kld_layer = PixelwiseKLD()
+
+            def modules():
+                p, q = main_l.clone().requires_grad_(True), aux_l.clone().requires_grad_(True)
+                kld = kld_layer(p, q)
+                loss = crit(p + 0.5 * q, target, kld) * 20 + kld.mean()
+                loss.backward()
+            med, best = timed(modules, iters, flush=flush)
+            report("loss_b64_reference_named_modules_autograd", b * h * w, 88, med, best,
+                   note="PixelwiseKLD + UncertaintyWeightedSegmentationLoss kernels + torch glue (clone, add, mul, mean, autograd)")
+
+            def torch_eager():
+                import torch.nn.functional as F
+                p, q = main_l.clone().requires_grad_(True), aux_l.clone().requires_grad_(True)
+                p1, lp1, lp2 = F.softmax(p, 1), F.log_softmax(p, 1), F.log_softmax(q, 1)
+                kld = (p1 * lp1 - p1 * lp2).sum(1)
+                lp = -F.log_softmax(p + 0.5 * q, 1) * cw.reshape(1, -1, 1, 1)
+                loss = (lp.gather(1, target.view(b, 1, h, w)) * torch.exp(-kld.reshape(b, 1, h, w))).mean() * 20 + kld.mean()
+                loss.backward()
+            med, best = timed(torch_eager, max(3, iters // 4), flush=flush)
+            report("loss_b64_torch_eager_cuda_for_context", b * h * w, 88, med, best,
+                   note="the reference's op sequence run by PyTorch eager on this GPU (not a CPU baseline)")
+        del main_l, aux_l, target
+
+    if args.section == "loss":
+        return
+    # ---- non-headline policies on the 13/20/5 configuration -----------------------------------------------------------
+    n = 100 if args.quick else 400
+    srcs = (("camvid", 13), ("cityscapes", 20), ("forest", 5))
+    mains, auxs = zip(*[logits(n, c, h, w, dev, 3 + i) for i, (_, c) in enumerate(srcs)])
+    luts = [SOURCE_TABLES[s] for s, _ in srcs]
+    for policy in ("all", "half", "prob"):
+        med, best = timed(lambda: ops.fuse_sources(list(mains), list(auxs), luts, policy=policy), iters)
+        report("k1_policy_%s_%dimg" % (policy, n), n * h * w, 313, med, best)
+    gen = LabelGenerator(luts, policy="all")
+    med, best = timed(lambda: gen.run(list(mains), list(auxs)), iters)
+    report("labelgen_all_thresholds_%dimg" % n, n * h * w, 319, med, best)
+    del mains, auxs
+
+    # ---- config 5: stress ---------------------------------------------------------------------------------------------
+    hs, ws = 512, 1024
+    ns = 16 if args.quick else 64
+    mains, auxs = zip(*[logits(ns, 20, hs, ws, dev, 30 + i) for i in range(3)])
+    luts = [SOURCE_TABLES["cityscapes"]] * 3
+    med, best = timed(lambda: ops.fuse_sources(list(mains), list(auxs), luts, policy="all"), iters)
+    report("stress_1024x512_3x20cls_k1_%dimg" % ns, ns * hs * ws, 489, med, best)
+    gen = LabelGenerator(luts, policy="all")
+    med, best = timed(lambda: gen.run(list(mains), list(auxs)), iters)
+    report("stress_1024x512_3x20cls_labelgen_%dimg" % ns, ns * hs * ws, 495, med, best)
+
+
+if __name__ == "__main__":
+    main()
