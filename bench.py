@@ -193,14 +193,14 @@ def run_reference(args):
     val = round(mpix / el, 3)
     sample = ("%d synthetic %dx%d images x 3 sources per step (bounded sample of configs[1]), oracle port of the reference CPU "
               "path; /root/reference is pure Python and cannot travel to the GPU box" % (n, args.width, args.height))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "pseudo-labelled Mpix/s (3-source fusion)", "value": val, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.images_per_gpu),
         "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 def workload_config(args, images_per_gpu):
@@ -211,8 +211,28 @@ def workload_config(args, images_per_gpu):
             "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (images_per_gpu * args.height * args.width * 304 / 1e9)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, torchrun notices) to stderr, so that stdout
+    carries exactly ONE line: the JSON result written by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -338,7 +358,7 @@ def main():
                         "class_hist": job.class_hist.tolist(), "final_hist": job.final_hist.tolist(),
                         "thresholds": [round(x, 6) for x in job.thresh.tolist()] if job.thresh is not None else None, "kept": kept},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,127 @@
+"""-m gpu: the reference-named generators (generate_pseudo_label[_multi_model]) end to end with stand-in source models
+and an in-memory loader: PNG label maps, tgt_train.lst and class weights against the oracle's restatement of the
+reference loop (uest_seg_multi_os.py:888-950)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import mspl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SOURCES = (("camvid", 13), ("cityscapes", 20), ("forest", 5))
+N, H, W = 5, 32, 48
+
+
+class TinySource(torch.nn.Module):
+    """A deterministic 'segmentation network' with a main and an auxiliary head (tuple output, like ESPDNetUE)."""
+
+    def __init__(self, classes, seed, as_dict=False):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.main = torch.nn.Conv2d(3, classes, 3, padding=1)
+        self.aux = torch.nn.Conv2d(3, classes, 3, padding=1)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 2.0)
+        self.as_dict = as_dict
+
+    def forward(self, x):
+        m, a = self.main(x), self.aux(x)
+        return {"out": m, "aux": a} if self.as_dict else (m, a)
+
+
+def _loader():
+    g = torch.Generator().manual_seed(21)
+    for i in range(N):
+        image = torch.randn(1, 3, H, W, generator=g)
+        yield image, torch.zeros(1, H, W, dtype=torch.long), ["/tmp/dataset/greenhouse/color/img_%03d.png" % i], torch.zeros(1)
+
+
+def _args(**kw):
+    a = types.SimpleNamespace(classes=5, use_depth=False, eval_training=False, class_weighting='normal',
+                              merge_label_policy='half', dataset='greenhouse')
+    a.__dict__.update(kw)
+    return a
+
+
+def _oracle_run(models, names, policy):
+    mains, auxs = [], []
+    images = torch.cat([b[0] for b in _loader()])
+    with torch.no_grad():
+        for m in models:
+            out = m.cpu()(images)
+            pm, pa = (out["out"], out["aux"]) if isinstance(out, dict) else out
+            mains.append(pm.contiguous()), auxs.append(pa.contiguous())
+    luts = [O.LUTS[n] for n in names]
+    labels, class_array = O.multi_source_labels(mains, auxs, luts, policy)
+    marg = O.fuse_sources(mains, auxs, luts, policy)["marginal"].numpy()
+    return labels, class_array, marg
+
+
+@pytest.mark.parametrize("policy", ["half", "all", 2])
+def test_generate_pseudo_label_multi_model(tmp_path, policy):
+    from mspl_b200 import uest_seg_multi_os as U
+    models = [TinySource(c, 5 + i, as_dict=(i == 1)) for i, (_, c) in enumerate(SOURCES)]
+    names = [n for n, _ in SOURCES]
+    want, class_array, marg = _oracle_run(models, names, policy)
+    lst, cw = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', str(tmp_path), 0, N, None, None,
+                                                  _args(merge_label_policy=policy), None, None, None, testloader=_loader(),
+                                                  batch_images=2)
+    assert lst == os.path.join(str(tmp_path), 'tgt_train.lst')
+    rows = [ln.strip().split(',') for ln in open(lst)]
+    assert len(rows) == N
+    n_diff = 0
+    for i, (img_path, lab_path) in enumerate(rows):
+        assert img_path == "/tmp/dataset/greenhouse/color/img_%03d.png" % i
+        assert lab_path == os.path.join(str(tmp_path), 'pred', 'img_%03d.png' % i)
+        got = np.array(Image.open(lab_path))
+        assert got.dtype == np.uint8 and got.shape == (H, W)
+        diff = got != want[i]
+        assert not (diff & ~marg[i]).any()
+        n_diff += int(diff.sum())
+    assert cw.is_cuda and cw.dtype == torch.float32 and cw.shape == (5,)
+    if n_diff == 0:
+        torch.testing.assert_close(cw.cpu(), O.class_weights_from_histogram(class_array, 'normal'))
+    assert cw[0].item() == 0.0
+
+
+def test_generate_pseudo_label_single_model(tmp_path):
+    """--label-update rounds: the target model's own 5-class argmax, no table, no vote (uest_seg_multi_os.py:730-829)."""
+    from mspl_b200 import uest_seg_multi_os as U
+    model = TinySource(5, 77)
+    images = torch.cat([b[0] for b in _loader()])
+    with torch.no_grad():
+        pm, pa = model(images)
+    lst, cw = U.generate_pseudo_label(model, 'cuda:0', str(tmp_path), 1, N, None, None, _args(class_weighting='flat'), None,
+                                      None, None, testloader=_loader(), batch_images=3)
+    P = torch.softmax(pm + 0.5 * pa, dim=1)
+    want = P.argmax(dim=1).numpy().astype(np.uint8)
+    top2 = torch.topk(P, 2, dim=1).values
+    marg = ((top2[:, 0] - top2[:, 1]) < 1e-6).numpy()
+    for i, ln in enumerate(open(lst)):
+        got = np.array(Image.open(ln.strip().split(',')[1]))
+        assert not ((got != want[i]) & ~marg[i]).any()
+    assert torch.equal(cw.cpu(), torch.ones(5))
+
+
+def test_generate_with_class_balanced_thresholds(tmp_path):
+    """[NEW] stage switched on: labels below their class threshold become the ignore class; kept fraction ~ portion."""
+    from mspl_b200 import uest_seg_multi_os as U
+    models = [TinySource(c, 5 + i) for i, (_, c) in enumerate(SOURCES)]
+    names = [n for n, _ in SOURCES]
+    base, _, _ = _oracle_run(models, names, 'half')
+    lst, _ = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', str(tmp_path), 0, N, None, None,
+                                                 _args(cb_thresholds=True, init_tgt_port=0.3, ds_rate=1), None, None, None,
+                                                 testloader=_loader(), batch_images=2)
+    got = np.stack([np.array(Image.open(ln.strip().split(',')[1])) for ln in open(lst)])
+    changed = got != base
+    assert (got[changed] == 4).all()
+    for k in (1, 2, 3):
+        nk = int((base == k).sum())
+        if nk >= 50:
+            assert abs(int((got == k).sum()) - int(nk * 0.3)) <= max(3, nk // 50)
