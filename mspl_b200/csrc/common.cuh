@@ -56,8 +56,8 @@ MSPL_DEVINL float exp_shifted(float x, float Ml) { return exp2f(fmaf(x, kLog2e, 
 
 // Order-preserving map fp32 -> u32 (larger float <=> larger key) and back; used by the radix select.
 MSPL_DEVINL uint32_t float_to_key(float f) {
-    uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);      // negative: flip all bits; else set the sign bit
 }
 MSPL_DEVINL float key_to_float(uint32_t k) {
     uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;

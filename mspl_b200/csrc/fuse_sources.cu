@@ -13,40 +13,30 @@ namespace mspl {
 #ifndef MSPL_FUSE_MINB
 #define MSPL_FUSE_MINB 2      // direct kernel: resident CTAs per SM the register allocator must leave room for
 #endif
-#ifndef MSPL_TMA_NCW
-#define MSPL_TMA_NCW 16       // TMA kernel: consumer warps per CTA
-#endif
-#ifndef MSPL_TMA_P
-#define MSPL_TMA_P 2          // TMA kernel: pixels per consumer thread
-#endif
-#ifndef MSPL_TMA_STAGES
-#define MSPL_TMA_STAGES 4     // TMA kernel: ring depth (stage = 2 heads x CH classes x 1024 pixels x 4 B = 40 KB)
-#endif
 #ifndef MSPL_USE_TMA
 #define MSPL_USE_TMA 1
 #endif
 
+// TMA-staged kernel configurations <consumer warps, pixels per thread, classes per chunk, ring stages>, picked from the
+// tools/k1_sweep runs on B200 (profiles/r01_k1_sweep_*.txt):
+//   vote with threshold == S ('all', or a single source): HBM-bound; 15 consumer + 1 producer warps = 16 warps, so the
+//     register file splits evenly (128 regs/thread); 960-pixel tiles, 4 x 38.4 KB stages            -> 99 % of the copy peak
+//   policies that need per-target-class probabilities ('half', int < S, 'prob'): ~25 % more instructions per pixel, so
+//     more consumer warps win; 19 + 1 = 20 warps (96 regs/thread), 1216-pixel tiles, 3 x 48.6 KB stages -> 80 %
+using TmaCfgVoteAll = TmaCfg<15, 2, MSPL_FUSE_CH, 4>;
+using TmaCfgPerClass = TmaCfg<19, 2, MSPL_FUSE_CH, 3>;
 constexpr int kDirectThreads = 256;
-
-template <int P, int KT>
-static int dispatch_direct(const FuseParams& prm, bool gk, cudaStream_t stream) {
-    constexpr int CH = MSPL_FUSE_CH, MB = MSPL_FUSE_MINB;
-    if (gk) return launch_fuse_direct<P, kDirectThreads>(fuse_sources_direct_kernel<P, CH, KT, true, true, kDirectThreads, 1>, prm, stream);
-    return launch_fuse_direct<P, kDirectThreads>(fuse_sources_direct_kernel<P, CH, KT, false, true, kDirectThreads, MB>, prm, stream);
-}
-
-template <int KT>
-static int dispatch_tma(const FuseParams& prm, bool gk, cudaStream_t stream) {
-    using Cfg = TmaCfg<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES>;
-    if (gk) return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, KT, true, true>, prm, stream);
-    return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, KT, false, true>, prm, stream);
-}
 
 template <int KT>
 static int dispatch_fuse(const FuseParams& prm, int P, bool gk, cudaStream_t stream) {
-    using Cfg = TmaCfg<MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES>;
-    if (MSPL_USE_TMA && P == 4 && tma_eligible<Cfg>(prm)) return dispatch_tma<KT>(prm, gk, stream);
-    return dispatch_direct<1, KT>(prm, gk, stream);   // odd shapes / unaligned views: scalar streaming loads
+    constexpr int CH = MSPL_FUSE_CH;
+    if (MSPL_USE_TMA && P == 4 && tma_eligible<TmaCfgVoteAll>(prm)) {
+        if (gk) return launch_fuse_tma<TmaCfgPerClass>(fuse_sources_tma_kernel<19, 2, CH, 3, KT, true, true>, prm, stream);
+        return launch_fuse_tma<TmaCfgVoteAll>(fuse_sources_tma_kernel<15, 2, CH, 4, KT, false, true>, prm, stream);
+    }
+    // odd shapes / unaligned views: per-thread scalar streaming loads, same math
+    if (gk) return launch_fuse_direct<1, kDirectThreads>(fuse_sources_direct_kernel<1, CH, KT, true, true, kDirectThreads, 1>, prm, stream);
+    return launch_fuse_direct<1, kDirectThreads>(fuse_sources_direct_kernel<1, CH, KT, false, true, kDirectThreads, MSPL_FUSE_MINB>, prm, stream);
 }
 
 // merge_outputs (uest_seg_multi_os.py:695-718) on (S, npix) hard labels.
@@ -73,12 +63,11 @@ __global__ void __launch_bounds__(256) vote_labels_kernel(const uint8_t* __restr
 using namespace mspl;
 
 extern "C" const char* mspl_fuse_variant(void) {
-    static char name[192];
-    if (MSPL_USE_TMA)
-        snprintf(name, sizeof(name), "tma-bulk ring: consumer warps=%d P=%d CH=%d stages=%d (direct-ldg fallback for unaligned shapes: P=1 CH=%d minblocks=%d)",
-                 MSPL_TMA_NCW, MSPL_TMA_P, MSPL_FUSE_CH, MSPL_TMA_STAGES, MSPL_FUSE_CH, MSPL_FUSE_MINB);
-    else
-        snprintf(name, sizeof(name), "direct-ldg128 P=4 CH=%d threads=%d minblocks=%d", MSPL_FUSE_CH, kDirectThreads, MSPL_FUSE_MINB);
+    static char name[224];
+    snprintf(name, sizeof(name),
+             "tma-bulk ring, CH=%d: vote-all <15 consumer warps, P=2, 4 stages>, per-class <19, P=2, 3 stages>; "
+             "direct-ldg P=1 fallback for unaligned shapes%s",
+             MSPL_FUSE_CH, MSPL_USE_TMA ? "" : " (TMA disabled at build time)");
     return name;
 }
 

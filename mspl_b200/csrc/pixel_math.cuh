@@ -112,16 +112,23 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const f
             sa = fmaf(h, h, sa);
             sz = fmaf(em, h, sz);
         }
-        if (GK) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int l = lut[c0 + j];          // warp-uniform; padded classes read table slack and carry kPadLogit
-#pragma unroll
-                for (int k = 1; k < K; ++k) zk[k][p] = fmaxf(zk[k][p], l == k ? z[j] : -INFINITY);
-            }
-        }
         st.Mm[p] = nMm; st.Ma[p] = nMa; st.Mz[p] = z1; st.z2[p] = zr; st.amax[p] = i1;
         st.Sm[p] = sm; st.Sa[p] = sa; st.Sz[p] = sz; st.T[p] = t;
+    }
+    if (GK) {
+        // class-major: the table entry is warp-uniform, so one uniform branch per class selects the target class whose
+        // running max takes this class's z (padded classes read table slack and carry kPadLogit: harmless)
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int l = lut[c0 + j];
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                if (l == k) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) zk[k][p] = fmaxf(zk[k][p], fmaf(0.5f, a[j][p], m[j][p]));
+                }
+            }
+        }
     }
 }
 

@@ -38,24 +38,26 @@ MSPL_DEVINL void store_bytes(uint8_t* __restrict__ dst, int64_t i0, const uint8_
     else dst[i0] = v[0];
 }
 
-template <int VEC>
+// Histogram of the PASS-th digit of the conf keys whose higher bits equal the class's resolved prefix.
+// Instruction-lean inner loop (5 B/pixel leaves ~25 issue slots per pixel at full HBM rate): one shared-memory lookup
+// per pixel returns the class's prefix, or an impossible value for classes that are done / out of range.
+template <int VEC, int PASS>
 __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
-                                                                  int64_t npix, int64_t hw, int K, int pass,
+                                                                  int64_t npix, int64_t hw, int K,
                                                                   const RadixState* __restrict__ state,
                                                                   unsigned long long* __restrict__ hist, int ds_rate) {
     extern __shared__ uint32_t s_hist[];
-    __shared__ uint32_t s_prefix[MSPL_MAX_CLASSES];
-    __shared__ uint32_t s_done[MSPL_MAX_CLASSES];
+    __shared__ uint32_t s_prefix[MSPL_MAX_CLASSES + 1];
     const int nbins = K * MSPL_RADIX_BINS;
     for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
-    if (threadIdx.x < K) {
-        s_prefix[threadIdx.x] = state[threadIdx.x].prefix;
-        s_done[threadIdx.x] = state[threadIdx.x].done;
+    if (threadIdx.x <= MSPL_MAX_CLASSES) {
+        const int k = threadIdx.x;
+        s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;    // no key prefix has all 32 bits set
     }
     __syncthreads();
     // conf == +0 is by far the most common duplicate (every ignore-labelled pixel of the vote policies): those are counted
     // in registers (8 bits per class, spilled before overflow) instead of hammering one shared-memory address
-    const uint32_t zero_key = float_to_key(0.f);
+    constexpr uint32_t zero_key = 0x80000000u;       // float_to_key(+0.f)
     unsigned long long zpacked = 0;
     uint32_t zcnt[MSPL_MAX_CLASSES] = {};
     int pending = 0;
@@ -77,14 +79,14 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
         for (int u = 0; u < kUnroll; ++u) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const int64_t i = (g0 + u * kHistThreads) * VEC + v;
-                const uint32_t lab = l[u][v];
-                if (lab >= (uint32_t)K || s_done[lab]) continue;
-                if (ds_rate > 1 && ((i % hw) % ds_rate) != 0) continue;
+                const uint32_t lab = min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES);
                 const uint32_t key = float_to_key(c[u][v]);
-                if (radix_prefix(key, pass) != s_prefix[lab]) continue;
-                if (key == zero_key) zpacked += 1ull << (8 * lab);
-                else atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, pass)], 1u);
+                bool match = radix_prefix(key, PASS) == s_prefix[lab];
+                if (ds_rate > 1) match = match && (((g0 + u * kHistThreads) * VEC + v) % hw) % ds_rate == 0;
+                if (match) {
+                    if (key == zero_key) zpacked += 1ull << (8 * lab);
+                    else atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, PASS)], 1u);
+                }
             }
         }
         if ((pending += VEC * kUnroll) > 255 - VEC * kUnroll) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
     for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
         zcnt[k] += (uint32_t)(zpacked >> (8 * k)) & 0xffu;
         const uint32_t w = __reduce_add_sync(0xffffffffu, zcnt[k]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[k * MSPL_RADIX_BINS + radix_digit(zero_key, pass)], w);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[k * MSPL_RADIX_BINS + radix_digit(zero_key, PASS)], w);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += kHistThreads)
@@ -166,11 +168,12 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
                                                                const float* __restrict__ thresh, int64_t npix, int K, int ignore,
                                                                uint8_t* __restrict__ final_label, uint8_t* __restrict__ ignore_mask,
                                                                unsigned long long* __restrict__ final_hist) {
-    __shared__ float s_thresh[MSPL_MAX_CLASSES];
+    __shared__ float s_thresh[MSPL_MAX_CLASSES + 1];    // +inf for the ignore class and for labels outside [0,K): never kept
     __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
-    if (threadIdx.x < MSPL_MAX_CLASSES) {
-        s_thresh[threadIdx.x] = threadIdx.x < K ? thresh[threadIdx.x] : INFINITY;
-        s_cls[threadIdx.x] = 0;
+    if (threadIdx.x <= MSPL_MAX_CLASSES) {
+        const int k = threadIdx.x;
+        s_thresh[k] = (k < K && k != ignore) ? thresh[k] : INFINITY;
+        if (k < MSPL_MAX_CLASSES) s_cls[k] = 0;
     }
     __syncthreads();
     uint32_t cnt[MSPL_MAX_CLASSES] = {};
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
             uint8_t f[VEC], mk[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const bool keep = l[u][v] < K && l[u][v] != ignore && c[u][v] >= s_thresh[l[u][v]];
+                const bool keep = c[u][v] >= s_thresh[min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES)];
                 f[v] = keep ? l[u][v] : (uint8_t)ignore;
                 mk[v] = keep ? 0 : 1;
                 packed += 1ull << (8 * f[v]);
@@ -244,13 +247,14 @@ extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int
     const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int vec = (num_pixels % 4 == 0 && aligned_to(label, 4) && aligned_to(conf, 16)) ? 4 : 1;
-    auto kern = vec == 4 ? radix_hist_kernel<4> : radix_hist_kernel<1>;
+    auto kern = vec == 4 ? (pass == 0 ? radix_hist_kernel<4, 0> : pass == 1 ? radix_hist_kernel<4, 1> : radix_hist_kernel<4, 2>)
+                         : (pass == 0 ? radix_hist_kernel<1, 0> : pass == 1 ? radix_hist_kernel<1, 1> : radix_hist_kernel<1, 2>);
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
     const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, kHistThreads, 4);
-    kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K, pass,
+    kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K,
                                                      static_cast<const RadixState*>(state), hist, ds_rate);
     return launch_status();
 }

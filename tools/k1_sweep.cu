@@ -162,6 +162,8 @@ int main(int argc, char** argv) {
         TMA(16, 2, 4, 5, false, true);
         TMA(8, 4, 10, 2, false, true);
         TMA(16, 2, 10, 2, false, true);
+        TMA(15, 2, 5, 4, false, true);
+        TMA(19, 2, 5, 3, false, true);
         TMA(20, 2, 5, 3, false, true);
         TMA(24, 2, 5, 2, false, true);
         TMA(24, 1, 5, 5, false, true);
@@ -174,6 +176,10 @@ int main(int argc, char** argv) {
         DIRECT(1, 5, 256, 3, true, true);
         TMA(8, 4, 5, 4, true, true);
         TMA(16, 2, 5, 4, true, true);
+        TMA(15, 2, 5, 4, true, true);
+        TMA(19, 2, 5, 3, true, true);
+        TMA(12, 2, 5, 5, true, true);
+        TMA(11, 2, 5, 5, true, true);
         TMA(16, 1, 5, 8, true, true);
     }
     return 0;
