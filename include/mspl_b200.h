@@ -153,6 +153,17 @@ MSPL_API int mspl_uw_loss_bwd(const float* pred, const int64_t* target, const fl
                      const float* class_weights, const float* grad_loss, int64_t n, int num_classes,
                      int64_t pixels_per_image, double norm_pixels, float* d_pred, float* d_u, void* stream);
 
+/* ---- GPU MIOU.get_iou (next-row component) ----------------------------------------------
+ * Replaces MIOU.get_iou (utilities/metrics/segmentation_miou.py:13-44; call sites uest_seg_multi_os.py:1032, 1198,
+ * eval_label.py:201), which moves pred/target to the CPU and runs torch.histc three times.
+ * counts: 3*num_classes u64, += [area_inter | area_pred | area_mask]; area_union = pred + mask - inter + 1e-6 on the host.
+ * Semantics are the reference's: uint8 casts, the "+1 so that 255 is 0" shift, pixels with shifted target 0 dropped,
+ * class ids >= num_classes not counted.  num_classes <= 255. */
+MSPL_API int mspl_miou_from_logits(const float* logits, const int64_t* target, int64_t n, int c, int64_t pixels_per_image,
+                          int num_classes, unsigned long long* counts, void* stream);
+MSPL_API int mspl_miou_from_labels(const void* pred, int pred_is_int64, const int64_t* target, int64_t num_pixels,
+                          int num_classes, unsigned long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

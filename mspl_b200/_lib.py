@@ -33,6 +33,8 @@ SIGNATURES = {
     "mspl_kld_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "mspl_uw_loss_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f64, c_vp, c_vp, c_sz, c_vp]),
     "mspl_uw_loss_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f64, c_vp, c_vp, c_vp]),
+    "mspl_miou_from_logits": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_vp]),
+    "mspl_miou_from_labels": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_vp]),
 }
 
 _lib = None

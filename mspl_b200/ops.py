@@ -376,3 +376,34 @@ def uw_segmentation_loss(pred, target, u_weight, class_weights, norm_pixels=None
     if cw.numel() != k:
         raise ValueError("class_weights must have %d entries" % k)
     return _UwLoss.apply(pred, target, u_weight, cw, norm_pixels)
+
+
+def miou_counts(output, target, num_classes, counts=None):
+    """GPU MIOU.get_iou counting (utilities/metrics/segmentation_miou.py:13-44).  output: (B,C,H,W) fp32 logits (argmax over
+    classes is taken, first maximal index) or a (B,H,W) uint8/int64 label map; target: integer label map (255 = dropped).
+    Returns an int64 (3, num_classes) tensor [area_inter, area_pred, area_mask] (accumulated into `counts` if given)."""
+    if not isinstance(output, torch.Tensor) or not output.is_cuda:
+        raise ValueError("output must be a CUDA tensor (mspl_b200 has no CPU path)")
+    dev = output.device
+    target = target.to(device=dev, dtype=torch.int64).contiguous()
+    if counts is None:
+        counts = torch.zeros((3, num_classes), dtype=torch.int64, device=dev)
+    _require_cuda(counts, "counts", torch.int64)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        if output.dim() == 4:
+            out = _require_cuda(output.detach().float().contiguous(), "output", torch.float32, 4)
+            n, c, h, w = out.shape
+            if target.numel() != n * h * w:
+                raise ValueError("target must hold one label per pixel")
+            st = lib.mspl_miou_from_logits(_ptr(out), _ptr(target), n, c, h * w, num_classes, _ptr(counts), _stream(dev))
+        else:
+            pred = output.detach().contiguous()
+            if pred.dtype not in (torch.uint8, torch.int64):
+                pred = pred.to(torch.int64)
+            if target.numel() != pred.numel():
+                raise ValueError("pred/target sizes differ")
+            st = lib.mspl_miou_from_labels(_ptr(pred), int(pred.dtype == torch.int64), _ptr(target), pred.numel(), num_classes,
+                                           _ptr(counts), _stream(dev))
+    _lib.check(st, "mspl_miou")
+    return counts

@@ -182,16 +182,36 @@ def golden_loss(ref):
     np.savez_compressed(os.path.join(GOLDEN_DIR, "loss_k5.npz"), **out)
 
 
+def golden_miou(ref):
+    """MIOU.get_iou (utilities/metrics/segmentation_miou.py:13-44) on logits and on label maps, with 255-labelled and
+    out-of-range pixels, for 5 and 21 classes."""
+    from utilities.metrics.segmentation_miou import MIOU
+    gen = torch.Generator().manual_seed(3)
+    out = {}
+    for nc in (5, 21):
+        logits = torch.randn(3, nc, 20, 28, generator=gen)
+        logits[:, :, :2] = 0.0                                   # exact ties -> first maximal index
+        target = torch.randint(0, nc + 2, (3, 20, 28), generator=gen)
+        target[target == nc + 1] = 255                           # "ignore" pixels of the reference loaders
+        inter, union = MIOU(num_classes=nc).get_iou(logits.clone(), target.clone())
+        out["logits_%d" % nc], out["target_%d" % nc] = logits.numpy(), target.numpy()
+        out["inter_%d" % nc], out["union_%d" % nc] = inter, union
+        pred = torch.randint(0, nc + 1, (3, 20, 28), generator=gen)
+        inter, union = MIOU(num_classes=nc).get_iou(pred.clone(), target.clone())
+        out["pred_%d" % nc], out["inter_lab_%d" % nc], out["union_lab_%d" % nc] = pred.numpy(), inter, union
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "miou.npz"), **out)
+
+
 def main():
     ref = load_reference()
     if ref is None:
         sys.exit("reference tree not found; golden fixtures can only be generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
-    golden_multi_source(ref)
-    golden_adversarial(ref)
-    golden_loss(ref)
-    golden_config1(ref)
+    only = sys.argv[1:]
+    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou):
+        if not only or fn.__name__.replace("golden_", "") in only:
+            fn(ref)
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

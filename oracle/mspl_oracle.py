@@ -15,6 +15,7 @@ reference functions on the path (paths relative to the reference tree):
   * ``transfer_output_to_greenhouse``   uest_seg_multi_os.py:1334-1350
   * ``UncertaintyWeightedSegmentationLoss`` loss_fns/segmentation_loss.py:146-175
   * the training-loss combination       uest_seg_multi_os.py:1020-1023
+  * ``MIOU.get_iou``                    utilities/metrics/segmentation_miou.py:13-44
 
 Parity status.  The functions above are PINNED: tests/test_oracle_vs_reference.py runs them against
 the live reference in the build container, and tests/golden/*.npz hold outputs generated from the
@@ -180,6 +181,28 @@ def training_loss_and_grads(main, aux, labels, class_weights, alpha=20.0, dtype=
     loss = training_loss(m, a, labels, class_weights.to(dtype), alpha)
     gm, ga = torch.autograd.grad(loss, (m, a))
     return loss.detach(), gm, ga
+
+
+def miou_get_iou(output, target, num_classes=21, epsilon=1e-6):
+    """MIOU.get_iou, utilities/metrics/segmentation_miou.py:13-44 (CPU tensors): returns (area_inter, area_union) float32
+    ndarrays of length num_classes."""
+    if isinstance(output, tuple):
+        output = output[0]
+    if output.dim() == 4:
+        _, pred = torch.max(output, 1)
+    else:
+        pred = output
+    pred = pred.type(torch.ByteTensor)
+    target = target.type(torch.ByteTensor)
+    pred = pred + 1          # shift by 1 so that 255 is 0 (uint8 wrap-around)
+    target = target + 1
+    pred = pred * (target > 0)
+    inter = pred * (pred == target)
+    area_inter = torch.histc(inter.float(), bins=num_classes, min=1, max=num_classes)
+    area_pred = torch.histc(pred.float(), bins=num_classes, min=1, max=num_classes)
+    area_mask = torch.histc(target.float(), bins=num_classes, min=1, max=num_classes)
+    area_union = area_pred + area_mask - area_inter + epsilon
+    return area_inter.numpy(), area_union.numpy()
 
 
 # --------------------------------------------------------------------------------------------

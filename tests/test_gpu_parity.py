@@ -422,3 +422,28 @@ def _sharded_thresholds(ops, shards, portion):
             _lib.check(lib.mspl_radix_hist_pass(p(lab), p(conf), lab.numel(), hw, K, ps, p(state), p(hist), 1, st), "hist")
         _lib.check(lib.mspl_radix_select(p(hist), K, ps, portion, p(state), p(thresh), None, st), "select")
     return thresh
+
+
+def test_miou_matches_reference_golden(dev, golden):
+    """GPU MIOU.get_iou against the live-reference fixture: integer areas, so exact."""
+    from mspl_b200.utilities.metrics.segmentation_miou import MIOU
+    g = golden("miou.npz")
+    for nc in (5, 21):
+        logits, target = _t(g["logits_%d" % nc]).to(dev), _t(g["target_%d" % nc]).to(dev)
+        inter, union = MIOU(num_classes=nc).get_iou(logits, target)
+        assert inter.dtype == np.float32 and union.dtype == np.float32
+        assert np.array_equal(inter, g["inter_%d" % nc]) and np.array_equal(union, g["union_%d" % nc])
+        inter, union = MIOU(num_classes=nc).get_iou((logits, logits), target)           # tuple outputs, as train() passes them
+        assert np.array_equal(inter, g["inter_%d" % nc])
+        pred = _t(g["pred_%d" % nc])
+        for p in (pred.to(dev), pred.to(torch.uint8).to(dev)):
+            inter, union = MIOU(num_classes=nc).get_iou(p, target)
+            assert np.array_equal(inter, g["inter_lab_%d" % nc]) and np.array_equal(union, g["union_lab_%d" % nc])
+    # full-size batch against the oracle (config 4 shape, one image)
+    gen = torch.Generator().manual_seed(8)
+    logits = torch.randn(2, 5, 256, 480, generator=gen)
+    target = torch.randint(0, 6, (2, 256, 480), generator=gen)
+    target[target == 5] = 255
+    inter, union = MIOU(num_classes=5).get_iou(logits.to(dev), target.to(dev))
+    i_ref, u_ref = O.miou_get_iou(logits, target, 5)
+    assert np.array_equal(inter, i_ref) and np.array_equal(union, u_ref)

@@ -150,3 +150,12 @@ def test_cb_thresholds_properties():
     assert (th == 1.0).all()
     final, mask = O.apply_thresholds(label, conf, O.cb_thresholds(label, conf, 0.2)[0])
     assert ((final == 4) == (mask == 1)).all() and ((final == label) | (final == 4)).all()
+
+
+def test_miou_golden(golden):
+    g = golden("miou.npz")
+    for nc in (5, 21):
+        inter, union = O.miou_get_iou(_t(g["logits_%d" % nc]), _t(g["target_%d" % nc]), nc)
+        assert np.array_equal(inter, g["inter_%d" % nc]) and np.array_equal(union, g["union_%d" % nc])
+        inter, union = O.miou_get_iou(_t(g["pred_%d" % nc]), _t(g["target_%d" % nc]), nc)
+        assert np.array_equal(inter, g["inter_lab_%d" % nc]) and np.array_equal(union, g["union_lab_%d" % nc])

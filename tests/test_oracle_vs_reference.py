@@ -98,3 +98,16 @@ def test_config1_full_resolution(ref):
             want = ref.uest.merge_outputs(np.array([lut[amax]]), seg_classes=5, thresh=None)
             got, _ = O.multi_source_labels([main], [aux], [O.ID_CITYSCAPES_TO_GREENHOUSE], None)
             assert np.array_equal(got[0], want)
+
+
+def test_miou_matches_reference(ref):
+    import sys
+    from utilities.metrics.segmentation_miou import MIOU
+    gen = torch.Generator().manual_seed(17)
+    for nc in (5, 21):
+        logits = torch.randn(2, nc, 18, 26, generator=gen)
+        target = torch.randint(0, nc + 2, (2, 18, 26), generator=gen)
+        target[target == nc + 1] = 255
+        want = MIOU(num_classes=nc).get_iou(logits.clone(), target.clone())
+        got = O.miou_get_iou(logits, target, nc)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
