@@ -26,6 +26,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .label_io import LabelWriter
 from .data_loader.segmentation.greenhouse import (IGNORE_LABEL, SOURCE_TABLES, id_camvid_to_greenhouse,
                                                   id_cityscapes_to_greenhouse, id_forest_to_greenhouse)
 
@@ -147,7 +148,6 @@ def _image_and_names(batch, use_depth):
 
 
 def _generate(model_list, luts, device, save_path, round_idx, args, logger, testloader, batch_images, policy):
-    from PIL import Image
     dev = _cuda_device(device)
     num_classes = args.classes
     use_depth = getattr(args, 'use_depth', False)
@@ -175,15 +175,19 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
     marginal = torch.zeros((), dtype=torch.int64, device=dev)
     kept_labels, kept_confs = [], []
 
+    writer = LabelWriter(dev, workers=int(getattr(args, 'label_writer_threads', 8)))
+
     def save_maps(label_u8, batch_names):
-        host = label_u8.cpu().numpy()
-        for lab, path_name in zip(host, batch_names):
+        # PNG encode + file write happen on the writer's threads while the GPU works on the next batch
+        out_paths = []
+        for path_name in batch_names:
             image_name = path_name.split('/')[-1].rsplit('.', 1)[0]
-            Image.fromarray(lab).save('%s/%s.png' % (save_pred_path, image_name))
+            out_paths.append('%s/%s.png' % (save_pred_path, image_name))
             image_path_list.append(path_name)
-            label_path_list.append('%s/%s.png' % (save_pred_path, image_name))
+            label_path_list.append(out_paths[-1])
             if use_depth:
                 depth_path_list.append(path_name.replace('color', 'depth'))
+        writer.submit(label_u8, out_paths)
 
     def flush(images, batch_names):
         x = torch.cat(images).to(dev, non_blocking=True)
@@ -221,6 +225,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
                 save_maps(final[pos:pos + len(batch_names)], batch_names)
                 pos += len(batch_names)
 
+    writer.close()       # every label map is on disk before the list that points at it is written
     update_image_list(tgt_train_lst, image_path_list, label_path_list, depth_path_list)
     class_weights = _class_weights_from_histogram(class_hist.cpu().numpy(), getattr(args, 'class_weighting', 'normal'), dev)
     if logger is not None:

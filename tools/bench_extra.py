@@ -63,10 +63,35 @@ def logits(n, c, h, w, dev, seed):
     return m, a
 
 
+def label_io_section(dev):
+    """uint8 label maps on the GPU -> PNG files, asynchronous writer vs the reference's synchronous PIL save."""
+    import tempfile
+    import time
+    from PIL import Image
+    from mspl_b200.label_io import LabelWriter
+    n, h, w = 256, 256, 480
+    labels = torch.randint(0, 5, (n, h, w), device=dev, dtype=torch.uint8)
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with LabelWriter(dev, workers=8) as wr:
+            for lo in range(0, n, 32):
+                wr.submit(labels[lo:lo + 32], ["%s/a_%04d.png" % (tmp, i) for i in range(lo, lo + 32)])
+        t_async = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        host = labels[:32].cpu().numpy()
+        for i in range(32):
+            Image.fromarray(host[i]).save("%s/b_%04d.png" % (tmp, i))
+        t_pil = (time.perf_counter() - t0) * n / 32
+    print(json.dumps({"name": "label_io_256img_480x256", "async_writer_ms_per_image": round(1e3 * t_async / n, 3),
+                      "pil_sync_ms_per_image": round(1e3 * t_pil / n, 3), "speedup": round(t_pil / t_async, 1),
+                      "note": "D2H + PNG encode + file write; PIL figure extrapolated from 32 images"}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress"))
+    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     iters = 5 if args.quick else 20
@@ -108,7 +133,9 @@ def main():
                    note="the reference's op sequence run by PyTorch eager on this GPU (not a CPU baseline)")
         del main_l, aux_l, target
 
-    if args.section == "loss":
+    if args.section in ("all", "io"):
+        label_io_section(dev)
+    if args.section in ("loss", "io"):
         return
     # ---- non-headline policies on the 13/20/5 configuration -----------------------------------------------------------
     n = 100 if args.quick else 400
