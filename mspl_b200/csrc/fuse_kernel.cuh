@@ -112,7 +112,9 @@ struct PixelFusion {
                     if (c > bc) { bc = c; bk = k; }
                 }
                 label[p] = ((int)bc < prm.vote_t) ? ignore : bk;     // (:716)
-                float f = csum[p];
+                // every source voted for `label`, so G_s[label] is that source's max probability -- except for target class 0,
+                // which transfer_output_to_greenhouse never fills (G[0] = 0, uest_seg_multi_os.py:1340)
+                float f = (label[p] == 0) ? 0.f : csum[p];
                 if (GK) {
                     f = 0.f;
 #pragma unroll

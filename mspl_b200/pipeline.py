@@ -59,6 +59,7 @@ class LabelGenerator:
         self.ops = ops if ops is not None else _cuda_ops
         self.group = group
         self.launches = 0          # kernels of libmspl_b200.so launched so far (bench.py reports this)
+        self.k1_events = None      # set to a list to collect (start, end) CUDA events around every K1 launch of run()
 
     # -- distributed plumbing -----------------------------------------------------------------------------------
     def _world(self):
@@ -78,9 +79,15 @@ class LabelGenerator:
         """mains/auxs: this rank's shard, lists of (N_local, C_s, H, W) device tensors.  Returns a LabelJob whose
         histograms / thresholds are GLOBAL (all-reduced) and whose maps are local."""
         ops = self.ops
+        if self.k1_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         r = ops.fuse_sources(mains, auxs, self.luts, policy=self.policy, num_classes=self.num_classes,
                              ignore_label=self.ignore_label, ds_rate=self.ds_rate, want_conf=self.thresholds,
                              want_unc=want_unc, want_conf_hist=self.thresholds)
+        if self.k1_events is not None:
+            e1.record()
+            self.k1_events.append((e0, e1))
         self.launches += 1
         class_hist = self._all_reduce(r.class_hist)
         marginal = self._all_reduce(r.marginal) if r.marginal is not None else None

@@ -447,3 +447,47 @@ def test_miou_matches_reference_golden(dev, golden):
     inter, union = MIOU(num_classes=5).get_iou(logits.to(dev), target.to(dev))
     i_ref, u_ref = O.miou_get_iou(logits, target, 5)
     assert np.array_equal(inter, i_ref) and np.array_equal(union, u_ref)
+
+
+@pytest.mark.parametrize("num_sources,num_classes,src_classes,shape", [
+    (1, 2, (3,), (2, 8, 16)),            # smallest supported K
+    (5, 7, (37, 4, 9, 1, 20), (2, 24, 40)),   # K > 5 -> the 8-class instantiation; C not a multiple of the chunk; C = 1
+    (8, 8, (6, 6, 6, 6, 6, 6, 6, 6), (1, 20, 36)),   # maximum S and K
+    (2, 5, (256, 130), (1, 12, 20)),     # maximum source classes (uint8 argmax in the reference)
+])
+def test_generic_tables_sources_and_classes(ops, dev, num_sources, num_classes, src_classes, shape):
+    """Arbitrary label tables, 1..8 sources, 2..8 target classes, 1..256 source classes, against the oracle."""
+    n, h, w = shape
+    gen = torch.Generator().manual_seed(num_sources * 100 + num_classes)
+    mains, auxs, luts = [], [], []
+    for s, c in enumerate(src_classes):
+        m, a = O.synthetic_logits(n, c, h, w, seed=300 + s)
+        mains.append(m), auxs.append(a)
+        luts.append(torch.randint(0, num_classes, (c,), generator=gen).numpy())
+    ignore = num_classes - 1
+    for policy in ("half", "all", 1, "prob"):
+        r = ops.fuse_sources([m.to(dev) for m in mains], [a.to(dev) for a in auxs], luts, policy=policy, num_classes=num_classes,
+                             ignore_label=ignore, want_kld=True)
+        ref = _oracle_generic(mains, auxs, luts, policy, num_classes, ignore)
+        diff = r.label.cpu() != ref["label"]
+        assert not bool((diff & ~ref["marginal"]).any())
+        ok = ~diff
+        torch.testing.assert_close(r.conf.cpu()[ok], ref["conf"][ok], rtol=RTOL, atol=1e-7)
+        torch.testing.assert_close(r.unc.cpu(), ref["unc"], rtol=RTOL, atol=KLD_ATOL)
+        if not bool(diff.any()):
+            assert torch.equal(r.class_hist.cpu(), ref["class_hist"])
+            th, kept = ops.cb_thresholds(r.label, r.conf, 0.3, num_classes=num_classes, conf_hist=r.conf_hist)
+            th_ref, kept_ref = O.cb_thresholds(r.label.cpu(), r.conf.cpu(), 0.3, 1, num_classes)
+            assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+
+
+def _oracle_generic(mains, auxs, luts, policy, num_classes, ignore):
+    """O.fuse_sources writes the reference's hard-coded ignore id 4 in merge_outputs; remap it for other class counts."""
+    if ignore == 4:
+        return O.fuse_sources(mains, auxs, luts, policy, num_classes, ignore)
+    saved = O.IGNORE_LABEL
+    O.IGNORE_LABEL = ignore
+    try:
+        return O.fuse_sources(mains, auxs, luts, policy, num_classes, ignore)
+    finally:
+        O.IGNORE_LABEL = saved
