@@ -91,6 +91,22 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
                       float* const* kld_per_source, unsigned long long* class_hist,
                       unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream);
 
+/* ---- K1-lowres: K1 with the network's final upsample fused in (next-row component) ------------------
+ * Same outputs and semantics as mspl_fuse_sources, but source s hands over its logits BEFORE the final
+ * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) of model/segmentation/espdnet_ue.py:301-302:
+ * main_logits[s] is (num_images, C_s, main_hw[2s], main_hw[2s+1]) and aux_logits[s] is (num_images, C_s, aux_hw[2s],
+ * aux_hw[2s+1]); the kernel interpolates with ATen's upsample_bilinear2d arithmetic.  HBM traffic falls from
+ * 8*sum(C_s) to ~1.25*sum(C_s) bytes per output pixel for the x2 / x4 heads of ESPDNetUE.
+ * Needs every row length (main/aux width) to be a multiple of 4 and out_h*out_w % 4 == 0; returns MSPL_ERR_UNSUPPORTED when
+ * the tile's source rows do not fit in shared memory (very wide images): upsample and call mspl_fuse_sources instead.
+ * Contract: |logit| differences between the heads beyond 64 units lose confidence precision (no slow path here). */
+MSPL_API int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,
+                             const int* num_classes, const uint8_t* const* lut, const int* main_hw, const int* aux_hw,
+                             int64_t num_images, int out_h, int out_w, int num_target_classes, int policy, int vote_t,
+                             int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
+                             float* const* kld_per_source, unsigned long long* class_hist,
+                             unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream);
+
 /* ---- merge_outputs on hard labels ----------------------------------------------------------------
  * Replaces merge_outputs (uest_seg_multi_os.py:695-718; duplicate eval_label.py:76-100).
  * labels is (num_sources, num_pixels) u8 with values < K. */

@@ -16,6 +16,17 @@
 
 namespace mspl {
 
+// Geometry of the fused-upsample variant (K1-lowres): the sources hand over their logits BEFORE the network's final
+// F.interpolate(..., mode='bilinear', align_corners=True) (model/segmentation/espdnet_ue.py:301-302); the kernel
+// interpolates on the fly.  All zero for the plain kernels.
+struct LowresGeom {
+    int H, W;                            // output (full) resolution; hw == H * W
+    int hm[MSPL_MAX_SOURCES], wm[MSPL_MAX_SOURCES];   // main head resolution per source
+    int ha[MSPL_MAX_SOURCES], wa[MSPL_MAX_SOURCES];   // aux head resolution per source
+    int main_cls_stride, aux_cls_stride, aux_base;    // float offsets inside one ring stage
+    int stage_floats;
+};
+
 struct FuseParams {
     const float* main[MSPL_MAX_SOURCES];
     const float* aux[MSPL_MAX_SOURCES];
@@ -30,6 +41,7 @@ struct FuseParams {
     unsigned long long* class_hist;
     unsigned long long* conf_hist;
     unsigned long long* marginal;
+    LowresGeom lr;
 };
 
 // Shared-memory bookkeeping common to both kernels: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B tables]
@@ -77,6 +89,30 @@ struct PixelFusion {
 #pragma unroll
                 for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
                     Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
+            } else {
+                csum[p] += r.pmax;
+            }
+        }
+    }
+
+    // K1-lowres has no full-resolution logits to recompute from: a degenerate pixel (heads more than 64 logit units apart)
+    // falls back to the exact-but-underflow-prone shared-exponential value, clamped to a valid probability.
+    MSPL_DEVINL void add_source_lowres(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P]) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            SourceResult r = finish_source<P>(st, p);
+            if (r.degenerate) {
+                r.pmax = fminf(fmaxf(r.pmax, 0.f), 1.f);
+                if (!(r.pmax == r.pmax)) r.pmax = 1.f;
+            }
+            d[p] = r.kld;
+            usum[p] += r.kld;
+            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
+            const int lab = s_lut_s[st.amax[p]];
+            votes[p] += 1u << (4 * lab);
+            if (GK) {
+#pragma unroll
+                for (int k = 1; k < K; ++k) Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
             } else {
                 csum[p] += r.pmax;
             }
@@ -443,6 +479,184 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
         }
     }
     tally.flush(prm, s_hist, s_cls, Cfg::kThreads);
+}
+
+// ======================================================================================================================
+// K1-lowres: the same fusion, reading the sources' logits at their native (pre-upsample) resolution and performing the
+// network's final bilinear align_corners=True interpolation in the consumer warps (next-row component).
+// HBM traffic drops from 8*sum(C) B/pixel to 4*sum(C)*(hm*wm + ha*wa)/(H*W) (1.25*sum(C) for the x2 / x4 heads of
+// ESPDNetUE); the kernel becomes instruction-bound.
+//   A tile is TP consecutive output pixels (row-major) of one image.  For every class of the chunk the producer copies
+//   the block of source rows the tile's output rows interpolate from (whole rows, one bulk copy per class and head).
+//   Arithmetic follows ATen's upsample_bilinear2d: src = dst * (in-1)/(out-1); i = (int)src; lambda = src - i;
+//   val = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
+// ======================================================================================================================
+struct BilinearTap {           // one output pixel's taps into one head, relative to the first staged source row
+    int o00, dx, dy;           // offset of v00, +dx for the right column, +dy for the lower row
+    float w0, w1, h0, h1;
+};
+
+MSPL_DEVINL float lowres_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+MSPL_DEVINL BilinearTap make_tap(int y, int x, int hin, int win, float rh, float rw, int first_row) {
+    BilinearTap t;
+    const float h1r = rh * (float)y, w1r = rw * (float)x;
+    const int h1 = (int)h1r, w1 = (int)w1r;
+    t.h1 = h1r - (float)h1; t.h0 = 1.0f - t.h1;
+    t.w1 = w1r - (float)w1; t.w0 = 1.0f - t.w1;
+    t.dy = (h1 < hin - 1) ? win : 0;
+    t.dx = (w1 < win - 1) ? 1 : 0;
+    t.o00 = (h1 - first_row) * win + w1;
+    return t;
+}
+
+MSPL_DEVINL float bilinear(const float* __restrict__ s, const BilinearTap& t) {
+    const float v00 = s[t.o00], v01 = s[t.o00 + t.dx], v10 = s[t.o00 + t.dy], v11 = s[t.o00 + t.dy + t.dx];
+    return t.h0 * (t.w0 * v00 + t.w1 * v01) + t.h1 * (t.w0 * v10 + t.w1 * v11);
+}
+
+template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(const __grid_constant__ FuseParams prm) {
+    constexpr int kThreads = (NCW + 1) * 32;
+    constexpr int TP = NCW * 32 * P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const LowresGeom& lr = prm.lr;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    const size_t ring_bytes = sizeof(float) * (size_t)lr.stage_floats * NSTAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
+    uint64_t* empty = full + NSTAGE;
+    uint32_t *s_hist, *s_cls;
+    uint8_t* s_lut;
+    tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, kThreads);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int S = prm.S, H = lr.H, W = lr.W;
+    const int64_t hw = prm.hw;
+    const int64_t tpi = (hw + TP - 1) / TP;
+    const int64_t n_tiles = prm.n_img * tpi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Tally<KT> tally;
+
+    if (warp == NCW) {
+        // ------------------------------- producer warp -------------------------------
+        const uint64_t policy = tma::evict_first_policy();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t n = tile / tpi;
+            const int64_t off = (tile - n * tpi) * TP;
+            const int y_first = (int)(off / W);
+            const int64_t last = (off + TP < hw ? off + TP : hw) - 1;
+            const int y_last = (int)(last / W);
+            for (int s = 0; s < S; ++s) {
+                const int C = prm.C[s], hm = lr.hm[s], wm = lr.wm[s], ha = lr.ha[s], wa = lr.wa[s];
+                const float rhm = lowres_scale(hm, H), rha = lowres_scale(ha, H);
+                const int m0 = (int)(rhm * (float)y_first), m1 = min((int)(rhm * (float)y_last) + 1, hm - 1);
+                const int a0 = (int)(rha * (float)y_first), a1 = min((int)(rha * (float)y_last) + 1, ha - 1);
+                const uint32_t mbytes = (uint32_t)((m1 - m0 + 1) * wm * sizeof(float));
+                const uint32_t abytes = (uint32_t)((a1 - a0 + 1) * wa * sizeof(float));
+                const float* pm = prm.main[s] + ((n * C) * hm + m0) * wm;
+                const float* pa = prm.aux[s] + ((n * C) * ha + a0) * wa;
+                for (int c0 = 0; c0 < C; c0 += CH) {
+                    const int cn = min(CH, C - c0);
+                    tma::mbar_wait(&empty[stage], phase ^ 1);
+                    float* dst = ring + (size_t)stage * lr.stage_floats;
+                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], cn * (mbytes + abytes));
+                    __syncwarp();
+                    for (int j = lane; j < 2 * cn; j += 32) {
+                        const int head = j >= cn, c = head ? j - cn : j;
+                        if (head) tma::bulk_g2s(dst + lr.aux_base + c * lr.aux_cls_stride, pa + (int64_t)(c0 + c) * ha * wa, abytes, &full[stage], policy);
+                        else tma::bulk_g2s(dst + c * lr.main_cls_stride, pm + (int64_t)(c0 + c) * hm * wm, mbytes, &full[stage], policy);
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps -------------------------------
+        const float inv_s = 1.0f / (float)S;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int px = (warp * 32 + lane) * P;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t n = tile / tpi;
+            const int64_t tile_off = (tile - n * tpi) * TP;
+            const int64_t off = tile_off + px;
+            const bool active = off < hw;
+            const int y_first = (int)(tile_off / W);
+            int yy[P], xx[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int64_t o = active ? off + p : tile_off;      // idle lanes interpolate the tile's first pixel
+                yy[p] = (int)(o / W);
+                xx[p] = (int)(o - (int64_t)yy[p] * W);
+            }
+            PixelFusion<P, KT, GK, TOP2> fus;
+            fus.reset();
+            for (int s = 0; s < S; ++s) {
+                const int C = prm.C[s], hm = lr.hm[s], wm = lr.wm[s], ha = lr.ha[s], wa = lr.wa[s];
+                const float rhm = lowres_scale(hm, H), rwm = lowres_scale(wm, W);
+                const float rha = lowres_scale(ha, H), rwa = lowres_scale(wa, W);
+                const int m0 = (int)(rhm * (float)y_first), a0 = (int)(rha * (float)y_first);
+                BilinearTap tm[P], ta[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    tm[p] = make_tap(yy[p], xx[p], hm, wm, rhm, rwm, m0);
+                    ta[p] = make_tap(yy[p], xx[p], ha, wa, rha, rwa, a0);
+                }
+                SourceStats<P> st;
+                st.reset();
+                float zk[KT][P];
+                reset_zk<KT, P>(zk);
+                for (int c0 = 0; c0 < C; c0 += CH) {
+                    const int cn = min(CH, C - c0);
+                    float m[CH][P], a[CH][P];
+                    tma::mbar_wait(&full[stage], phase);
+                    const float* src = ring + (size_t)stage * lr.stage_floats;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        if (j < cn) {
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                m[j][p] = bilinear(src + j * lr.main_cls_stride, tm[p]);
+                                a[j][p] = bilinear(src + lr.aux_base + j * lr.aux_cls_stride, ta[p]);
+                            }
+                        } else {
+                            fill_pad<P>(m[j]);
+                            fill_pad<P>(a[j]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) tma::mbar_arrive(&empty[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                }
+                float d[P];
+                // (the degenerate-pixel slow path would need the full-resolution logits this variant never materialises;
+                //  mspl_fuse_sources_lowres documents the |logit| <= 64 contract instead)
+                fus.add_source_lowres(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
+                if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+            }
+            int label[P];
+            float conf[P], unc[P];
+            fus.finish(prm, inv_s, label, conf, unc);
+            if (active) {
+                const int64_t o = n * hw + off;
+                store_labels<P>(prm.label + o, label);
+                if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
+                if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
+            }
+            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
+        }
+    }
+    tally.flush(prm, s_hist, s_cls, kThreads);
 }
 
 }  // namespace mspl

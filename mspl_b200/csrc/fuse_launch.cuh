@@ -1,5 +1,7 @@
 // Host-side launch helpers for the two K1 kernels (shared by libmspl_b200.so and tools/k1_sweep).
 #pragma once
+#include <algorithm>
+
 #include "fuse_kernel.cuh"
 
 namespace mspl {
@@ -57,6 +59,42 @@ bool tma_eligible(const FuseParams& prm) {
     for (int s = 0; s < prm.S; ++s)
         if (!aligned_to(prm.main[s], 16) || !aligned_to(prm.aux[s], 16) || (prm.kld[s] && !aligned_to(prm.kld[s], 16))) return false;
     return aligned_to(prm.label, 4) && (!prm.conf || aligned_to(prm.conf, 16)) && (!prm.unc || aligned_to(prm.unc, 16));
+}
+
+// ---- K1-lowres ------------------------------------------------------------------------------------------------------
+// Fills prm.lr's stage layout for tiles of `tile_pix` consecutive output pixels; returns the dynamic shared memory the
+// kernel needs with `stages` ring slots, or 0 if the geometry is unsupported (rows not 16-byte multiples).
+inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages) {
+    LowresGeom& lr = prm.lr;
+    const int rows_spanned = (int)std::min<int64_t>(lr.H, (tile_pix - 1) / lr.W + 2);
+    int main_stride = 0, aux_stride = 0;
+    for (int s = 0; s < prm.S; ++s) {
+        if (lr.wm[s] % 4 || lr.wa[s] % 4 || lr.hm[s] < 1 || lr.ha[s] < 1) return 0;
+        auto rows = [&](int hin) {
+            const float scale = lr.H > 1 ? (float)(hin - 1) / (float)(lr.H - 1) : 0.f;
+            return std::min(hin, (int)((rows_spanned - 1) * scale) + 3);
+        };
+        main_stride = std::max(main_stride, rows(lr.hm[s]) * lr.wm[s]);
+        aux_stride = std::max(aux_stride, rows(lr.ha[s]) * lr.wa[s]);
+    }
+    lr.main_cls_stride = main_stride;
+    lr.aux_cls_stride = aux_stride;
+    lr.aux_base = chunk * main_stride;
+    lr.stage_floats = chunk * (main_stride + aux_stride);
+    return sizeof(float) * (size_t)lr.stage_floats * stages + 2 * stages * sizeof(uint64_t) + fuse_tally_smem_bytes(prm.K) + 128;
+}
+
+template <int NCW, int P, typename Kern>
+int launch_fuse_lowres(Kern kern, const FuseParams& prm, size_t smem, cudaStream_t stream) {
+    const DeviceInfo di = device_info();
+    if (!di.ok || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
+    constexpr int TP = NCW * 32 * P;
+    const int64_t n_tiles = prm.n_img * ((prm.hw + TP - 1) / TP);
+    kern<<<(unsigned)(n_tiles < di.sms ? n_tiles : di.sms), (NCW + 1) * 32, smem, stream>>>(prm);
+    return launch_status();
 }
 
 }  // namespace mspl

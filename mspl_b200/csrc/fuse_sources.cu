@@ -16,6 +16,12 @@ namespace mspl {
 #ifndef MSPL_USE_TMA
 #define MSPL_USE_TMA 1
 #endif
+#ifndef MSPL_LOWRES_NCW
+#define MSPL_LOWRES_NCW 15     // K1-lowres: consumer warps (instruction-bound kernel; 16 warps split the register file evenly)
+#endif
+#ifndef MSPL_LOWRES_STAGES
+#define MSPL_LOWRES_STAGES 4
+#endif
 
 // TMA-staged kernel configurations <consumer warps, pixels per thread, classes per chunk, ring stages>, picked from the
 // tools/k1_sweep runs on B200 (profiles/r01_k1_sweep_*.txt):
@@ -118,6 +124,64 @@ extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logit
     const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return K <= 5 ? dispatch_fuse<5>(prm, P, gk, st) : dispatch_fuse<8>(prm, P, gk, st);
+}
+
+extern "C" int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,
+                                        const int* num_classes, const uint8_t* const* lut, const int* main_hw, const int* aux_hw,
+                                        int64_t num_images, int out_h, int out_w, int num_target_classes, int policy, int vote_t,
+                                        int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
+                                        float* const* kld_per_source, unsigned long long* class_hist,
+                                        unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream) {
+    const int S = num_sources, K = num_target_classes;
+    if (S < 1 || S > MSPL_MAX_SOURCES || K < 2 || K > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (!main_logits || !aux_logits || !num_classes || !lut || !main_hw || !aux_hw || !label || !class_hist) return MSPL_ERR_BAD_ARG;
+    if (num_images < 0 || out_h < 1 || out_w < 1 || ds_rate < 1) return MSPL_ERR_BAD_ARG;
+    if (ignore_label < 0 || ignore_label >= K) return MSPL_ERR_BAD_ARG;
+    if (policy != MSPL_POLICY_VOTE && policy != MSPL_POLICY_PROB) return MSPL_ERR_BAD_ARG;
+    if (conf_hist && !conf) return MSPL_ERR_BAD_ARG;
+    if (num_images == 0) return MSPL_OK;
+    FuseParams prm;
+    memset(&prm, 0, sizeof(prm));
+    const int64_t hw = (int64_t)out_h * out_w;
+    if (hw % 4 != 0) return MSPL_ERR_UNSUPPORTED;
+    for (int s = 0; s < S; ++s) {
+        const int C = num_classes[s];
+        if (C < 1 || C > MSPL_MAX_SRC_CLASSES || !main_logits[s] || !aux_logits[s] || !lut[s]) return MSPL_ERR_BAD_ARG;
+        if (main_hw[2 * s] < 1 || main_hw[2 * s + 1] < 1 || aux_hw[2 * s] < 1 || aux_hw[2 * s + 1] < 1) return MSPL_ERR_BAD_ARG;
+        if (!aligned_to(main_logits[s], 16) || !aligned_to(aux_logits[s], 16)) return MSPL_ERR_ALIGN;
+        prm.main[s] = main_logits[s];
+        prm.aux[s] = aux_logits[s];
+        prm.kld[s] = kld_per_source ? kld_per_source[s] : nullptr;
+        if (prm.kld[s] && !aligned_to(prm.kld[s], 16)) return MSPL_ERR_ALIGN;
+        prm.C[s] = C;
+        prm.lr.hm[s] = main_hw[2 * s]; prm.lr.wm[s] = main_hw[2 * s + 1];
+        prm.lr.ha[s] = aux_hw[2 * s]; prm.lr.wa[s] = aux_hw[2 * s + 1];
+        for (int c = 0; c < C; ++c) {
+            if (lut[s][c] >= K) return MSPL_ERR_BAD_ARG;
+            prm.lut[s][c] = lut[s][c];
+        }
+    }
+    if (!aligned_to(label, 4) || (conf && !aligned_to(conf, 16)) || (unc && !aligned_to(unc, 16))) return MSPL_ERR_ALIGN;
+    if (!aligned_to(class_hist, 8) || (conf_hist && !aligned_to(conf_hist, 8)) || (marginal_count && !aligned_to(marginal_count, 8)))
+        return MSPL_ERR_ALIGN;
+    prm.S = S; prm.K = K; prm.policy = policy; prm.vote_t = vote_t < 1 ? 1 : vote_t;
+    prm.ignore = ignore_label; prm.ds_rate = ds_rate;
+    prm.n_img = num_images; prm.hw = hw;
+    prm.lr.H = out_h; prm.lr.W = out_w;
+    prm.label = label; prm.conf = conf; prm.unc = unc;
+    prm.class_hist = class_hist; prm.conf_hist = conf_hist; prm.marginal = marginal_count;
+
+    constexpr int NCW = MSPL_LOWRES_NCW, P = 2, CH = MSPL_FUSE_CH, NST = MSPL_LOWRES_STAGES;
+    const size_t smem = lowres_plan(prm, NCW * 32 * P, CH, NST);
+    if (smem == 0 || smem > 227 * 1024) return MSPL_ERR_UNSUPPORTED;    // caller upsamples and uses mspl_fuse_sources instead
+    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (K <= 5) {
+        if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, true>, prm, smem, st);
+        return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true>, prm, smem, st);
+    }
+    if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, true, true>, prm, smem, st);
+    return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, false, true>, prm, smem, st);
 }
 
 extern "C" int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,

@@ -136,6 +136,69 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
                       marginal if count_marginal else None)
 
 
+def fuse_sources_lowres(mains, auxs, luts, out_size, policy='half', num_classes=5, ignore_label=4, ds_rate=1,
+                        want_conf=True, want_unc=True, want_kld=False, want_conf_hist=True, count_marginal=True,
+                        class_hist=None, conf_hist=None, marginal=None):
+    """K1 with the networks' final bilinear upsample fused in: mains[s] is (N, C_s, hm, wm), auxs[s] is (N, C_s, ha, wa) --
+    the tensors ESPDNetUE feeds to its closing ``F.interpolate(..., size=out_size, mode='bilinear', align_corners=True)``
+    (model/segmentation/espdnet_ue.py:301-302) -- and the labels come out at ``out_size = (H, W)``.  Everything else is as
+    in fuse_sources.  Raises NotImplementedError when the geometry is not supported by the fused kernel (row lengths not
+    multiples of 4, H*W % 4 != 0, or source rows too wide for shared memory): upsample and call fuse_sources then."""
+    S = len(mains)
+    if S < 1 or S > MAX_SOURCES or len(auxs) != S or len(luts) != S:
+        raise ValueError("need 1..%d sources with matching mains/auxs/luts" % MAX_SOURCES)
+    if not (2 <= num_classes <= MAX_CLASSES) or not (0 <= ignore_label < num_classes):
+        raise ValueError("num_classes must be in [2,%d] and ignore_label inside it" % MAX_CLASSES)
+    h, w = int(out_size[0]), int(out_size[1])
+    m0 = _require_cuda(mains[0], "mains[0]", torch.float32, 4)
+    n, dev = m0.shape[0], m0.device
+    lut_bufs, cls, mhw, ahw = [], [], [], []
+    for s in range(S):
+        m = _require_cuda(mains[s], "mains[%d]" % s, torch.float32, 4)
+        a = _require_cuda(auxs[s], "auxs[%d]" % s, torch.float32, 4)
+        if m.shape[:2] != a.shape[:2] or m.shape[0] != n or m.device != dev or a.device != dev:
+            raise ValueError("source %d: main/aux batch, class count or device disagree" % s)
+        cls.append(m.shape[1])
+        mhw += [m.shape[2], m.shape[3]]
+        ahw += [a.shape[2], a.shape[3]]
+        lut_bufs.append(_lut_bytes(luts[s], m.shape[1], num_classes))
+    if policy == 'prob':
+        pol, vt = POLICY_PROB, 0
+    else:
+        pol, vt = POLICY_VOTE, vote_threshold(S, policy)
+    label = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    conf = torch.empty((n, h, w), dtype=torch.float32, device=dev) if (want_conf or want_conf_hist) else None
+    unc = torch.empty((n, h, w), dtype=torch.float32, device=dev) if want_unc else None
+    kld = [torch.empty((n, h, w), dtype=torch.float32, device=dev) for _ in range(S)] if want_kld else None
+    if class_hist is None:
+        class_hist = torch.zeros(num_classes, dtype=torch.int64, device=dev)
+    if want_conf_hist and conf_hist is None:
+        conf_hist = torch.zeros((num_classes, RADIX_BINS), dtype=torch.int64, device=dev)
+    if count_marginal and marginal is None:
+        marginal = torch.zeros((), dtype=torch.int64, device=dev)
+    vp = ctypes.c_void_p
+    main_ptrs = (vp * S)(*[m.data_ptr() for m in mains])
+    aux_ptrs = (vp * S)(*[a.data_ptr() for a in auxs])
+    kld_ptrs = (vp * S)(*[k.data_ptr() for k in kld]) if kld is not None else None
+    ncls = (ctypes.c_int * S)(*cls)
+    lut_ptrs = (vp * S)(*[ctypes.addressof(b) for b in lut_bufs])
+    mhw_arr, ahw_arr = (ctypes.c_int * (2 * S))(*mhw), (ctypes.c_int * (2 * S))(*ahw)
+    if n == 0:
+        return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
+                          marginal if count_marginal else None)
+    with torch.cuda.device(dev):
+        st = _lib.load().mspl_fuse_sources_lowres(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, mhw_arr, ahw_arr, n, h, w, num_classes,
+                                                  pol, vt, ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,
+                                                  _ptr(class_hist), _ptr(conf_hist if want_conf_hist else None),
+                                                  _ptr(marginal if count_marginal else None), _stream(dev))
+    if st == -3:
+        raise NotImplementedError("fuse_sources_lowres: geometry not supported by the fused-upsample kernel; upsample and use "
+                                  "fuse_sources")
+    _lib.check(st, "mspl_fuse_sources_lowres")
+    return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
+                      marginal if count_marginal else None)
+
+
 def vote_labels(labels, num_classes=5, thresh=None, ignore_label=4):
     """merge_outputs on a (S, ...) uint8 CUDA tensor of hard labels -> uint8 tensor of shape labels.shape[1:]."""
     labels = _require_cuda(labels, "labels", torch.uint8)
@@ -276,6 +339,9 @@ class _UwCeLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_parts):
+        if ctx.grads is None:
+            raise RuntimeError("uw_ce_loss: backward through this loss a second time is not supported (its gradients are "
+                               "produced by the forward launch and handed over once)")
         d_main, d_aux = ctx.grads
         ctx.grads = None
         if d_main is None:

@@ -264,6 +264,18 @@ def fuse_sources(mains, auxs, luts, policy='half', seg_classes=NUM_GREENHOUSE_CL
                 marginal=marginal, fused=Fm)
 
 
+def upsample_heads(main_lr, aux_lr, out_size):
+    """The closing statement of ESPDNetwithUncertaintyEstimation.forward, model/segmentation/espdnet_ue.py:301-302."""
+    return (F.interpolate(main_lr, size=out_size, mode='bilinear', align_corners=True),
+            F.interpolate(aux_lr, size=out_size, mode='bilinear', align_corners=True))
+
+
+def fuse_sources_lowres(mains_lr, auxs_lr, luts, out_size, policy='half', seg_classes=NUM_GREENHOUSE_CLASSES, ignore=IGNORE_LABEL):
+    """K1-lowres definition: upsample each source's heads exactly as the network would, then fuse_sources."""
+    ups = [upsample_heads(m, a, out_size) for m, a in zip(mains_lr, auxs_lr)]
+    return fuse_sources([u[0] for u in ups], [u[1] for u in ups], luts, policy, seg_classes, ignore)
+
+
 def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUSE_CLASSES):
     """Class-balanced (CBST/CRST-style) per-class confidence thresholds (SURVEY.md section 8 A4'').
 

@@ -491,3 +491,45 @@ def _oracle_generic(mains, auxs, luts, policy, num_classes, ignore):
         return O.fuse_sources(mains, auxs, luts, policy, num_classes, ignore)
     finally:
         O.IGNORE_LABEL = saved
+
+
+@pytest.mark.parametrize("out_size,main_size,aux_size", [((256, 480), (128, 240), (64, 120)),     # ESPDNetUE at the benchmark resolution
+                                                         ((64, 96), (32, 48), (16, 24)),
+                                                         ((48, 100), (24, 52), (12, 28)),          # non-integer scale factors
+                                                         ((30, 44), (30, 44), (8, 12))])          # main already at full size
+def test_fuse_sources_lowres(ops, dev, out_size, main_size, aux_size):
+    """K1 with the network's final bilinear upsample fused in, against upsample-then-fuse on the CPU (its own parity
+    definition, SURVEY.md 8f-1: the kernel and ATen's CPU interpolation round differently in the last ulp of a logit, which
+    moves probabilities by up to ~1e-6, so labels are excused where the oracle's top-2 margin is below 1e-5 and floats get
+    1e-4 relative / 1e-5 absolute)."""
+    n = 2
+    gen = torch.Generator().manual_seed(out_size[0])
+    mains, auxs = [], []
+    for nm, c in SOURCES:
+        m = 3 * torch.randn(n, c, *main_size, generator=gen) + 3 * torch.randn(n, c, 1, 1, generator=gen)
+        a = 3 * torch.randn(n, c, *aux_size, generator=gen)
+        mains.append(m.contiguous()), auxs.append(a.contiguous())
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    saved = O.NEAR_TIE_MARGIN
+    O.NEAR_TIE_MARGIN = 1e-5
+    try:
+        for policy in ("all", "half", "prob"):
+            r = ops.fuse_sources_lowres([m.to(dev) for m in mains], [a.to(dev) for a in auxs], luts, out_size, policy=policy,
+                                        want_kld=True)
+            ref = O.fuse_sources_lowres(mains, auxs, luts, out_size, policy)
+            diff = r.label.cpu() != ref["label"]
+            assert not bool((diff & ~ref["marginal"]).any()), "%d mismatches outside near-ties" % int((diff & ~ref["marginal"]).sum())
+            ok = ~diff
+            torch.testing.assert_close(r.conf.cpu()[ok], ref["conf"][ok], rtol=1e-4, atol=1e-6)
+            torch.testing.assert_close(r.unc.cpu(), ref["unc"], rtol=1e-4, atol=1e-5)
+            for got, want in zip(r.kld, ref["kld"]):
+                torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+            assert torch.equal(r.class_hist, torch.bincount(r.label.reshape(-1).long(), minlength=5))
+            assert torch.equal(r.conf_hist.sum(dim=1), r.class_hist)
+            # and against the un-fused GPU path on GPU-upsampled logits: same labels except at near-ties
+            ups = [O.upsample_heads(m.to(dev), a.to(dev), out_size) for m, a in zip(mains, auxs)]
+            r2 = ops.fuse_sources([u[0].contiguous() for u in ups], [u[1].contiguous() for u in ups], luts, policy=policy)
+            d2 = (r.label != r2.label).cpu()
+            assert not bool((d2 & ~ref["marginal"]).any())
+    finally:
+        O.NEAR_TIE_MARGIN = saved

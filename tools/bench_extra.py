@@ -88,10 +88,39 @@ def label_io_section(dev):
                       "note": "D2H + PNG encode + file write; PIL figure extrapolated from 32 images"}), flush=True)
 
 
+def lowres_section(dev, iters):
+    """K1 with ESPDNetUE's final bilinear upsample (x2 main, x4 aux) fused in, against what the reference
+    pipeline does on the GPU today: F.interpolate both heads to full size (PyTorch kernels), then fuse."""
+    import torch.nn.functional as F
+    n, h, w = 200, 256, 480
+    srcs = (("camvid", 13), ("cityscapes", 20), ("forest", 5))
+    g = torch.Generator(device=dev).manual_seed(5)
+    mains = [3 * torch.randn((n, c, h // 2, w // 2), device=dev, generator=g) for _, c in srcs]
+    auxs = [3 * torch.randn((n, c, h // 4, w // 4), device=dev, generator=g) for _, c in srcs]
+    luts = [SOURCE_TABLES[s] for s, _ in srcs]
+    lr_bytes = 4 * sum(c for _, c in srcs) * (1 / 4 + 1 / 16) + 9
+
+    med, best = timed(lambda: ops.fuse_sources_lowres(mains, auxs, luts, (h, w), policy="all"), iters)
+    report("k1_lowres_fused_upsample_all_%dimg" % n, n * h * w, lr_bytes, med, best,
+           note="reads pre-upsample logits (%.1f B/pixel); instruction-bound" % lr_bytes)
+
+    def unfused():
+        um = [F.interpolate(m, size=(h, w), mode="bilinear", align_corners=True) for m in mains]
+        ua = [F.interpolate(a, size=(h, w), mode="bilinear", align_corners=True) for a in auxs]
+        return ops.fuse_sources(um, ua, luts, policy="all")
+    med2, best2 = timed(unfused, iters)
+    report("k1_after_torch_upsample_all_%dimg" % n, n * h * w, lr_bytes, med2, best2,
+           note="F.interpolate x6 (PyTorch) + K1; speed-up of the fused kernel: %.2fx" % (med2 / med))
+    um = [F.interpolate(m, size=(h, w), mode="bilinear", align_corners=True) for m in mains]
+    ua = [F.interpolate(a, size=(h, w), mode="bilinear", align_corners=True) for a in auxs]
+    med3, best3 = timed(lambda: ops.fuse_sources(um, ua, luts, policy="all"), iters)
+    report("k1_fullres_only_all_%dimg" % n, n * h * w, 313, med3, best3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io"))
+    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io", "lowres"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     iters = 5 if args.quick else 20
@@ -135,7 +164,9 @@ def main():
 
     if args.section in ("all", "io"):
         label_io_section(dev)
-    if args.section in ("loss", "io"):
+    if args.section in ("all", "lowres"):
+        lowres_section(dev, iters)
+    if args.section in ("loss", "io", "lowres"):
         return
     # ---- non-headline policies on the 13/20/5 configuration -----------------------------------------------------------
     n = 100 if args.quick else 400
