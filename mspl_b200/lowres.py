@@ -1,0 +1,49 @@
+"""Getting a source network's logits BEFORE its final upsample, without editing the network.
+
+ESPDNetUE ends its forward with
+
+    return (F.interpolate(bu_out,  size=x_size, mode='bilinear', align_corners=True),
+            F.interpolate(aux_out, size=x_size, mode='bilinear', align_corners=True))        # espdnet_ue.py:301-302
+
+and those two calls write 8*C bytes per pixel that the label-generation kernel immediately reads back.
+``forward_lowres`` runs the model with ``torch.nn.functional.interpolate`` temporarily wrapped: calls that match that closing
+pattern (bilinear, align_corners=True, target size == the input image size) are recorded and answered with a zero-stride
+placeholder of the right shape; every other interpolate call (the decoder's internal upsampling) goes through untouched.
+The recorded tensors feed ``ops.fuse_sources_lowres``, which interpolates inside the fusion kernel.
+"""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+
+@contextlib.contextmanager
+def _intercept_final_upsample(out_size, captured):
+    original = F.interpolate
+
+    def wrapper(input, size=None, scale_factor=None, mode='nearest', align_corners=None, **kwargs):
+        want = tuple(int(v) for v in size) if isinstance(size, (tuple, list, torch.Size)) else None
+        if mode == 'bilinear' and align_corners and want == tuple(out_size) and input.dim() == 4:
+            captured.append(input)
+            return input.new_empty(1).expand(input.shape[0], input.shape[1], *want)     # never read by the caller
+        return original(input, size=size, scale_factor=scale_factor, mode=mode, align_corners=align_corners, **kwargs)
+
+    F.interpolate = wrapper
+    try:
+        yield
+    finally:
+        F.interpolate = original
+
+
+def forward_lowres(model, x):
+    """Run ``model(x)``; return ``(main_lowres, aux_lowres)`` if the model closed with exactly two matching upsample calls
+    (main first, aux second, as ESPDNetUE does), else ``None`` -- the caller then uses the ordinary full-resolution path."""
+    captured = []
+    with _intercept_final_upsample(x.shape[-2:], captured):
+        out = model(x)
+    if len(captured) != 2 or not isinstance(out, (tuple, list)) or len(out) != 2:
+        return None
+    main_lr, aux_lr = captured
+    if main_lr.shape[1] != aux_lr.shape[1] or tuple(out[0].shape[-2:]) != tuple(x.shape[-2:]):
+        return None
+    return main_lr, aux_lr

@@ -15,7 +15,9 @@ network.  Differences from the reference, all deliberate:
   * the generators batch images through the networks and fuse all sources in ONE kernel pass on the device --
     no per-source softmax/KLD maps ever travel to the host; only the final uint8 label map does;
   * optional class-balanced confidence thresholds ([NEW], ``args.cb_thresholds``; the reference keeps only the
-    CBST/CRST flags ``--init-tgt-port`` / ``--ds-rate`` at :216-219).
+    CBST/CRST flags ``--init-tgt-port`` / ``--ds-rate`` at :216-219);
+  * optional fused upsample ([NEW], ``args.fuse_upsample``): the sources' closing bilinear ``F.interpolate`` calls are
+    intercepted (mspl_b200/lowres.py) and performed inside the fusion kernel.
 """
 import os
 import os.path as osp
@@ -27,6 +29,7 @@ import torch
 
 from . import ops
 from .label_io import LabelWriter
+from .lowres import forward_lowres
 from .data_loader.segmentation.greenhouse import (IGNORE_LABEL, SOURCE_TABLES, id_camvid_to_greenhouse,
                                                   id_cityscapes_to_greenhouse, id_forest_to_greenhouse)
 
@@ -189,16 +192,30 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
                 depth_path_list.append(path_name.replace('color', 'depth'))
         writer.submit(label_u8, out_paths)
 
+    fuse_upsample = bool(getattr(args, 'fuse_upsample', False))
+
     def flush(images, batch_names):
         x = torch.cat(images).to(dev, non_blocking=True)
-        mains, auxs = [], []
-        for m in model_list:
-            pred, pred_aux = _split_heads(m(x))
-            mains.append(pred.float().contiguous())
-            auxs.append(pred_aux.float().contiguous())
-        r = ops.fuse_sources(mains, auxs, luts, policy=policy, num_classes=num_classes, ignore_label=IGNORE_LABEL,
-                             ds_rate=ds_rate, want_conf=use_cb, want_unc=False, want_conf_hist=use_cb,
-                             class_hist=None if use_cb else class_hist, conf_hist=conf_hist, marginal=marginal)
+        kw = dict(policy=policy, num_classes=num_classes, ignore_label=IGNORE_LABEL, ds_rate=ds_rate, want_conf=use_cb,
+                  want_unc=False, want_conf_hist=use_cb, class_hist=None if use_cb else class_hist, conf_hist=conf_hist,
+                  marginal=marginal)
+        r = None
+        if fuse_upsample:
+            # [NEW] take every source's logits before its closing bilinear upsample and interpolate inside the kernel
+            heads = [forward_lowres(m, x) for m in model_list]
+            if all(h is not None for h in heads):
+                try:
+                    r = ops.fuse_sources_lowres([h[0].float().contiguous() for h in heads],
+                                                [h[1].float().contiguous() for h in heads], luts, x.shape[-2:], **kw)
+                except NotImplementedError:
+                    r = None        # geometry the fused kernel does not cover: fall through to the full-resolution path
+        if r is None:
+            mains, auxs = [], []
+            for m in model_list:
+                pred, pred_aux = _split_heads(m(x))
+                mains.append(pred.float().contiguous())
+                auxs.append(pred_aux.float().contiguous())
+            r = ops.fuse_sources(mains, auxs, luts, **kw)
         if use_cb:      # labels wait on the device until the dataset-wide thresholds are known
             kept_labels.append(r.label), kept_confs.append(r.conf), names.append(batch_names)
         else:

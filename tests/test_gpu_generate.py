@@ -125,3 +125,55 @@ def test_generate_with_class_balanced_thresholds(tmp_path):
         nk = int((base == k).sum())
         if nk >= 50:
             assert abs(int((got == k).sum()) - int(nk * 0.3)) <= max(3, nk // 50)
+
+
+class UpsamplingSource(torch.nn.Module):
+    """Main head at 1/2, aux head at 1/4 resolution, closed by the two bilinear align_corners=True upsamples of ESPDNetUE
+    (model/segmentation/espdnet_ue.py:301-302), plus an unrelated internal interpolate that must NOT be intercepted."""
+
+    def __init__(self, classes, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.main = torch.nn.Conv2d(3, classes, 3, padding=1)
+        self.aux = torch.nn.Conv2d(3, classes, 3, padding=1)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 2.0)
+
+    def forward(self, x):
+        import torch.nn.functional as F
+        size = x.shape[-2:]
+        half = F.interpolate(x, scale_factor=0.5, mode='bilinear', align_corners=True)
+        quarter = F.interpolate(half, scale_factor=0.5, mode='bilinear', align_corners=True)
+        return (F.interpolate(self.main(half), size=size, mode='bilinear', align_corners=True),
+                F.interpolate(self.aux(quarter), size=size, mode='bilinear', align_corners=True))
+
+
+def test_generate_with_fused_upsample(tmp_path):
+    from mspl_b200 import uest_seg_multi_os as U
+    from mspl_b200.lowres import forward_lowres
+    models = [UpsamplingSource(c, 9 + i) for i, (_, c) in enumerate(SOURCES)]
+    names = [n for n, _ in SOURCES]
+    x = torch.randn(2, 3, H, W)
+    heads = forward_lowres(models[0], x)
+    assert heads is not None and heads[0].shape[-2:] == (H // 2, W // 2) and heads[1].shape[-2:] == (H // 4, W // 4)
+    assert forward_lowres(TinySource(5, 1), x) is None                      # no closing upsample -> ordinary path
+    import torch.nn.functional as F
+    assert F.interpolate.__module__ == "torch.nn.functional"               # the wrapper is gone after the call
+    plain, fused = tmp_path / "plain", tmp_path / "fused"
+    lst_a, cw_a = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', str(plain), 0, N, None, None, _args(), None, None,
+                                                      None, testloader=_loader(), batch_images=2)
+    lst_b, cw_b = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', str(fused), 0, N, None, None,
+                                                      _args(fuse_upsample=True), None, None, None, testloader=_loader(), batch_images=2)
+    want, _, _ = _oracle_run(models, names, 'half')
+    saved = O.NEAR_TIE_MARGIN
+    O.NEAR_TIE_MARGIN = 1e-5
+    try:
+        _, _, marg = _oracle_run(models, names, 'half')
+    finally:
+        O.NEAR_TIE_MARGIN = saved
+    for i, (la, lb) in enumerate(zip(open(lst_a), open(lst_b))):
+        a = np.array(Image.open(la.strip().split(',')[1]))
+        b = np.array(Image.open(lb.strip().split(',')[1]))
+        assert not ((a != want[i]) & ~marg[i]).any()
+        assert not ((b != want[i]) & ~marg[i]).any()

@@ -95,6 +95,17 @@ static void run_variant(const char* name, Bench& b, F launch) {
             });                                                                                                                  \
     }
 
+#define LOWRES(NCW, P, CH, NST)                                                                                                  \
+    {                                                                                                                            \
+        FuseParams q = b.prm;                                                                                                    \
+        const size_t smem = lowres_plan(q, NCW * 32 * P, CH, NST);                                                               \
+        if (smem && smem <= 227 * 1024)                                                                                          \
+            run_variant("lowres ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST, b, [&] {                                       \
+                return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true>, q, smem, 0);     \
+            });                                                                                                                  \
+        else printf("lowres ncw=" #NCW " P=" #P " stages=" #NST ": smem %zu does not fit\n", smem);                             \
+    }
+
 static const char* g_filter = nullptr;
 static bool want(const char* key, const char* family) {
     if (!g_filter) return true;
@@ -104,7 +115,7 @@ static bool want(const char* key, const char* family) {
 int main(int argc, char** argv) {
     int64_t n_img = 400, H = 256, W = 480;
     int reps = 5, vote_t = 3, policy = MSPL_POLICY_VOTE;
-    bool hist = true;
+    bool hist = true, lowres = false;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--images")) n_img = atoll(argv[++i]);
         else if (!strcmp(argv[i], "--reps")) reps = atoi(argv[++i]);
@@ -112,6 +123,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--vote")) vote_t = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--prob")) policy = MSPL_POLICY_PROB;
         else if (!strcmp(argv[i], "--nohist")) hist = false;
+        else if (!strcmp(argv[i], "--lowres")) lowres = true;
         else if (!strcmp(argv[i], "--only")) g_filter = argv[++i];
     }
     const int C[3] = {13, 20, 5};
@@ -127,7 +139,8 @@ int main(int argc, char** argv) {
         float *m, *a;
         const int64_t cnt = npix * C[s];
         if (cudaMalloc(&m, cnt * 4) != cudaSuccess || cudaMalloc(&a, cnt * 4) != cudaSuccess) { printf("alloc failed\n"); return 1; }
-        fill_logits<<<148 * 8, 256>>>(m, a, cnt, 0x9e3779b9u * (s + 1), C[s], hw);
+        fill_logits<<<148 * 8, 256>>>(m, a, cnt, 0x9e3779b9u * (s + 1), C[s], lowres ? hw / 4 : hw);
+        b.prm.lr.hm[s] = (int)H / 2; b.prm.lr.wm[s] = (int)W / 2; b.prm.lr.ha[s] = (int)H / 4; b.prm.lr.wa[s] = (int)W / 4;
         b.prm.main[s] = m; b.prm.aux[s] = a; b.prm.C[s] = C[s];
         memcpy(b.prm.lut[s], luts[s], C[s]);
     }
@@ -142,6 +155,20 @@ int main(int argc, char** argv) {
     const bool gk = policy == MSPL_POLICY_PROB || vote_t < 3;
     printf("# k1_sweep: %lld images %lldx%lld, 3 sources 13/20/5, policy=%d vote_t=%d gk=%d hist=%d, %.2f GB of logits\n", (long long)n_img,
            (long long)W, (long long)H, policy, vote_t, (int)gk, (int)hist, npix * 304.0 / 1e9);
+    if (lowres) {
+        // main at H/2 x W/2 and aux at H/4 x W/4 occupy the front of the full-size buffers allocated above
+        b.prm.lr.H = (int)H; b.prm.lr.W = (int)W;
+        LOWRES(15, 2, 5, 4);
+        LOWRES(19, 2, 5, 3);
+        LOWRES(19, 2, 5, 4);
+        LOWRES(23, 2, 5, 3);
+        LOWRES(11, 2, 5, 4);
+        LOWRES(15, 1, 5, 4);
+        LOWRES(23, 1, 5, 4);
+        LOWRES(31, 1, 5, 4);
+        LOWRES(15, 4, 5, 3);
+        return 0;
+    }
     if (!gk) {
         DIRECT(4, 5, 256, 2, false, true);
         DIRECT(4, 5, 256, 1, false, true);
