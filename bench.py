@@ -230,6 +230,34 @@ def emit(line):
     out.flush()
 
 
+def full_size_checks(torch, job, pix_local, world, dist, portion):
+    """Properties that must hold for any input, verified on the very outputs of the timed run (all ranks): histograms are
+    exact pixel counts, thresholding only ever moves a label to the ignore class and keeps conf >= thresh, about `portion`
+    of each class survives, and the global histograms equal the sum of the per-rank bincounts."""
+    ok = {}
+    K = job.class_hist.numel()
+    local_hist = torch.bincount(job.label.reshape(-1).long(), minlength=K)[:K]
+    local_final = torch.bincount(job.final.reshape(-1).long(), minlength=K)[:K]
+    if dist is not None:
+        dist.all_reduce(local_hist)
+        dist.all_reduce(local_final)
+    ok["class_hist_is_bincount_of_labels"] = bool(torch.equal(local_hist, job.class_hist))
+    ok["final_hist_is_bincount_of_final"] = bool(torch.equal(local_final, job.final_hist))
+    ok["histograms_count_every_pixel"] = int(job.class_hist.sum()) == pix_local * world == int(job.final_hist.sum())
+    ok["kept_equals_class_hist"] = bool(torch.equal(job.kept, job.class_hist))
+    changed = job.final != job.label
+    ok["threshold_only_moves_to_ignore"] = bool((job.final[changed] == 4).all())
+    keep = job.final != 4
+    ok["kept_pixels_reach_their_threshold"] = bool((job.conf[keep] >= job.thresh[job.final[keep].long()]).all())
+    ok["dropped_pixels_below_threshold"] = bool((job.conf[changed] < job.thresh[job.label[changed].long()]).all())
+    frac = [(int(job.final_hist[k]) / max(1, int(job.class_hist[k]))) for k in range(1, 4)]
+    ok["kept_fraction_close_to_portion"] = all(abs(f - portion) < 0.01 for f in frac)
+    ok["conf_in_unit_interval"] = bool(((job.conf >= 0) & (job.conf <= 1.0000001)).all())
+    ok["uncertainty_finite_nonnegative"] = bool(torch.isfinite(job.unc).all()) and float(job.unc.min()) > -1e-5
+    ok["all_passed"] = all(v for v in ok.values())
+    return ok
+
+
 def main():
     args = parse_args()
     claim_stdout()
@@ -329,6 +357,9 @@ def main():
                "api": "mspl_b200.pipeline.LabelGenerator.run_from_host (pinned host logits -> uint8 label maps on host)"}
         del hm, ha
 
+    # ---- size-independent properties at the full benchmark size (the CPU oracle cannot run 2,000 images) -------------
+    checks = full_size_checks(torch, job, pix_local, world, dist if world > 1 else None, args.portion)
+
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline(torch, args, args.cpu_seconds)
         kept = job.kept.tolist() if job.kept is not None else None
@@ -336,7 +367,7 @@ def main():
             "metric": "pseudo-labelled Mpix/s (3-source fusion)", "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
             "results": {"near_tie_pixels": int(job.marginal.item()) if job.marginal is not None else None,
                         "class_hist": job.class_hist.tolist(), "final_hist": job.final_hist.tolist(),
                         "thresholds": [round(x, 6) for x in job.thresh.tolist()] if job.thresh is not None else None, "kept": kept},
