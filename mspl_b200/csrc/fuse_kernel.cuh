@@ -41,12 +41,21 @@ struct FuseParams {
     unsigned long long* class_hist;
     unsigned long long* conf_hist;
     unsigned long long* marginal;
+    // Optional candidate compaction for the threshold passes: every pixel that takes part in the per-class order
+    // statistic with a NON-zero-conf entry is appended (key, label) to the calling CTA's region of these arrays;
+    // pixels counted through the conf == 0 fast path are only tallied in zero_count[label].
+    uint32_t* cand_key;
+    uint8_t* cand_label;
+    uint32_t* cand_count;               // one counter per CTA region, written at kernel end
+    unsigned long long* zero_count;     // K
+    int64_t cand_region_cap;
     LowresGeom lr;
 };
 
 // Shared-memory bookkeeping common to both kernels: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B tables]
 inline size_t fuse_tally_smem_bytes(int K) {
-    return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 8) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;   // +16: padded-class table reads
+    // [K*2048 hist][8 class counts][8 misc: candidate cursor, ...][tables] (+16: padded-class table reads)
+    return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 16) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;
 }
 
 // ---- per-pixel accumulation across sources --------------------------------------------------------------------------
@@ -181,6 +190,7 @@ struct Tally {
     MSPL_DEVINL void add(const FuseParams& prm, uint32_t* s_hist, const int (&label)[P], const float (&conf)[P],
                          const bool (&marg)[P], int64_t off, bool active) {
         const bool want_hist = prm.conf_hist != nullptr;
+        uint32_t* s_cursor = s_hist + prm.K * MSPL_RADIX_BINS + 8;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             packed += (unsigned long long)active << (8 * label[p]);
@@ -188,8 +198,24 @@ struct Tally {
             if (want_hist) {
                 const bool keep = active && (prm.ds_rate <= 1 || ((off + p) % prm.ds_rate) == 0);
                 // vote policies give ignore-labelled pixels conf == 0: one known bin, counted without atomics
-                if (prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore) n_ignore_zero += keep;
+                const bool zero_path = prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore;
+                if (zero_path) n_ignore_zero += keep;
                 else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + (float_to_key(conf[p]) >> 21)], 1u);
+                if (prm.cand_key != nullptr) {      // warp-uniform: compact the candidates of radix passes 1-2
+                    const bool cand = keep && !zero_path;
+                    const uint32_t peers = __ballot_sync(__activemask(), cand);
+                    if (peers) {
+                        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(s_cursor, (uint32_t)__popc(peers));
+                        base = __shfl_sync(__activemask(), base, leader);
+                        if (cand) {
+                            const int64_t at = (int64_t)blockIdx.x * prm.cand_region_cap + base + __popc(peers & ((1u << lane) - 1u));
+                            prm.cand_key[at] = float_to_key(conf[p]);
+                            prm.cand_label[at] = (uint8_t)label[p];
+                        }
+                    }
+                }
             }
         }
         if ((pending += P) > 255 - P) spill();
@@ -205,10 +231,14 @@ struct Tally {
             if (leader && w) atomicAdd(&s_cls[k], w);
         }
         const uint32_t wz = __reduce_add_sync(0xffffffffu, n_ignore_zero);
-        if (leader && wz) atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
+        if (leader && wz) {
+            atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
+            if (prm.zero_count) atomicAdd(prm.zero_count + prm.ignore, (unsigned long long)wz);
+        }
         const uint32_t wm = __reduce_add_sync(0xffffffffu, n_marginal);
         if (leader && wm && prm.marginal) atomicAdd(prm.marginal, (unsigned long long)wm);
         __syncthreads();
+        if (threadIdx.x == 0 && prm.cand_count) prm.cand_count[blockIdx.x] = s_cls[8];
         if ((int)threadIdx.x < prm.K && s_cls[threadIdx.x]) atomicAdd(prm.class_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
         if (prm.conf_hist)
             for (int i = threadIdx.x; i < prm.K * MSPL_RADIX_BINS; i += nthreads)
@@ -220,10 +250,10 @@ MSPL_DEVINL void tally_smem_init(const FuseParams& prm, unsigned char* smem, uin
                                  int nthreads) {
     const int nbins = prm.K * MSPL_RADIX_BINS;
     s_hist = reinterpret_cast<uint32_t*>(smem);
-    s_cls = s_hist + nbins;
-    s_lut = reinterpret_cast<uint8_t*>(s_cls + 8);
+    s_cls = s_hist + nbins;                              // s_cls[0..7]: class counts, s_cls[8]: candidate cursor
+    s_lut = reinterpret_cast<uint8_t*>(s_cls + 16);
     for (int i = threadIdx.x; i < nbins; i += nthreads) s_hist[i] = 0;
-    if (threadIdx.x < 8) s_cls[threadIdx.x] = 0;
+    if (threadIdx.x < 16) s_cls[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += nthreads)
         s_lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
 }
@@ -357,6 +387,12 @@ template <> MSPL_DEVINL void lds<4>(const float* p, float (&v)[4]) {
 
 }  // namespace tma
 
+// 1: the first chunk of a source skips the rescale of the (empty) accumulators, which makes the compiler peel that
+// iteration (two copies of the chunk body, ~38 KB of code); 0: one copy, the rescale runs on empty accumulators too.
+#ifndef MSPL_PEEL_FIRST
+#define MSPL_PEEL_FIRST 1
+#endif
+
 template <int NCW, int P, int CH, int NSTAGE>
 struct TmaCfg {
     static constexpr int kThreads = (NCW + 1) * 32;
@@ -410,8 +446,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                     const int cn = min(CH, C - c0);
                     tma::mbar_wait(&empty[stage], phase ^ 1);          // all consumers released this slot
                     float* dst = ring + (size_t)stage * Cfg::kStageFloats;
-                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);
+                    if (cn < CH) {
+                        // tail chunk: the class rows this source does not have are filled with kPadLogit HERE, so that the
+                        // consumers' loads and math carry no predicates and exist only once in the instruction stream
+                        const float4 pad = make_float4(kPadLogit, kPadLogit, kPadLogit, kPadLogit);
+                        for (int j = cn; j < CH; ++j)
+                            for (int i = lane; i < TP / 4; i += 32) {
+                                reinterpret_cast<float4*>(dst + j * TP)[i] = pad;
+                                reinterpret_cast<float4*>(dst + (CH + j) * TP)[i] = pad;
+                            }
+                        __threadfence_block();
+                    }
                     __syncwarp();
+                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);   // release: publishes the padding too
                     for (int j = lane; j < 2 * cn; j += 32) {
                         const int head = j >= cn, c = head ? j - cn : j;
                         const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
@@ -439,27 +486,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                 st.reset();
                 float zk[KT][P];
                 reset_zk<KT, P>(zk);
+#pragma unroll 1
                 for (int c0 = 0; c0 < C; c0 += CH) {
-                    const int cn = min(CH, C - c0);
                     float m[CH][P], a[CH][P];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * Cfg::kStageFloats + px;
-                    if (cn == CH) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) tma::lds<P>(src + j * TP, m[j]);
+                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + j * TP, m[j]);
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) tma::lds<P>(src + (CH + j) * TP, a[j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            if (j < cn) { tma::lds<P>(src + j * TP, m[j]); tma::lds<P>(src + (CH + j) * TP, a[j]); }
-                            else { fill_pad<P>(m[j]); fill_pad<P>(a[j]); }
-                        }
-                    }
+                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + (CH + j) * TP, a[j]);
                     __syncwarp();
                     if (lane == 0) tma::mbar_arrive(&empty[stage]);    // values are in registers: hand the slot back
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, MSPL_PEEL_FIRST ? c0 == 0 : false, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
                 }
                 float d[P];
                 const int64_t goff = (n * C) * hw + (active ? off : 0);
@@ -568,8 +607,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                     const int cn = min(CH, C - c0);
                     tma::mbar_wait(&empty[stage], phase ^ 1);
                     float* dst = ring + (size_t)stage * lr.stage_floats;
-                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], cn * (mbytes + abytes));
+                    if (cn < CH) {      // pad the class blocks a tail chunk lacks (see fuse_sources_tma_kernel)
+                        const float4 pad = make_float4(kPadLogit, kPadLogit, kPadLogit, kPadLogit);
+                        for (int j = cn; j < CH; ++j) {
+                            for (int i = lane; i < (int)(mbytes / 16); i += 32) reinterpret_cast<float4*>(dst + j * lr.main_cls_stride)[i] = pad;
+                            for (int i = lane; i < (int)(abytes / 16); i += 32)
+                                reinterpret_cast<float4*>(dst + lr.aux_base + j * lr.aux_cls_stride)[i] = pad;
+                        }
+                        __threadfence_block();
+                    }
                     __syncwarp();
+                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], cn * (mbytes + abytes));
                     for (int j = lane; j < 2 * cn; j += 32) {
                         const int head = j >= cn, c = head ? j - cn : j;
                         if (head) tma::bulk_g2s(dst + lr.aux_base + c * lr.aux_cls_stride, pa + (int64_t)(c0 + c) * ha * wa, abytes, &full[stage], policy);
@@ -615,22 +663,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 st.reset();
                 float zk[KT][P];
                 reset_zk<KT, P>(zk);
+#pragma unroll 1
                 for (int c0 = 0; c0 < C; c0 += CH) {
-                    const int cn = min(CH, C - c0);
                     float m[CH][P], a[CH][P];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * lr.stage_floats;
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
-                        if (j < cn) {
 #pragma unroll
-                            for (int p = 0; p < P; ++p) {
-                                m[j][p] = bilinear(src + j * lr.main_cls_stride, tm[p]);
-                                a[j][p] = bilinear(src + lr.aux_base + j * lr.aux_cls_stride, ta[p]);
-                            }
-                        } else {
-                            fill_pad<P>(m[j]);
-                            fill_pad<P>(a[j]);
+                        for (int p = 0; p < P; ++p) {
+                            m[j][p] = bilinear(src + j * lr.main_cls_stride, tm[p]);
+                            a[j][p] = bilinear(src + lr.aux_base + j * lr.aux_cls_stride, ta[p]);
                         }
                     }
                     __syncwarp();

@@ -59,7 +59,9 @@ struct SourceStats {
     MSPL_DEVINL void reset() {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            Mm[p] = Ma[p] = Mz[p] = z2[p] = -INFINITY;
+            // finite sentinel (not -inf): the rescale of an empty accumulator then evaluates to exactly 0 without NaNs, so
+            // kernels may run it unconditionally on a source's first chunk
+            Mm[p] = Ma[p] = Mz[p] = z2[p] = -1.0e30f;
             Sm[p] = Sa[p] = Sz[p] = T[p] = 0.f;
             amax[p] = 0;
         }
@@ -155,8 +157,10 @@ MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
 }
 
 // Slow path for a degenerate pixel: recompute 1/sum_c e^{z_c - Mz} directly from global memory (rare; divergent).
-MSPL_DEVINL float recompute_pmax(const float* __restrict__ pm, const float* __restrict__ pa, int C, int64_t hw, float Mz) {
+// Deliberately out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
+static __device__ __noinline__ float recompute_pmax(const float* __restrict__ pm, const float* __restrict__ pa, int C, int64_t hw, float Mz) {
     float s = 0.f;
+#pragma unroll 1
     for (int c = 0; c < C; ++c) s += exp_neg(fmaf(0.5f, __ldg(pa + c * hw), __ldg(pm + c * hw)) - Mz);
     return __frcp_rn(s);
 }
