@@ -91,27 +91,6 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
                       float* const* kld_per_source, unsigned long long* class_hist,
                       unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream);
 
-/* K1 with candidate compaction for the threshold passes: in addition to everything mspl_fuse_sources does, every pixel that
- * enters a class's order statistic with a non-zero-conf entry is appended as (order-preserving key of conf, label) to the
- * region of the CTA that processed it, and pixels tallied through the conf == 0 fast path (ignore-labelled pixels of the vote
- * policies) are counted in zero_count[label] (K u64, +=).  mspl_radix_hist_pass_compact then runs radix passes 1-2 on those
- * few % of the pixels instead of re-reading label+conf of the whole dataset.  Layout: mspl_fuse_candidate_layout() gives
- * num_regions and region_capacity; cand_key (u32) and cand_label (u8) hold num_regions*region_capacity entries, cand_count
- * num_regions u32.  Returns MSPL_ERR_UNSUPPORTED for shapes served by the scalar fallback kernel (use the plain passes). */
-MSPL_API int mspl_fuse_candidate_layout(int num_sources, int64_t num_images, int64_t pixels_per_image, int policy, int vote_t,
-                               int64_t* num_regions, int64_t* region_capacity);
-MSPL_API int mspl_fuse_sources_compact(int num_sources, const float* const* main_logits, const float* const* aux_logits,
-                              const int* num_classes, const uint8_t* const* lut, int64_t num_images,
-                              int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
-                              int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
-                              float* const* kld_per_source, unsigned long long* class_hist,
-                              unsigned long long* conf_hist, unsigned long long* marginal_count, uint32_t* cand_key,
-                              uint8_t* cand_label, uint32_t* cand_count, unsigned long long* zero_count,
-                              int64_t num_regions, int64_t region_capacity, void* stream);
-MSPL_API int mspl_radix_hist_pass_compact(const uint32_t* cand_key, const uint8_t* cand_label, const uint32_t* cand_count,
-                                 int64_t num_regions, int64_t region_capacity, const unsigned long long* zero_count,
-                                 int num_target_classes, int pass, const void* state, unsigned long long* hist, void* stream);
-
 /* ---- K1-lowres: K1 with the network's final upsample fused in (next-row component) ------------------
  * Same outputs and semantics as mspl_fuse_sources, but source s hands over its logits BEFORE the final
  * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) of model/segmentation/espdnet_ue.py:301-302:

@@ -20,10 +20,6 @@ SIGNATURES = {
     "mspl_softmax_kld": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "mspl_fuse_sources": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mspl_fuse_candidate_layout": (c_int, [c_int, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
-    "mspl_fuse_sources_compact": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
-                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "mspl_radix_hist_pass_compact": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "mspl_fuse_sources_lowres": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_vote_labels": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp]),

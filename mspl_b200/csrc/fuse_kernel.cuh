@@ -41,20 +41,12 @@ struct FuseParams {
     unsigned long long* class_hist;
     unsigned long long* conf_hist;
     unsigned long long* marginal;
-    // Optional candidate compaction for the threshold passes: every pixel that takes part in the per-class order
-    // statistic with a NON-zero-conf entry is appended (key, label) to the calling CTA's region of these arrays;
-    // pixels counted through the conf == 0 fast path are only tallied in zero_count[label].
-    uint32_t* cand_key;
-    uint8_t* cand_label;
-    uint32_t* cand_count;               // one counter per CTA region, written at kernel end
-    unsigned long long* zero_count;     // K
-    int64_t cand_region_cap;
     LowresGeom lr;
 };
 
 // Shared-memory bookkeeping common to both kernels: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B tables]
 inline size_t fuse_tally_smem_bytes(int K) {
-    // [K*2048 hist][8 class counts][8 misc: candidate cursor, ...][tables] (+16: padded-class table reads)
+    // [K*2048 hist][16 u32: class counts + spare][tables] (+16: padded-class table reads)
     return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 16) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;
 }
 
@@ -190,7 +182,6 @@ struct Tally {
     MSPL_DEVINL void add(const FuseParams& prm, uint32_t* s_hist, const int (&label)[P], const float (&conf)[P],
                          const bool (&marg)[P], int64_t off, bool active) {
         const bool want_hist = prm.conf_hist != nullptr;
-        uint32_t* s_cursor = s_hist + prm.K * MSPL_RADIX_BINS + 8;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             packed += (unsigned long long)active << (8 * label[p]);
@@ -198,24 +189,8 @@ struct Tally {
             if (want_hist) {
                 const bool keep = active && (prm.ds_rate <= 1 || ((off + p) % prm.ds_rate) == 0);
                 // vote policies give ignore-labelled pixels conf == 0: one known bin, counted without atomics
-                const bool zero_path = prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore;
-                if (zero_path) n_ignore_zero += keep;
+                if (prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore) n_ignore_zero += keep;
                 else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + (float_to_key(conf[p]) >> 21)], 1u);
-                if (prm.cand_key != nullptr) {      // warp-uniform: compact the candidates of radix passes 1-2
-                    const bool cand = keep && !zero_path;
-                    const uint32_t peers = __ballot_sync(__activemask(), cand);
-                    if (peers) {
-                        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-                        uint32_t base = 0;
-                        if (lane == leader) base = atomicAdd(s_cursor, (uint32_t)__popc(peers));
-                        base = __shfl_sync(__activemask(), base, leader);
-                        if (cand) {
-                            const int64_t at = (int64_t)blockIdx.x * prm.cand_region_cap + base + __popc(peers & ((1u << lane) - 1u));
-                            prm.cand_key[at] = float_to_key(conf[p]);
-                            prm.cand_label[at] = (uint8_t)label[p];
-                        }
-                    }
-                }
             }
         }
         if ((pending += P) > 255 - P) spill();
@@ -231,14 +206,10 @@ struct Tally {
             if (leader && w) atomicAdd(&s_cls[k], w);
         }
         const uint32_t wz = __reduce_add_sync(0xffffffffu, n_ignore_zero);
-        if (leader && wz) {
-            atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
-            if (prm.zero_count) atomicAdd(prm.zero_count + prm.ignore, (unsigned long long)wz);
-        }
+        if (leader && wz) atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
         const uint32_t wm = __reduce_add_sync(0xffffffffu, n_marginal);
         if (leader && wm && prm.marginal) atomicAdd(prm.marginal, (unsigned long long)wm);
         __syncthreads();
-        if (threadIdx.x == 0 && prm.cand_count) prm.cand_count[blockIdx.x] = s_cls[8];
         if ((int)threadIdx.x < prm.K && s_cls[threadIdx.x]) atomicAdd(prm.class_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
         if (prm.conf_hist)
             for (int i = threadIdx.x; i < prm.K * MSPL_RADIX_BINS; i += nthreads)
@@ -250,7 +221,7 @@ MSPL_DEVINL void tally_smem_init(const FuseParams& prm, unsigned char* smem, uin
                                  int nthreads) {
     const int nbins = prm.K * MSPL_RADIX_BINS;
     s_hist = reinterpret_cast<uint32_t*>(smem);
-    s_cls = s_hist + nbins;                              // s_cls[0..7]: class counts, s_cls[8]: candidate cursor
+    s_cls = s_hist + nbins;
     s_lut = reinterpret_cast<uint8_t*>(s_cls + 16);
     for (int i = threadIdx.x; i < nbins; i += nthreads) s_hist[i] = 0;
     if (threadIdx.x < 16) s_cls[threadIdx.x] = 0;

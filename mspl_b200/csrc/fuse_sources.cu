@@ -77,30 +77,12 @@ extern "C" const char* mspl_fuse_variant(void) {
     return name;
 }
 
-struct CandidateSink {
-    uint32_t* key = nullptr;
-    uint8_t* label = nullptr;
-    uint32_t* count = nullptr;
-    unsigned long long* zero_count = nullptr;
-    int64_t num_regions = 0, region_capacity = 0;
-};
-
-// Candidate regions of the TMA-staged kernel: one per CTA of the persistent grid, each able to hold every pixel that CTA
-// can be handed (tiles are dealt round-robin).
-static void candidate_layout(int64_t num_images, int64_t hw, bool gk, int sms, int64_t* regions, int64_t* capacity) {
-    const int64_t tp = gk ? TmaCfgPerClass::kTilePix : TmaCfgVoteAll::kTilePix;
-    const int64_t n_tiles = num_images * ((hw + tp - 1) / tp);
-    const int64_t grid = n_tiles < sms ? n_tiles : sms;
-    *regions = grid;
-    *capacity = grid > 0 ? ((n_tiles + grid - 1) / grid) * tp : 0;
-}
-
-static int fuse_impl(int num_sources, const float* const* main_logits, const float* const* aux_logits,
-                     const int* num_classes, const uint8_t* const* lut, int64_t num_images,
-                     int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
-                     int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
-                     float* const* kld_per_source, unsigned long long* class_hist,
-                     unsigned long long* conf_hist, unsigned long long* marginal_count, const CandidateSink* sink, void* stream) {
+extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
+                                 const int* num_classes, const uint8_t* const* lut, int64_t num_images,
+                                 int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
+                                 int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
+                                 float* const* kld_per_source, unsigned long long* class_hist,
+                                 unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream) {
     const int S = num_sources, K = num_target_classes;
     if (S < 1 || S > MSPL_MAX_SOURCES || K < 2 || K > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
     if (!main_logits || !aux_logits || !num_classes || !lut || !label || !class_hist) return MSPL_ERR_BAD_ARG;
@@ -141,56 +123,7 @@ static int fuse_impl(int num_sources, const float* const* main_logits, const flo
     // Per-target-class probabilities are only needed when a pixel can win without every source's vote.
     const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (sink) {
-        if (!conf_hist || !sink->key || !sink->label || !sink->count || !sink->zero_count) return MSPL_ERR_BAD_ARG;
-        if (!(MSPL_USE_TMA && P == 4 && tma_eligible<TmaCfgVoteAll>(prm))) return MSPL_ERR_UNSUPPORTED;   // direct path: no regions
-        int64_t regions = 0, cap = 0;
-        const DeviceInfo di = device_info();
-        if (!di.ok) return MSPL_ERR_CUDA;
-        candidate_layout(num_images, pixels_per_image, gk, di.sms, &regions, &cap);
-        if (sink->num_regions != regions || sink->region_capacity != cap) return MSPL_ERR_BAD_ARG;
-        prm.cand_key = sink->key; prm.cand_label = sink->label; prm.cand_count = sink->count;
-        prm.zero_count = sink->zero_count; prm.cand_region_cap = cap;
-    }
     return K <= 5 ? dispatch_fuse<5>(prm, P, gk, st) : dispatch_fuse<8>(prm, P, gk, st);
-}
-
-extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
-                                 const int* num_classes, const uint8_t* const* lut, int64_t num_images,
-                                 int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
-                                 int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
-                                 float* const* kld_per_source, unsigned long long* class_hist,
-                                 unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream) {
-    return fuse_impl(num_sources, main_logits, aux_logits, num_classes, lut, num_images, pixels_per_image, num_target_classes, policy,
-                     vote_t, ignore_label, ds_rate, label, conf, unc, kld_per_source, class_hist, conf_hist, marginal_count, nullptr,
-                     stream);
-}
-
-extern "C" int mspl_fuse_candidate_layout(int num_sources, int64_t num_images, int64_t pixels_per_image, int policy, int vote_t,
-                                          int64_t* num_regions, int64_t* region_capacity) {
-    if (!num_regions || !region_capacity || num_sources < 1 || num_images < 0 || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
-    if (pixels_per_image % 4 != 0) return MSPL_ERR_UNSUPPORTED;
-    const DeviceInfo di = device_info();
-    if (!di.ok) return MSPL_ERR_CUDA;
-    const bool gk = (policy == MSPL_POLICY_PROB) || ((vote_t < 1 ? 1 : vote_t) < num_sources);
-    candidate_layout(num_images, pixels_per_image, gk, di.sms, num_regions, region_capacity);
-    return MSPL_OK;
-}
-
-extern "C" int mspl_fuse_sources_compact(int num_sources, const float* const* main_logits, const float* const* aux_logits,
-                                         const int* num_classes, const uint8_t* const* lut, int64_t num_images,
-                                         int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
-                                         int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
-                                         float* const* kld_per_source, unsigned long long* class_hist,
-                                         unsigned long long* conf_hist, unsigned long long* marginal_count, uint32_t* cand_key,
-                                         uint8_t* cand_label, uint32_t* cand_count, unsigned long long* zero_count,
-                                         int64_t num_regions, int64_t region_capacity, void* stream) {
-    CandidateSink sink;
-    sink.key = cand_key; sink.label = cand_label; sink.count = cand_count; sink.zero_count = zero_count;
-    sink.num_regions = num_regions; sink.region_capacity = region_capacity;
-    return fuse_impl(num_sources, main_logits, aux_logits, num_classes, lut, num_images, pixels_per_image, num_target_classes, policy,
-                     vote_t, ignore_label, ds_rate, label, conf, unc, kld_per_source, class_hist, conf_hist, marginal_count, &sink,
-                     stream);
 }
 
 extern "C" int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,

@@ -107,45 +107,6 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
         if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
 }
 
-// Radix passes 1-2 over the COMPACTED candidates K1 wrote (key + label of every pixel that takes part in a class's order
-// statistic with a non-zero-conf entry; a few % of the pixels), instead of re-reading label+conf of the whole dataset.
-// blockIdx.y = candidate region (one per K1 CTA), blockIdx.x = slice of the region.  zero_count[k] (pixels tallied through
-// the conf == 0 fast path) is added to the zero key's bin by block (0,0).
-template <int PASS>
-__global__ void __launch_bounds__(kHistThreads) radix_hist_cand_kernel(const uint32_t* __restrict__ cand_key, const uint8_t* __restrict__ cand_label,
-                                                                       const uint32_t* __restrict__ cand_count, int64_t region_cap,
-                                                                       const unsigned long long* __restrict__ zero_count, int K,
-                                                                       const RadixState* __restrict__ state,
-                                                                       unsigned long long* __restrict__ hist) {
-    extern __shared__ uint32_t s_hist[];
-    __shared__ uint32_t s_prefix[MSPL_MAX_CLASSES + 1];
-    const int nbins = K * MSPL_RADIX_BINS;
-    const uint32_t count = cand_count[blockIdx.y];
-    const uint32_t first = blockIdx.x * kHistThreads + threadIdx.x, step = gridDim.x * kHistThreads;
-    if (blockIdx.x * kHistThreads >= count && !(blockIdx.x == 0 && blockIdx.y == 0)) return;     // nothing for this block
-    for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
-    if (threadIdx.x <= MSPL_MAX_CLASSES) {
-        const int k = threadIdx.x;
-        s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;
-    }
-    __syncthreads();
-    const uint32_t* keys = cand_key + (int64_t)blockIdx.y * region_cap;
-    const uint8_t* labs = cand_label + (int64_t)blockIdx.y * region_cap;
-    for (uint32_t i = first; i < count; i += step) {
-        const uint32_t key = __ldcs(keys + i);
-        const uint32_t lab = min((uint32_t)__ldcs(labs + i), (uint32_t)MSPL_MAX_CLASSES);
-        if (radix_prefix(key, PASS) == s_prefix[lab]) atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, PASS)], 1u);
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
-        constexpr uint32_t zero_key = 0x80000000u;
-        const unsigned long long z = zero_count[threadIdx.x];
-        if (z && radix_prefix(zero_key, PASS) == s_prefix[threadIdx.x]) atomicAdd(hist + threadIdx.x * MSPL_RADIX_BINS + radix_digit(zero_key, PASS), z);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nbins; i += kHistThreads)
-        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
-}
-
 // One CTA per class: locate the bin holding the rank-th largest key, extend the prefix, zero the histogram row.
 __global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* __restrict__ hist, int pass, double portion,
                                                            RadixState* __restrict__ state, float* __restrict__ thresh,
@@ -295,28 +256,6 @@ extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int
     const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, kHistThreads, 4);
     kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K,
                                                      static_cast<const RadixState*>(state), hist, ds_rate);
-    return launch_status();
-}
-
-extern "C" int mspl_radix_hist_pass_compact(const uint32_t* cand_key, const uint8_t* cand_label, const uint32_t* cand_count,
-                                            int64_t num_regions, int64_t region_capacity, const unsigned long long* zero_count,
-                                            int num_target_classes, int pass, const void* state, unsigned long long* hist,
-                                            void* stream) {
-    const int K = num_target_classes;
-    if (!cand_key || !cand_label || !cand_count || !zero_count || !state || !hist) return MSPL_ERR_BAD_ARG;
-    if (K < 1 || K > MSPL_MAX_CLASSES || pass < 1 || pass >= MSPL_RADIX_PASSES || num_regions < 0 || region_capacity < 0) return MSPL_ERR_BAD_ARG;
-    if (num_regions == 0) return MSPL_OK;
-    if (num_regions > 65535) return MSPL_ERR_UNSUPPORTED;
-    const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
-    auto kern = pass == 1 ? radix_hist_cand_kernel<1> : radix_hist_cand_kernel<2>;
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return MSPL_ERR_CUDA;
-    }
-    int64_t slices = (region_capacity + kHistThreads * 64 - 1) / (kHistThreads * 64);      // >= 64 candidates per thread at capacity
-    slices = slices < 1 ? 1 : (slices > 8 ? 8 : slices);
-    kern<<<dim3((unsigned)slices, (unsigned)num_regions), kHistThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        cand_key, cand_label, cand_count, region_capacity, zero_count, K, static_cast<const RadixState*>(state), hist);
     return launch_status();
 }
 

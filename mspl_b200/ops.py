@@ -18,9 +18,7 @@ MAX_SOURCES = 8
 MAX_CLASSES = 8
 POLICY_VOTE, POLICY_PROB = 0, 1
 
-FuseResult = namedtuple("FuseResult", "label conf unc kld class_hist conf_hist marginal candidates", defaults=(None,))
-# compacted (key, label) candidates of radix passes 1-2 written by K1 (see mspl_fuse_sources_compact)
-Candidates = namedtuple("Candidates", "key label count zero_count num_regions region_capacity")
+FuseResult = namedtuple("FuseResult", "label conf unc kld class_hist conf_hist marginal")
 
 
 def _require_cuda(t, name, dtype=None, ndim=None):
@@ -68,16 +66,14 @@ def _lut_bytes(lut, num_src_classes, num_classes):
 
 def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4, ds_rate=1,
                  want_conf=True, want_unc=True, want_kld=False, want_conf_hist=True, count_marginal=True,
-                 class_hist=None, conf_hist=None, marginal=None, label_out=None, conf_out=None, unc_out=None,
-                 want_candidates=False):
+                 class_hist=None, conf_hist=None, marginal=None, label_out=None, conf_out=None, unc_out=None):
     """K1: fused multi-source pseudo-label generation (replaces uest_seg_multi_os.py:897-921).
 
     mains/auxs: lists (one entry per source) of (N, C_s, H, W) fp32 CUDA logits; luts: per-source tables
     source class -> target class.  policy: 'half' | 'all' | int (the reference's vote, merge_outputs) or
     'prob' ([NEW] averaged greenhouse-class probabilities).  Histogram / counter tensors passed in are
     accumulated into (int64); otherwise fresh zeroed ones are returned.  label_out/conf_out/unc_out: optional
-    preallocated (N,H,W) outputs (e.g. slices of a dataset-wide map).  want_candidates: also compact the (key, label) pairs
-    the threshold passes need (result.candidates; silently None for shapes served by the scalar fallback kernel).
+    preallocated (N,H,W) outputs (e.g. slices of a dataset-wide map).
     """
     S = len(mains)
     if S < 1 or S > MAX_SOURCES or len(auxs) != S or len(luts) != S:
@@ -130,33 +126,14 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
     if n == 0:      # nothing to label: empty maps, untouched histograms
         return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
                           marginal if count_marginal else None)
-    cands = None
     with torch.cuda.device(dev):
-        if want_candidates and want_conf_hist and hw % 4 == 0:
-            regions, cap = ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.check(lib.mspl_fuse_candidate_layout(S, n, hw, pol, vt, ctypes.byref(regions), ctypes.byref(cap)),
-                       "mspl_fuse_candidate_layout")
-            total = regions.value * cap.value
-            cands = Candidates(torch.empty(total, dtype=torch.int32, device=dev), torch.empty(total, dtype=torch.uint8, device=dev),
-                               torch.zeros(regions.value, dtype=torch.int32, device=dev),
-                               torch.zeros(num_classes, dtype=torch.int64, device=dev), regions.value, cap.value)
-            st = lib.mspl_fuse_sources_compact(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, n, hw, num_classes, pol, vt,
-                                               ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,
-                                               _ptr(class_hist), _ptr(conf_hist), _ptr(marginal if count_marginal else None),
-                                               _ptr(cands.key), _ptr(cands.label), _ptr(cands.count), _ptr(cands.zero_count),
-                                               cands.num_regions, cands.region_capacity, _stream(dev))
-            if st == -3:        # unaligned views: the scalar kernel has no candidate regions
-                cands = None
-            else:
-                _lib.check(st, "mspl_fuse_sources_compact")
-        if cands is None:
-            st = lib.mspl_fuse_sources(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, n, hw, num_classes, pol, vt,
-                                       ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,
-                                       _ptr(class_hist), _ptr(conf_hist if want_conf_hist else None),
-                                       _ptr(marginal if count_marginal else None), _stream(dev))
-            _lib.check(st, "mspl_fuse_sources")
+        st = lib.mspl_fuse_sources(S, main_ptrs, aux_ptrs, ncls, lut_ptrs, n, hw, num_classes, pol, vt,
+                                   ignore_label, int(ds_rate), _ptr(label), _ptr(conf), _ptr(unc), kld_ptrs,
+                                   _ptr(class_hist), _ptr(conf_hist if want_conf_hist else None),
+                                   _ptr(marginal if count_marginal else None), _stream(dev))
+    _lib.check(st, "mspl_fuse_sources")
     return FuseResult(label, conf, unc, kld, class_hist, conf_hist if want_conf_hist else None,
-                      marginal if count_marginal else None, cands)
+                      marginal if count_marginal else None)
 
 
 def fuse_sources_lowres(mains, auxs, luts, out_size, policy='half', num_classes=5, ignore_label=4, ds_rate=1,
@@ -250,14 +227,13 @@ def softmax_kld(main, aux, want_prob=True, want_kld=True):
     return prob, kld
 
 
-def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None, candidates=None):
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None):
     """K2: class-balanced thresholds by 3-pass radix select; exact order statistics, no sort, no host sync.
 
     label (N,H,W) u8, conf (N,H,W) f32.  conf_hist: the pass-0 histogram already accumulated by fuse_sources
     (it is consumed: zeroed on return); if None, pass 0 is computed here.  all_reduce: optional callable applied
     in place to each pass's (K, 2048) int64 histogram (e.g. ``lambda h: dist.all_reduce(h)``) so that every rank
-    selects the same bins -- thresholds are then identical for 1 or N GPUs.  candidates: the compacted (key, label) list the
-    same fuse_sources call produced (requires conf_hist from that call); passes 1-2 then touch only those entries.
+    selects the same bins -- thresholds are then identical for 1 or N GPUs.
     Returns (thresh f32 (K,), kept_count int64 (K,)).
     """
     label = _require_cuda(label, "label", torch.uint8)
@@ -280,12 +256,7 @@ def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=
     with torch.cuda.device(dev):
         st = _stream(dev)
         for p in range(RADIX_PASSES):
-            if p > 0 and candidates is not None and conf_hist is not None:
-                c = candidates
-                _lib.check(lib.mspl_radix_hist_pass_compact(_ptr(c.key), _ptr(c.label), _ptr(c.count), c.num_regions,
-                                                            c.region_capacity, _ptr(c.zero_count), K, p, _ptr(state), _ptr(hist),
-                                                            st), "mspl_radix_hist_pass_compact")
-            elif p > 0 or conf_hist is None:
+            if p > 0 or conf_hist is None:
                 _lib.check(lib.mspl_radix_hist_pass(_ptr(label), _ptr(conf), npix, hw, K, p, _ptr(state), _ptr(hist),
                                                     int(ds_rate), st), "mspl_radix_hist_pass")
             if all_reduce is not None:

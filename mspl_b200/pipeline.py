@@ -84,7 +84,7 @@ class LabelGenerator:
             e0.record()
         r = ops.fuse_sources(mains, auxs, self.luts, policy=self.policy, num_classes=self.num_classes,
                              ignore_label=self.ignore_label, ds_rate=self.ds_rate, want_conf=self.thresholds,
-                             want_unc=want_unc, want_conf_hist=self.thresholds, want_candidates=self.thresholds)
+                             want_unc=want_unc, want_conf_hist=self.thresholds)
         if self.k1_events is not None:
             e1.record()
             self.k1_events.append((e0, e1))
@@ -94,8 +94,7 @@ class LabelGenerator:
         if not self.thresholds:
             return LabelJob(r.label, r.label, None, r.conf, r.unc, None, None, class_hist, class_hist, marginal)
         thresh, kept = ops.cb_thresholds(r.label, r.conf, self.portion, self.ds_rate, self.num_classes,
-                                         conf_hist=r.conf_hist, all_reduce=self._all_reduce if self._world() > 1 else None,
-                                         candidates=getattr(r, "candidates", None))
+                                         conf_hist=r.conf_hist, all_reduce=self._all_reduce if self._world() > 1 else None)
         self.launches += 5         # radix passes 1-2 (hist) + three selects
         final, mask, final_hist = ops.apply_thresholds(r.label, r.conf, thresh, self.ignore_label, want_mask=want_mask)
         self.launches += 1

@@ -25,7 +25,7 @@ def _prefix(keys, p):
 
 def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4, ds_rate=1, want_conf=True, want_unc=True,
                  want_kld=False, want_conf_hist=True, count_marginal=True, class_hist=None, conf_hist=None, marginal=None,
-                 label_out=None, conf_out=None, unc_out=None, want_candidates=False):
+                 label_out=None, conf_out=None, unc_out=None):
     r = O.fuse_sources(mains, auxs, luts, policy, num_classes, ignore_label)
     h, w = r["label"].shape[-2:]
     ch = r["class_hist"].clone() if class_hist is None else class_hist.add_(r["class_hist"])
@@ -42,7 +42,7 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
     return FuseResult(r["label"], r["conf"], r["unc"], r["kld"] if want_kld else None, ch, hist, marg)
 
 
-def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None, candidates=None):
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None):
     """3-pass radix select written with torch ops (independent of the CUDA implementation)."""
     h, w = label.shape[-2:]
     keep = (torch.arange(h * w) % ds_rate == 0).reshape(h, w).expand(label.shape)

@@ -236,16 +236,10 @@ def test_cb_thresholds_exact(ops, dev, portion, ds_rate):
     for policy in ("half", "prob"):
         r = _fuse(ops, dev, mains, auxs, luts, policy, ds_rate=ds_rate)
         th_ref, kept_ref = O.cb_thresholds(r.label.cpu(), r.conf.cpu(), portion, ds_rate)
-        rc = _fuse(ops, dev, mains, auxs, luts, policy, ds_rate=ds_rate, want_candidates=True)
-        assert rc.candidates is not None and torch.equal(rc.label, r.label) and torch.equal(rc.conf, r.conf)
-        assert torch.equal(rc.conf_hist, r.conf_hist)
-        assert int(rc.candidates.count.sum()) + int(rc.candidates.zero_count.sum()) == int(rc.conf_hist.sum())
-        th_c, kept_c = ops.cb_thresholds(rc.label, rc.conf, portion, ds_rate, conf_hist=rc.conf_hist, candidates=rc.candidates)
         th_a, kept_a = ops.cb_thresholds(r.label, r.conf, portion, ds_rate)                  # pass 0 computed standalone
         th_b, kept_b = ops.cb_thresholds(r.label, r.conf, portion, ds_rate, conf_hist=r.conf_hist)   # pass 0 fused in K1
         assert torch.equal(th_a.cpu(), th_ref) and torch.equal(kept_a.cpu(), kept_ref)
         assert torch.equal(th_b.cpu(), th_ref) and torch.equal(kept_b.cpu(), kept_ref)
-        assert torch.equal(th_c.cpu(), th_ref) and torch.equal(kept_c.cpu(), kept_ref)          # compacted passes 1-2
         final, mask, fh = ops.apply_thresholds(r.label, r.conf, th_a)
         f_ref, m_ref = O.apply_thresholds(r.label.cpu(), r.conf.cpu(), th_ref)
         assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
@@ -392,9 +386,6 @@ def test_full_size_properties(ops, dev):
         assert torch.equal(r.conf_hist.sum(dim=1), r.class_hist)
         assert int(r.class_hist.sum()) == n * h * w
         th, kept = ops.cb_thresholds(r.label, r.conf, 0.2, conf_hist=r.conf_hist.clone())
-        rc = ops.fuse_sources(mains, auxs, luts, policy=policy, want_candidates=True)
-        th_c, _ = ops.cb_thresholds(rc.label, rc.conf, 0.2, conf_hist=rc.conf_hist, candidates=rc.candidates)
-        assert torch.equal(th_c, th)
         # 2-way "sharded" thresholds: histograms of the two halves are summed before each select
         halves = [(ra.label, ra.conf), (rb.label, rb.conf)]
         th2 = _sharded_thresholds(ops, halves, 0.2)
