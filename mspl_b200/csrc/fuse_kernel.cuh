@@ -373,6 +373,54 @@ struct TmaCfg {
     static size_t smem_bytes(int K) { return kRingBytes + 2 * NSTAGE * sizeof(uint64_t) + fuse_tally_smem_bytes(K) + 128; }
 };
 
+// Producer warp of the TMA-staged kernels: walks this CTA's tiles in (tile, source, chunk) order and fills the ring.
+template <int NCW, int P, int CH, int NSTAGE>
+MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t* full, uint64_t* empty, int lane) {
+    using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
+    constexpr int TP = Cfg::kTilePix;
+    const int S = prm.S;
+    const int64_t hw = prm.hw;
+    const int64_t tpi = (hw + TP - 1) / TP;
+    const int64_t n_tiles = prm.n_img * tpi;
+    const uint64_t policy = tma::evict_first_policy();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t n = tile / tpi;
+        const int64_t off = (tile - n * tpi) * TP;
+        const uint32_t row_bytes = (uint32_t)((hw - off < TP ? hw - off : TP) * sizeof(float));
+        for (int s = 0; s < S; ++s) {
+            const int C = prm.C[s];
+            const float* pm = prm.main[s] + (n * C) * hw + off;
+            const float* pa = prm.aux[s] + (n * C) * hw + off;
+            for (int c0 = 0; c0 < C; c0 += CH) {
+                const int cn = min(CH, C - c0);
+                tma::mbar_wait(&empty[stage], phase ^ 1);          // all consumers released this slot
+                float* dst = ring + (size_t)stage * Cfg::kStageFloats;
+                if (cn < CH) {
+                    // tail chunk: the class rows this source does not have are filled with kPadLogit HERE, so that the
+                    // consumers' loads and math carry no predicates and exist only once in the instruction stream
+                    const float4 pad = make_float4(kPadLogit, kPadLogit, kPadLogit, kPadLogit);
+                    for (int j = cn; j < CH; ++j)
+                        for (int i = lane; i < TP / 4; i += 32) {
+                            reinterpret_cast<float4*>(dst + j * TP)[i] = pad;
+                            reinterpret_cast<float4*>(dst + (CH + j) * TP)[i] = pad;
+                        }
+                    __threadfence_block();
+                }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);   // release: publishes the padding too
+                for (int j = lane; j < 2 * cn; j += 32) {
+                    const int head = j >= cn, c = head ? j - cn : j;
+                    const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
+                    tma::bulk_g2s(dst + (head * CH + c) * TP, src, row_bytes, &full[stage], policy);
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+}
+
 template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(const __grid_constant__ FuseParams prm) {
     using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
@@ -401,44 +449,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
     Tally<KT> tally;
 
     if (warp == NCW) {
-        // ------------------------------- producer warp -------------------------------
-        const uint64_t policy = tma::evict_first_policy();
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t n = tile / tpi;
-            const int64_t off = (tile - n * tpi) * TP;
-            const uint32_t row_bytes = (uint32_t)((hw - off < TP ? hw - off : TP) * sizeof(float));
-            for (int s = 0; s < S; ++s) {
-                const int C = prm.C[s];
-                const float* pm = prm.main[s] + (n * C) * hw + off;
-                const float* pa = prm.aux[s] + (n * C) * hw + off;
-                for (int c0 = 0; c0 < C; c0 += CH) {
-                    const int cn = min(CH, C - c0);
-                    tma::mbar_wait(&empty[stage], phase ^ 1);          // all consumers released this slot
-                    float* dst = ring + (size_t)stage * Cfg::kStageFloats;
-                    if (cn < CH) {
-                        // tail chunk: the class rows this source does not have are filled with kPadLogit HERE, so that the
-                        // consumers' loads and math carry no predicates and exist only once in the instruction stream
-                        const float4 pad = make_float4(kPadLogit, kPadLogit, kPadLogit, kPadLogit);
-                        for (int j = cn; j < CH; ++j)
-                            for (int i = lane; i < TP / 4; i += 32) {
-                                reinterpret_cast<float4*>(dst + j * TP)[i] = pad;
-                                reinterpret_cast<float4*>(dst + (CH + j) * TP)[i] = pad;
-                            }
-                        __threadfence_block();
-                    }
-                    __syncwarp();
-                    if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);   // release: publishes the padding too
-                    for (int j = lane; j < 2 * cn; j += 32) {
-                        const int head = j >= cn, c = head ? j - cn : j;
-                        const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
-                        tma::bulk_g2s(dst + (head * CH + c) * TP, src, row_bytes, &full[stage], policy);
-                    }
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
+        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane);
     } else {
         // ------------------------------- consumer warps -------------------------------
         const float fS = 1.0f / (float)S;
@@ -486,6 +497,103 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                 if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
             }
             tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
+        }
+    }
+    tally.flush(prm, s_hist, s_cls, Cfg::kThreads);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Labels-only variant: what the reference's generation loop actually keeps (uest_seg_multi_os.py:900-921 discards the KLD and
+// never forms a confidence).  With no confidence, uncertainty or histogram of confidences requested there is nothing to
+// exponentiate: per class and pixel the consumers do z = m + a/2 and a running first-argmax (4 instructions), so the kernel
+// is HBM-bound with a wide margin even at reduced clocks.  Same ring, same producer.
+// ----------------------------------------------------------------------------------------------------------------------
+template <int NCW, int P, int CH, int NSTAGE, int KT>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(const __grid_constant__ FuseParams prm) {
+    using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
+    constexpr int TP = Cfg::kTilePix;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kRingBytes);
+    uint64_t* empty = full + NSTAGE;
+    uint32_t *s_hist, *s_cls;
+    uint8_t* s_lut;
+    tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, Cfg::kThreads);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int S = prm.S;
+    const int64_t hw = prm.hw;
+    const int64_t tpi = (hw + TP - 1) / TP;
+    const int64_t n_tiles = prm.n_img * tpi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Tally<KT> tally;
+    if (warp == NCW) {
+        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane);
+    } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int px = (warp * 32 + lane) * P;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t n = tile / tpi;
+            const int64_t off = (tile - n * tpi) * TP + px;
+            const bool active = off < hw;
+            uint32_t votes[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) votes[p] = 0;
+            for (int s = 0; s < S; ++s) {
+                const int C = prm.C[s];
+                float best[P];
+                int amax[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p) { best[p] = -INFINITY; amax[p] = 0; }
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += CH) {
+                    float m[CH][P], a[CH][P];
+                    tma::mbar_wait(&full[stage], phase);
+                    const float* src = ring + (size_t)stage * Cfg::kStageFloats + px;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + j * TP, m[j]);
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + (CH + j) * TP, a[j]);
+                    __syncwarp();
+                    if (lane == 0) tma::mbar_arrive(&empty[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const float z = fmaf(0.5f, a[j][p], m[j][p]);     // as `pred + 0.5 * pred_aux` (:687); padded classes: -1.5e30
+                            amax[p] = (z > best[p]) ? (c0 + j) : amax[p];    // strict >: first maximal index, as np.argmax (:904)
+                            best[p] = fmaxf(best[p], z);
+                        }
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) votes[p] += 1u << (4 * s_lut[s * MSPL_MAX_SRC_CLASSES + amax[p]]);
+            }
+            int label[P];
+            float conf[P];
+            bool marg[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                int bk = 0;
+                uint32_t bc = votes[p] & 15u;
+#pragma unroll
+                for (int k = 1; k < KT; ++k) {        // merge_outputs: most votes, lowest class on ties (:713)
+                    const uint32_t c = (votes[p] >> (4 * k)) & 15u;
+                    if (c > bc) { bc = c; bk = k; }
+                }
+                label[p] = ((int)bc < prm.vote_t) ? prm.ignore : bk;     // (:716)
+                conf[p] = 0.f;
+                marg[p] = false;
+            }
+            if (active) store_labels<P>(prm.label + n * hw + off, label);
+            tally.template add<P>(prm, s_hist, label, conf, marg, off, active);
         }
     }
     tally.flush(prm, s_hist, s_cls, Cfg::kThreads);

@@ -37,6 +37,12 @@ template <int KT>
 static int dispatch_fuse(const FuseParams& prm, int P, bool gk, cudaStream_t stream) {
     constexpr int CH = MSPL_FUSE_CH;
     if (MSPL_USE_TMA && P == 4 && tma_eligible<TmaCfgVoteAll>(prm)) {
+        // nothing but hard labels requested under a vote policy (the reference's own generation loop): no softmax at all
+        const bool labels_only = prm.policy == MSPL_POLICY_VOTE && !prm.conf && !prm.unc && !prm.conf_hist && !prm.marginal;
+        bool any_kld = false;
+        for (int s = 0; s < prm.S; ++s) any_kld = any_kld || prm.kld[s] != nullptr;
+        if (labels_only && !any_kld)
+            return launch_fuse_tma<TmaCfgVoteAll>(fuse_labels_tma_kernel<15, 2, CH, 4, KT>, prm, stream);
         if (gk) return launch_fuse_tma<TmaCfgPerClass>(fuse_sources_tma_kernel<19, 2, CH, 3, KT, true, true>, prm, stream);
         return launch_fuse_tma<TmaCfgVoteAll>(fuse_sources_tma_kernel<15, 2, CH, 4, KT, false, true>, prm, stream);
     }
@@ -121,7 +127,8 @@ extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logit
     prm.class_hist = class_hist; prm.conf_hist = conf_hist; prm.marginal = marginal_count;
 
     // Per-target-class probabilities are only needed when a pixel can win without every source's vote.
-    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
+    // (under a vote policy they only ever feed conf, so a call without conf does not need them either)
+    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S && conf != nullptr);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return K <= 5 ? dispatch_fuse<5>(prm, P, gk, st) : dispatch_fuse<8>(prm, P, gk, st);
 }

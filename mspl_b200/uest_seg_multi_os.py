@@ -175,6 +175,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
     image_path_list, label_path_list, depth_path_list, names = [], [], [], []
     class_hist = torch.zeros(num_classes, dtype=torch.int64, device=dev)
     conf_hist = torch.zeros((num_classes, ops.RADIX_BINS), dtype=torch.int64, device=dev) if use_cb else None
+    count_ties = bool(getattr(args, 'count_near_ties', False))     # needs the softmax: off keeps the labels-only kernel
     marginal = torch.zeros((), dtype=torch.int64, device=dev)
     kept_labels, kept_confs = [], []
 
@@ -198,7 +199,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
         x = torch.cat(images).to(dev, non_blocking=True)
         kw = dict(policy=policy, num_classes=num_classes, ignore_label=IGNORE_LABEL, ds_rate=ds_rate, want_conf=use_cb,
                   want_unc=False, want_conf_hist=use_cb, class_hist=None if use_cb else class_hist, conf_hist=conf_hist,
-                  marginal=marginal)
+                  count_marginal=count_ties, marginal=marginal if count_ties else None)
         r = None
         if fuse_upsample:
             # [NEW] take every source's logits before its closing bilinear upsample and interpolate inside the kernel
@@ -246,8 +247,9 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
     update_image_list(tgt_train_lst, image_path_list, label_path_list, depth_path_list)
     class_weights = _class_weights_from_histogram(class_hist.cpu().numpy(), getattr(args, 'class_weighting', 'normal'), dev)
     if logger is not None:
-        logger.info('###### Finish evaluating target domain train set in round {}! Time cost: {:.2f} seconds. '
-                    '({} near-tie pixels) ######'.format(round_idx, time.time() - start_eval, int(marginal.item())))
+        ties = ' ({} near-tie pixels)'.format(int(marginal.item())) if count_ties else ''
+        logger.info('###### Finish evaluating target domain train set in round {}! Time cost: {:.2f} seconds.{} ######'.format(
+            round_idx, time.time() - start_eval, ties))
     return tgt_train_lst, class_weights
 
 

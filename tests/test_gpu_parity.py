@@ -533,3 +533,28 @@ def test_fuse_sources_lowres(ops, dev, out_size, main_size, aux_size):
             assert not bool((d2 & ~ref["marginal"]).any())
     finally:
         O.NEAR_TIE_MARGIN = saved
+
+
+def test_labels_only_kernel(ops, dev, golden):
+    """With no confidence / uncertainty / near-tie count requested under a vote policy the library runs its labels-only
+    kernel (argmax of z, table, vote -- what the reference's loop keeps): identical labels and class counts."""
+    g = golden("multi_source_3src.npz")
+    mains, auxs, luts = _golden_sources(g)
+    kw = dict(want_conf=False, want_unc=False, want_conf_hist=False, count_marginal=False)
+    for policy in ("half", "all", 1, 2, 3):
+        lean = _fuse(ops, dev, mains, auxs, luts, policy, **kw)
+        full = _fuse(ops, dev, mains, auxs, luts, policy)
+        assert lean.conf is None and lean.unc is None and lean.marginal is None
+        assert torch.equal(lean.label, full.label) and torch.equal(lean.class_hist, full.class_hist)
+        ref = O.fuse_sources(mains, auxs, luts, policy)
+        assert not bool(((lean.label.cpu() != _t(g["label_%s" % policy])) & ~ref["marginal"]).any())
+    # full-size images, partial tiles, 1..3 sources
+    n, h, w = 3, 256, 480
+    gen = torch.Generator(device=dev).manual_seed(4)
+    big_m = [3 * torch.randn(n, c, h, w, generator=gen, device=dev) for _, c in SOURCES]
+    big_a = [m + 1.5 * torch.randn(m.shape, generator=gen, device=dev) for m in big_m]
+    for S in (1, 2, 3):
+        for policy in ("half", "all"):
+            lean = ops.fuse_sources(big_m[:S], big_a[:S], luts[:S], policy=policy, **kw)
+            full = ops.fuse_sources(big_m[:S], big_a[:S], luts[:S], policy=policy)
+            assert torch.equal(lean.label, full.label) and torch.equal(lean.class_hist, full.class_hist)

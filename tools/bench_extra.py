@@ -176,6 +176,11 @@ def main():
     for policy in ("all", "half", "prob"):
         med, best = timed(lambda: ops.fuse_sources(list(mains), list(auxs), luts, policy=policy), iters)
         report("k1_policy_%s_%dimg" % (policy, n), n * h * w, 313, med, best)
+    for policy in ("all", "half"):
+        med, best = timed(lambda: ops.fuse_sources(list(mains), list(auxs), luts, policy=policy, want_conf=False, want_unc=False,
+                                                   want_conf_hist=False, count_marginal=False), iters)
+        report("k1_labels_only_%s_%dimg" % (policy, n), n * h * w, 305, med, best,
+               note="reference-exact output only (label map + class counts): no softmax needed")
     gen = LabelGenerator(luts, policy="all")
     med, best = timed(lambda: gen.run(list(mains), list(auxs)), iters)
     report("labelgen_all_thresholds_%dimg" % n, n * h * w, 319, med, best)
