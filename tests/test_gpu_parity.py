@@ -558,3 +558,96 @@ def test_labels_only_kernel(ops, dev, golden):
             lean = ops.fuse_sources(big_m[:S], big_a[:S], luts[:S], policy=policy, **kw)
             full = ops.fuse_sources(big_m[:S], big_a[:S], luts[:S], policy=policy)
             assert torch.equal(lean.label, full.label) and torch.equal(lean.class_hist, full.class_hist)
+
+
+def test_vote_and_threshold_invariants(ops, dev):
+    """Property tests: the voted label is always one some source proposed (or the ignore class),
+    raising the vote threshold only ever turns labels into the ignore class, 'all' == int S, thresholds are monotone in the
+    kept portion, and the label tables cover every source class."""
+    n, h, w = 2, 64, 96
+    mains, auxs = [], []
+    for i, (nm, c) in enumerate(SOURCES):
+        m, a = O.synthetic_logits(n, c, h, w, seed=500 + i)
+        mains.append(m.to(dev)), auxs.append(a.to(dev))
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    for (nm, c) in SOURCES:
+        assert len(O.LUTS[nm]) == c and set(np.unique(O.LUTS[nm])) <= {1, 2, 3, 4}      # no source class maps to 0
+    per_source = []
+    for m, a, lut in zip(mains, auxs, luts):
+        z = m + 0.5 * a
+        per_source.append(torch.as_tensor(lut, device=dev)[z.argmax(dim=1)])
+    votes = torch.stack(per_source)                                                       # (S, n, h, w)
+    labels = {t: ops.fuse_sources(mains, auxs, luts, policy=t).label.long() for t in (1, 2, 3)}
+    assert torch.equal(labels[3], ops.fuse_sources(mains, auxs, luts, policy='all').label.long())
+    assert torch.equal(labels[2], ops.fuse_sources(mains, auxs, luts, policy='half').label.long())
+    for t, lab in labels.items():
+        proposed = (votes == lab.unsqueeze(0)).any(dim=0)
+        assert bool((proposed | (lab == 4)).all())
+        agree = (votes == lab.unsqueeze(0)).sum(dim=0)
+        assert bool(((agree >= t) | (lab == 4)).all())
+    for lo, hi in ((1, 2), (2, 3)):
+        changed = labels[lo] != labels[hi]
+        assert bool((labels[hi][changed] == 4).all())
+    r = ops.fuse_sources(mains, auxs, luts, policy='half')
+    prev = None
+    for p in (0.01, 0.1, 0.3, 0.7, 1.0):
+        th, _ = ops.cb_thresholds(r.label, r.conf, p)
+        if prev is not None:
+            assert bool((th <= prev).all())
+        prev = th
+    # uncertainty is a mean of KL divergences: non-negative up to fp32 cancellation, and zero when the heads agree
+    assert float(r.unc.min()) > -1e-5
+    same = ops.fuse_sources(mains, [m.clone() for m in mains], luts, policy='half')
+    assert float(same.unc.abs().max()) < 1e-5
+
+
+def test_c_abi_error_codes(dev):
+    """The C entry points validate their arguments and report through status codes (never a crash, never a launch)."""
+    import ctypes
+    from mspl_b200 import _lib
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    m = torch.zeros(1, 5, 8, 8, device=dev)
+    label = torch.zeros(1, 8, 8, dtype=torch.uint8, device=dev)
+    hist = torch.zeros(5, dtype=torch.int64, device=dev)
+    table = (ctypes.c_ubyte * 5)(3, 1, 1, 2, 2)
+    ptrs = (vp * 1)(m.data_ptr())
+    ncls = (ctypes.c_int * 1)(5)
+    luts = (vp * 1)(ctypes.addressof(table))
+    st = vp(torch.cuda.current_stream(dev).cuda_stream)
+
+    def call(S=1, K=5, policy=0, ignore=4, ds=1, lab=label.data_ptr(), ch=hist.data_ptr(), cls=ncls, tab=luts):
+        return lib.mspl_fuse_sources(S, ptrs, ptrs, cls, tab, 1, 64, K, policy, 1, ignore, ds, vp(lab), None, None, None, vp(ch),
+                                     None, None, st)
+    assert call() == 0
+    assert call(S=0) == -1 and call(S=9) == -1 and call(K=1) == -1 and call(K=9) == -1
+    assert call(policy=7) == -1 and call(ignore=5) == -1 and call(ds=0) == -1
+    assert call(lab=0) == -1 and call(ch=0) == -1
+    assert call(cls=(ctypes.c_int * 1)(0)) == -1 and call(cls=(ctypes.c_int * 1)(257)) == -1
+    bad = (ctypes.c_ubyte * 5)(3, 1, 9, 2, 2)
+    assert call(tab=(vp * 1)(ctypes.addressof(bad))) == -1                 # table value >= K
+    assert call(ch=hist.data_ptr() + 4) == -2                               # misaligned histogram
+    ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+    out3 = torch.zeros(3, device=dev)
+    tgt = torch.zeros(1, 8, 8, dtype=torch.int64, device=dev)
+    cw = torch.ones(5, device=dev)
+    rc = lib.mspl_uw_ce_fwd_bwd(vp(m.data_ptr()), vp(m.data_ptr()), vp(tgt.data_ptr()), vp(cw.data_ptr()), 1, 5, 64, 20.0, 64.0, 1.0,
+                                vp(out3.data_ptr()), None, None, vp(ws.data_ptr()), ws.numel(), st)
+    assert rc == -5                                                          # workspace too small
+    big = torch.zeros(lib.mspl_uw_ce_workspace_bytes(), dtype=torch.uint8, device=dev)
+    m9 = torch.zeros(1, 9, 8, 8, device=dev)
+    rc = lib.mspl_uw_ce_fwd_bwd(vp(m9.data_ptr()), vp(m9.data_ptr()), vp(tgt.data_ptr()), vp(cw.data_ptr()), 1, 9, 64, 20.0, 64.0, 1.0,
+                                vp(out3.data_ptr()), None, None, vp(big.data_ptr()), big.numel(), st)
+    assert rc == -3                                                          # more classes than the fused loss is built for
+    assert lib.mspl_radix_select(None, 5, 0, 0.2, None, None, None, st) == -1
+    torch.cuda.synchronize()
+
+
+def test_non_contiguous_inputs_are_rejected(ops, dev):
+    m = torch.zeros(2, 5, 8, 16, device=dev)
+    with pytest.raises(ValueError, match="contiguous"):
+        ops.fuse_sources([m[:, :, :, ::2]], [m[:, :, :, ::2]], [O.ID_FOREST_TO_GREENHOUSE])
+    with pytest.raises(ValueError):
+        ops.fuse_sources([m], [m[:1]], [O.ID_FOREST_TO_GREENHOUSE])
+    with pytest.raises(ValueError):
+        ops.fuse_sources([m.double()], [m.double()], [O.ID_FOREST_TO_GREENHOUSE])
