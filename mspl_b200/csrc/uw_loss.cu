@@ -9,6 +9,8 @@
 //   g_D      = (1 - alpha ce e^{-D}) / N
 //   dL/dm_k  = dL/dz_k + g_D p1_k (log p1_k - log p2_k - D)
 //   dL/da_k  = dL/dz_k / 2 + g_D (p2_k - p1_k)
+#include <algorithm>
+
 #include "pixel_math.cuh"
 
 namespace mspl {
@@ -347,18 +349,34 @@ static int64_t persistent_grid(int64_t n_groups, int threads, int per_sm, int64_
 // Pixels per thread when rows are 16-byte aligned, picked on B200 (profiles/r01_loss_variants.txt): the backward keeps
 // 2*K*P gradient registers live, so it wants the narrower P=2 (77% of the measured HBM peak vs 68% at P=4); the
 // forward-only kernel is best at P=4 (76% vs 63%).
-constexpr int kLossCtasPerSm = 4;
+// Persistent grid of exactly the CTAs that are resident at once (occupancy query), so no second wave.
+template <typename Kern>
+static int64_t resident_grid(Kern kern, int64_t n_groups) {
+    int dev = 0, sms = kNumSMs, per_sm = 2;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLossThreads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    const int64_t blocks = (n_groups + kLossThreads - 1) / kLossThreads;
+    const int64_t cap = std::min<int64_t>((int64_t)sms * per_sm, kMaxLossBlocks);
+    return blocks < 1 ? 1 : (blocks < cap ? blocks : cap);
+}
 
 template <int K>
 static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, int64_t hw,
                         float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
     const int pv = P == 4 ? (bwd ? 2 : 4) : 1;
-    const int64_t grid = persistent_grid(n * (hw / pv), kLossThreads, kLossCtasPerSm, kMaxLossBlocks);
-#define MSPL_UWCE(PP, BB) uw_ce_fused_kernel<PP, K, BB><<<(unsigned)grid, kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws)
-    if (pv == 4) MSPL_UWCE(4, false);
-    else if (pv == 2) MSPL_UWCE(2, true);
-    else if (bwd) MSPL_UWCE(1, true);
-    else MSPL_UWCE(1, false);
+    const int64_t n_groups = n * (hw / pv);
+#define MSPL_UWCE(PP, BB)                                                                                                  \
+    {                                                                                                                      \
+        auto kern = uw_ce_fused_kernel<PP, K, BB>;                                                                         \
+        kern<<<(unsigned)resident_grid(kern, n_groups), kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws); \
+    }
+    if (pv == 4) MSPL_UWCE(4, false)
+    else if (pv == 2) MSPL_UWCE(2, true)
+    else if (bwd) MSPL_UWCE(1, true)
+    else MSPL_UWCE(1, false)
 #undef MSPL_UWCE
     return launch_status();
 }
