@@ -334,6 +334,120 @@ __global__ void __launch_bounds__(kLossThreads) uw_loss_kernel(const float* __re
     if (!BWD) finish_loss<1>(acc, 0.0, ws, inv_n, 1.0f, loss);
 }
 
+// ---- small class counts (C <= 8): logits live in registers, HBM and L2 see every value exactly once ----------------------
+// PixelwiseKLD forward (BWD = false: writes D) / backward (BWD = true: reads the upstream gradient, writes g1, g2).
+template <int P, int C, bool BWD>
+__global__ void __launch_bounds__(256) kld_small_kernel(const float* __restrict__ d1, const float* __restrict__ d2, const float* __restrict__ up,
+                                                        int64_t n_img, int64_t hw, float* __restrict__ kld, float* __restrict__ g1,
+                                                        float* __restrict__ g2) {
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const int64_t base = n * C * hw + off;
+        float x[C][P], y[C][P], u[P];
+#pragma unroll
+        for (int c = 0; c < C; ++c) PixVec<P>::load(d1 + base + c * hw, x[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) PixVec<P>::load(d2 + base + c * hw, y[c]);
+        if (BWD) PixVec<P>::load(up + n * hw + off, u);
+        float D[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float M1 = -INFINITY, M2 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { M1 = fmaxf(M1, x[c][p]); M2 = fmaxf(M2, y[c][p]); }
+            float e1[C], e2[C], S1 = 0.f, S2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                e1[c] = exp_neg(x[c][p] - M1); e2[c] = exp_neg(y[c][p] - M2);
+                S1 += e1[c]; S2 += e2[c];
+            }
+            const float r1 = __frcp_rn(S1), r2 = __frcp_rn(S2), lr = log_fast(S1 * r2);     // log S1 - log S2
+            float dl[C], d = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                dl[c] = ((x[c][p] - M1) - (y[c][p] - M2)) - lr;                             // log p1 - log p2
+                d = fmaf(e1[c] * r1, dl[c], d);
+            }
+            D[p] = d;
+            if (BWD) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float p1 = e1[c] * r1, p2 = e2[c] * r2;
+                    x[c][p] = u[p] * p1 * (dl[c] - d);
+                    y[c][p] = u[p] * (p2 - p1);
+                }
+            }
+        }
+        if (BWD) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) PixVec<P>::store(g1 + base + c * hw, x[c]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) PixVec<P>::store(g2 + base + c * hw, y[c]);
+        } else {
+            PixVec<P>::store(kld + n * hw + off, D);
+        }
+    }
+}
+
+// UncertaintyWeightedSegmentationLoss forward / backward with the logits in registers.
+template <int P, int C, bool BWD>
+__global__ void __launch_bounds__(kLossThreads) uw_small_kernel(const float* __restrict__ pred, const int64_t* __restrict__ target,
+                                                                const float* __restrict__ u, const float* __restrict__ cw,
+                                                                const float* __restrict__ grad_loss, int64_t n_img, int64_t hw,
+                                                                double inv_n, float* __restrict__ loss, float* __restrict__ d_pred,
+                                                                float* __restrict__ d_u, LossWorkspace* ws) {
+    __shared__ float s_w[C];
+    if (threadIdx.x < C) s_w[threadIdx.x] = cw[threadIdx.x];
+    __syncthreads();
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    const float inv_nf = (float)inv_n;
+    const float upg = BWD ? grad_loss[0] * inv_nf : 0.f;
+    double acc = 0;
+    for (int64_t g = blockIdx.x * (int64_t)kLossThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kLossThreads) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const int64_t base = n * C * hw + off;
+        float x[C][P], uu[P], du[P];
+#pragma unroll
+        for (int c = 0; c < C; ++c) PixVec<P>::load(pred + base + c * hw, x[c]);
+        PixVec<P>::load(u + n * hw + off, uu);
+        float lsum = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const long long t = __ldcs(target + n * hw + off + p);
+            const bool valid = t >= 0 && t < C;
+            const int ti = valid ? (int)t : -1;
+            float M = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < C; ++c) M = fmaxf(M, x[c][p]);
+            float e[C], S = 0.f, wt = 0.f, xt = M;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                e[c] = exp_neg(x[c][p] - M);
+                S += e[c];
+                wt = (ti == c) ? s_w[c] : wt;
+                xt = (ti == c) ? x[c][p] : xt;
+            }
+            const float eu = exp_neg(-uu[p]);
+            const float l = wt * (log_fast(S) - (xt - M)) * eu;
+            lsum += l;
+            if (BWD) {
+                const float r = __frcp_rn(S), coef = upg * eu * wt;
+#pragma unroll
+                for (int c = 0; c < C; ++c) x[c][p] = coef * (e[c] * r - (ti == c ? 1.0f : 0.0f));
+                du[p] = -upg * l;
+            }
+        }
+        acc += (double)lsum;
+        if (BWD) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) PixVec<P>::store(d_pred + base + c * hw, x[c]);
+            if (d_u) PixVec<P>::store(d_u + n * hw + off, du);
+        }
+    }
+    if (!BWD) finish_loss<1>(acc, 0.0, ws, inv_n, 1.0f, loss);
+}
+
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ x, int64_t count, const float* __restrict__ scale) {
     const float s = scale[0];
     if (s == 1.0f) return;
@@ -434,8 +548,27 @@ extern "C" int mspl_softmax_kld(const float* main_logits, const float* aux_logit
     return launch_status();
 }
 
+#define MSPL_SMALL_C_SWITCH(c, STMT)            \
+    switch (c) {                                \
+        case 2: { constexpr int CC = 2; STMT; } break; \
+        case 3: { constexpr int CC = 3; STMT; } break; \
+        case 4: { constexpr int CC = 4; STMT; } break; \
+        case 5: { constexpr int CC = 5; STMT; } break; \
+        case 6: { constexpr int CC = 6; STMT; } break; \
+        case 7: { constexpr int CC = 7; STMT; } break; \
+        case 8: { constexpr int CC = 8; STMT; } break; \
+        default: break;                         \
+    }
+
 extern "C" int mspl_kld_fwd(const float* dist1, const float* dist2, int64_t n, int c, int64_t pixels_per_image, float* kld, void* stream) {
     if (!kld) return MSPL_ERR_BAD_ARG;
+    if (c >= 2 && c <= 8 && dist1 && dist2 && n > 0 && pixels_per_image > 0 &&
+        pick_vec(pixels_per_image, {dist1, dist2, kld}) == 4) {
+        const int64_t grid = persistent_grid(n * (pixels_per_image / 4), 256, 4, 1 << 20);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        MSPL_SMALL_C_SWITCH(c, (kld_small_kernel<4, CC, false><<<(unsigned)grid, 256, 0, st>>>(dist1, dist2, nullptr, n, pixels_per_image, kld, nullptr, nullptr)));
+        return launch_status();
+    }
     return mspl_softmax_kld(dist1, dist2, n, c, pixels_per_image, nullptr, kld, stream);
 }
 
@@ -443,6 +576,12 @@ extern "C" int mspl_kld_bwd(const float* dist1, const float* dist2, const float*
                             float* grad1, float* grad2, void* stream) {
     if (bad_planes(dist1, dist2, n, c, pixels_per_image) || !grad_kld || !grad1 || !grad2) return MSPL_ERR_BAD_ARG;
     if (n == 0) return MSPL_OK;
+    if (c >= 2 && c <= 8 && pick_vec(pixels_per_image, {dist1, dist2, grad_kld, grad1, grad2}) == 4) {
+        const int64_t grid = persistent_grid(n * (pixels_per_image / 2), 256, 4, 1 << 20);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        MSPL_SMALL_C_SWITCH(c, (kld_small_kernel<2, CC, true><<<(unsigned)grid, 256, 0, st>>>(dist1, dist2, grad_kld, n, pixels_per_image, nullptr, grad1, grad2)));
+        return launch_status();
+    }
     const int P = pick_vec(pixels_per_image, {dist1, dist2, grad_kld, grad1, grad2}) == 4 ? 4 : 1;
     const int64_t grid = persistent_grid(n * (pixels_per_image / P), 256, 8, 1 << 20);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -461,6 +600,10 @@ extern "C" int mspl_uw_loss_fwd(const float* pred, const int64_t* target, const 
     const int64_t grid = persistent_grid(n * (pixels_per_image / P), kLossThreads, 4, kMaxLossBlocks);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
+    if (P == 4 && num_classes >= 2 && num_classes <= 8) {
+        MSPL_SMALL_C_SWITCH(num_classes, (uw_small_kernel<4, CC, false><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, nullptr, n, pixels_per_image, 1.0 / norm_pixels, loss, nullptr, nullptr, ws)));
+        return launch_status();
+    }
     if (P == 4) uw_loss_kernel<4, false><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, nullptr, n, num_classes, pixels_per_image, 1.0 / norm_pixels, loss, nullptr, nullptr, ws);
     else uw_loss_kernel<1, false><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, nullptr, n, num_classes, pixels_per_image, 1.0 / norm_pixels, loss, nullptr, nullptr, ws);
     return launch_status();
@@ -474,6 +617,10 @@ extern "C" int mspl_uw_loss_bwd(const float* pred, const int64_t* target, const 
     const int P = pick_vec(pixels_per_image, {pred, u_weight, d_pred, d_u}) == 4 ? 4 : 1;
     const int64_t grid = persistent_grid(n * (pixels_per_image / P), kLossThreads, 4, 1 << 20);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 4 && num_classes >= 2 && num_classes <= 8) {
+        MSPL_SMALL_C_SWITCH(num_classes, (uw_small_kernel<4, CC, true><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, grad_loss, n, pixels_per_image, 1.0 / norm_pixels, nullptr, d_pred, d_u, nullptr)));
+        return launch_status();
+    }
     if (P == 4) uw_loss_kernel<4, true><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, grad_loss, n, num_classes, pixels_per_image, 1.0 / norm_pixels, nullptr, d_pred, d_u, nullptr);
     else uw_loss_kernel<1, true><<<(unsigned)grid, kLossThreads, 0, st>>>(pred, target, u_weight, class_weights, grad_loss, n, num_classes, pixels_per_image, 1.0 / norm_pixels, nullptr, d_pred, d_u, nullptr);
     return launch_status();
