@@ -32,6 +32,12 @@ MSPL_DEVINL float log_fast(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r * 0.6931471805599453f;
 }
+// 1/x through MUFU.RCP alone (relative error <= 2^-23; the IEEE sequence adds a Newton step and a range check per call)
+MSPL_DEVINL float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 MSPL_DEVINL float max3(float a, float b, float c) {        // FMNMX3 (sm_100+)
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -147,10 +153,10 @@ struct SourceResult {
 template <int P>
 MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
     SourceResult r;
-    const float inv_sm = __frcp_rn(st.Sm[p]);
+    const float inv_sm = rcp_fast(st.Sm[p]);
     r.kld = fmaf(st.T[p], inv_sm, log_fast(st.Sa[p] * inv_sm));
     r.rz = fmaf(0.5f, st.Ma[p], st.Mm[p]);
-    r.inv_sz = __frcp_rn(st.Sz[p]);
+    r.inv_sz = rcp_fast(st.Sz[p]);
     r.pmax = exp_neg(st.Mz[p] - r.rz) * r.inv_sz;
     r.degenerate = !(r.rz - st.Mz[p] <= 64.f);      // Sz >= e^-64 otherwise: no underflow, full precision
     return r;
