@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
                 em[k] = exp_neg(m[k][p] - Mm); ea[k] = exp_neg(a[k][p] - Ma); ez[k] = exp_neg(z[k] - Mz);
                 Sm += em[k]; Sa += ea[k]; Sz += ez[k];
             }
-            const float rSm = __frcp_rn(Sm), rSa = __frcp_rn(Sa), rSz = __frcp_rn(Sz);
+            const float rSm = rcp_fast(Sm), rSa = rcp_fast(Sa), rSz = rcp_fast(Sz);
             const float lRatio = log_fast(Sm * rSa), lSz = log_fast(Sz);     // log Sm - log Sa, log Sz
             float dl[K], D = 0.f;                    // dl_k = log p1_k - log p2_k
 #pragma unroll
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) kld_small_kernel(const float* __restrict_
                 e1[c] = exp_neg(x[c][p] - M1); e2[c] = exp_neg(y[c][p] - M2);
                 S1 += e1[c]; S2 += e2[c];
             }
-            const float r1 = __frcp_rn(S1), r2 = __frcp_rn(S2), lr = log_fast(S1 * r2);     // log S1 - log S2
+            const float r1 = rcp_fast(S1), r2 = rcp_fast(S2), lr = log_fast(S1 * r2);     // log S1 - log S2
             float dl[C], d = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kLossThreads) uw_small_kernel(const float* __r
             const float l = wt * (log_fast(S) - (xt - M)) * eu;
             lsum += l;
             if (BWD) {
-                const float r = __frcp_rn(S), coef = upg * eu * wt;
+                const float r = rcp_fast(S), coef = upg * eu * wt;
 #pragma unroll
                 for (int c = 0; c < C; ++c) x[c][p] = coef * (e[c] * r - (ti == c ? 1.0f : 0.0f));
                 du[p] = -upg * l;
