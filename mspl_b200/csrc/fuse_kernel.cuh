@@ -633,14 +633,20 @@ MSPL_DEVINL float bilinear(const float* __restrict__ s, const BilinearTap& t) {
     return t.h0 * (t.w0 * v00 + t.w1 * v01) + t.h1 * (t.w0 * v10 + t.w1 * v11);
 }
 
-template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2>
+// MS / AS: compile-time class strides (floats) of the main / aux blocks inside a stage, or 0 to take them from the
+// geometry at run time.  With fixed strides every tap of every class is `LDS [tap_register + immediate]`: the per-class
+// address arithmetic disappears from the interpolation loop.
+template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2, int MS = 0, int AS = 0>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(const __grid_constant__ FuseParams prm) {
     constexpr int kThreads = (NCW + 1) * 32;
     constexpr int TP = NCW * 32 * P;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LowresGeom& lr = prm.lr;
+    const int main_stride = MS ? MS : lr.main_cls_stride, aux_stride = AS ? AS : lr.aux_cls_stride;
+    const int aux_base = MS ? CH * MS : lr.aux_base;
+    const int stage_floats = (MS && AS) ? CH * (MS + AS) : lr.stage_floats;
     float* ring = reinterpret_cast<float*>(smem_raw);
-    const size_t ring_bytes = sizeof(float) * (size_t)lr.stage_floats * NSTAGE;
+    const size_t ring_bytes = sizeof(float) * (size_t)stage_floats * NSTAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
     uint64_t* empty = full + NSTAGE;
     uint32_t *s_hist, *s_cls;
@@ -685,13 +691,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 for (int c0 = 0; c0 < C; c0 += CH) {
                     const int cn = min(CH, C - c0);
                     tma::mbar_wait(&empty[stage], phase ^ 1);
-                    float* dst = ring + (size_t)stage * lr.stage_floats;
+                    float* dst = ring + (size_t)stage * stage_floats;
                     if (cn < CH) {      // pad the class blocks a tail chunk lacks (see fuse_sources_tma_kernel)
                         const float4 pad = make_float4(kPadLogit, kPadLogit, kPadLogit, kPadLogit);
                         for (int j = cn; j < CH; ++j) {
-                            for (int i = lane; i < (int)(mbytes / 16); i += 32) reinterpret_cast<float4*>(dst + j * lr.main_cls_stride)[i] = pad;
+                            for (int i = lane; i < (int)(mbytes / 16); i += 32) reinterpret_cast<float4*>(dst + j * main_stride)[i] = pad;
                             for (int i = lane; i < (int)(abytes / 16); i += 32)
-                                reinterpret_cast<float4*>(dst + lr.aux_base + j * lr.aux_cls_stride)[i] = pad;
+                                reinterpret_cast<float4*>(dst + aux_base + j * aux_stride)[i] = pad;
                         }
                         __threadfence_block();
                     }
@@ -699,8 +705,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                     if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], cn * (mbytes + abytes));
                     for (int j = lane; j < 2 * cn; j += 32) {
                         const int head = j >= cn, c = head ? j - cn : j;
-                        if (head) tma::bulk_g2s(dst + lr.aux_base + c * lr.aux_cls_stride, pa + (int64_t)(c0 + c) * ha * wa, abytes, &full[stage], policy);
-                        else tma::bulk_g2s(dst + c * lr.main_cls_stride, pm + (int64_t)(c0 + c) * hm * wm, mbytes, &full[stage], policy);
+                        if (head) tma::bulk_g2s(dst + aux_base + c * aux_stride, pa + (int64_t)(c0 + c) * ha * wa, abytes, &full[stage], policy);
+                        else tma::bulk_g2s(dst + c * main_stride, pm + (int64_t)(c0 + c) * hm * wm, mbytes, &full[stage], policy);
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -746,13 +752,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 for (int c0 = 0; c0 < C; c0 += CH) {
                     float m[CH][P], a[CH][P];
                     tma::mbar_wait(&full[stage], phase);
-                    const float* src = ring + (size_t)stage * lr.stage_floats;
+                    const float* src = ring + (size_t)stage * stage_floats;
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            m[j][p] = bilinear(src + j * lr.main_cls_stride, tm[p]);
-                            a[j][p] = bilinear(src + lr.aux_base + j * lr.aux_cls_stride, ta[p]);
+                            m[j][p] = bilinear(src + j * main_stride, tm[p]);
+                            a[j][p] = bilinear(src + aux_base + j * aux_stride, ta[p]);
                         }
                     }
                     __syncwarp();

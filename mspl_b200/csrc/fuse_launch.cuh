@@ -64,7 +64,7 @@ bool tma_eligible(const FuseParams& prm) {
 // ---- K1-lowres ------------------------------------------------------------------------------------------------------
 // Fills prm.lr's stage layout for tiles of `tile_pix` consecutive output pixels; returns the dynamic shared memory the
 // kernel needs with `stages` ring slots, or 0 if the geometry is unsupported (rows not 16-byte multiples).
-inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages) {
+inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages, int fixed_main = 0, int fixed_aux = 0) {
     LowresGeom& lr = prm.lr;
     const int rows_spanned = (int)std::min<int64_t>(lr.H, (tile_pix - 1) / lr.W + 2);
     int main_stride = 0, aux_stride = 0;
@@ -76,6 +76,11 @@ inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages) 
         };
         main_stride = std::max(main_stride, rows(lr.hm[s]) * lr.wm[s]);
         aux_stride = std::max(aux_stride, rows(lr.ha[s]) * lr.wa[s]);
+    }
+    if (fixed_main > 0 && fixed_aux > 0) {          // compile-time strides requested: they must cover the geometry
+        if (main_stride > fixed_main || aux_stride > fixed_aux) return 0;
+        main_stride = fixed_main;
+        aux_stride = fixed_aux;
     }
     lr.main_cls_stride = main_stride;
     lr.aux_cls_stride = aux_stride;

@@ -179,10 +179,20 @@ extern "C" int mspl_fuse_sources_lowres(int num_sources, const float* const* mai
     prm.class_hist = class_hist; prm.conf_hist = conf_hist; prm.marginal = marginal_count;
 
     constexpr int NCW = MSPL_LOWRES_NCW, P = 2, CH = MSPL_FUSE_CH, NST = MSPL_LOWRES_STAGES;
+    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S && conf != nullptr);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {   // common geometries (e.g. ESPDNetUE at 480x256: 3 rows x 240 / 3 rows x 120 floats per class) fit fixed class strides,
+        // which turn every interpolation tap into an immediate-offset shared-memory load
+        constexpr int MS = 768, AS = 384;
+        FuseParams fixed = prm;
+        const size_t fsmem = lowres_plan(fixed, NCW * 32 * P, CH, NST, MS, AS);
+        if (fsmem != 0 && fsmem <= 227 * 1024 && K <= 5) {
+            if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, true, MS, AS>, fixed, fsmem, st);
+            return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true, MS, AS>, fixed, fsmem, st);
+        }
+    }
     const size_t smem = lowres_plan(prm, NCW * 32 * P, CH, NST);
     if (smem == 0 || smem > 227 * 1024) return MSPL_ERR_UNSUPPORTED;    // caller upsamples and uses mspl_fuse_sources instead
-    const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (K <= 5) {
         if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, true>, prm, smem, st);
         return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true>, prm, smem, st);
