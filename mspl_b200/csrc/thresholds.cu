@@ -16,7 +16,10 @@ constexpr int kHistThreads = 256;
 
 // VEC consecutive (label, conf) pairs per load: VEC = 4 -> uchar4 + float4 (a warp reads 128 B of labels and 512 B of conf,
 // both contiguous), VEC = 1 -> scalars.  Kernels keep kUnroll such groups in flight per thread, one block-stride apart.
-constexpr int kUnroll = 4;
+#ifndef MSPL_THR_UNROLL
+#define MSPL_THR_UNROLL 4
+#endif
+constexpr int kUnroll = MSPL_THR_UNROLL;
 
 template <int VEC>
 MSPL_DEVINL void load_label_conf(const uint8_t* __restrict__ label, const float* __restrict__ conf, int64_t i0, uint8_t (&l)[VEC],
@@ -222,9 +225,18 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
     }
 }
 
-static int64_t stream_grid(int64_t n_groups, int threads, int per_sm) {
-    int64_t blocks = (n_groups + threads - 1) / threads;
-    const int64_t cap = (int64_t)kNumSMs * per_sm;
+// Persistent grid of exactly the CTAs that can be resident at once (these kernels are latency-bound: a partial second
+// wave would run at a fraction of the occupancy).
+template <typename Kern>
+static int64_t resident_grid(Kern kern, int64_t n_groups, int threads, size_t smem) {
+    int dev = 0, sms = kNumSMs, per_sm = 1;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    const int64_t blocks = (n_groups + threads - 1) / threads;
+    const int64_t cap = (int64_t)sms * per_sm;
     return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
 }
 
@@ -253,7 +265,7 @@ extern "C" int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
-    const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, kHistThreads, 4);
+    const int64_t grid = resident_grid(kern, num_pixels / vec / kUnroll + 1, kHistThreads, smem);
     kern<<<(unsigned)grid, kHistThreads, smem, st>>>(label, conf, num_pixels, pixels_per_image, K,
                                                      static_cast<const RadixState*>(state), hist, ds_rate);
     return launch_status();
@@ -283,7 +295,8 @@ extern "C" int mspl_apply_thresholds(const uint8_t* label, const float* conf, co
     };
     const int vec = (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t grid = stream_grid(num_pixels / vec / kUnroll + 1, 256, 8);
+    const int64_t grid = vec == 4 ? resident_grid(apply_thresholds_kernel<4>, num_pixels / vec / kUnroll + 1, 256, 0)
+                                  : resident_grid(apply_thresholds_kernel<1>, num_pixels / vec / kUnroll + 1, 256, 0);
     if (vec == 4)
         apply_thresholds_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
                                                                   ignore_mask, final_hist);
