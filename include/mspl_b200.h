@@ -180,6 +180,23 @@ MSPL_API int mspl_miou_from_logits(const float* logits, const int64_t* target, i
 MSPL_API int mspl_miou_from_labels(const void* pred, int pred_is_int64, const int64_t* target, int64_t num_pixels,
                           int num_classes, unsigned long long* counts, void* stream);
 
+/* ---- NIDLoss (next-row component) ---------------------------------------------------------
+ * Replaces NIDLoss.forward + SoftArgMax (loss_fns/segmentation_loss.py:54-144; call site uest_seg_multi_os.py:1027-1030):
+ * loss = (NID(grey camera image, soft-argmax label) - 0.95) * 20 from soft joint / marginal histograms, in one pass over the
+ * pixels instead of image_bins sequential sigmoid-window passes and a (K x num_pixel)(num_pixel x C) product.
+ *   camera (batch, 3, pixels) f32, label (batch, num_classes, pixels) f32 logits; image_bins <= 32, label_bins <= 8
+ *   workspace: mspl_nid_workspace_bytes(), zeroed once by the caller; state: mspl_nid_state_bytes(), written by the forward
+ *   (its first float is the loss) and read by the backward; d_label gets d(loss * *grad_loss)/d(label) (the camera image
+ *   receives no gradient, as in the reference's use). */
+MSPL_API size_t mspl_nid_workspace_bytes(void);
+MSPL_API size_t mspl_nid_state_bytes(void);
+MSPL_API int mspl_nid_fwd(const float* camera, const float* label, int64_t batch, int num_classes, int64_t pixels_per_image,
+                 int image_bins, int label_bins, float bw_camera, float bw_label, void* workspace, size_t workspace_bytes,
+                 void* state, void* stream);
+MSPL_API int mspl_nid_bwd(const float* camera, const float* label, const float* grad_loss, int64_t batch, int num_classes,
+                 int64_t pixels_per_image, int image_bins, int label_bins, float bw_camera, float bw_label, const void* state,
+                 float* d_label, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,10 @@ SIGNATURES = {
     "mspl_kld_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "mspl_uw_loss_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f64, c_vp, c_vp, c_sz, c_vp]),
     "mspl_uw_loss_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f64, c_vp, c_vp, c_vp]),
+    "mspl_nid_workspace_bytes": (c_sz, []),
+    "mspl_nid_state_bytes": (c_sz, []),
+    "mspl_nid_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_sz, c_vp, c_vp]),
+    "mspl_nid_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "mspl_miou_from_logits": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_vp]),
     "mspl_miou_from_labels": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_vp]),
 }

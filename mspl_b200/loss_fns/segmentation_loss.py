@@ -67,3 +67,19 @@ class FusedUncertaintyWeightedLoss(nn.Module):
                                      norm_pixels, return_parts=True)
         self.last_parts = parts
         return loss
+
+
+class NIDLoss(nn.Module):
+    """loss_fns/segmentation_loss.py:54-118: normalised information distance between the grey-scale camera image and the
+    soft-argmax label map, rescaled as ``(nid - 0.95) * 20`` -- the optional ``--use-nid`` training term
+    (uest_seg_multi_os.py:514, 1027-1030).  Same constructor and ``forward(camera, label)``; one fused pass per direction."""
+
+    def __init__(self, image_bin=16, label_bin=4, bw_camera=0.005, bw_label=0.001):
+        super(NIDLoss, self).__init__()
+        self.K = image_bin
+        self.C = label_bin
+        self.bw_camera = bw_camera
+        self.bw_label = bw_label
+
+    def forward(self, camera, label):
+        return ops.nid_loss(camera, label, self.K, self.C, self.bw_camera, self.bw_label)

@@ -473,3 +473,52 @@ def miou_counts(output, target, num_classes, counts=None):
                                            _ptr(counts), _stream(dev))
     _lib.check(st, "mspl_miou")
     return counts
+
+
+# ---- NIDLoss ------------------------------------------------------------------------------------------------------------
+_nid_workspaces = {}
+
+
+class _NidLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, camera, label, image_bins, label_bins, bw_camera, bw_label):
+        cam = _require_cuda(camera.detach().float().contiguous(), "camera", torch.float32, 4)
+        lab = _require_cuda(label.detach().float().contiguous(), "label", torch.float32, 4)
+        b, three, h, w = cam.shape
+        if three != 3 or lab.shape[0] != b or lab.shape[2:] != (h, w):
+            raise ValueError("camera must be (B,3,H,W) and label (B,C,H,W) with the same B, H, W")
+        dev = cam.device
+        lib = _lib.load()
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        ws = _nid_workspaces.get(key)
+        if ws is None:
+            ws = _nid_workspaces[key] = torch.zeros(lib.mspl_nid_workspace_bytes(), dtype=torch.uint8, device=dev)
+        state = torch.empty(lib.mspl_nid_state_bytes() // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.mspl_nid_fwd(_ptr(cam), _ptr(lab), b, lab.shape[1], h * w, int(image_bins), int(label_bins), float(bw_camera),
+                                  float(bw_label), _ptr(ws), ws.numel(), _ptr(state), _stream(dev))
+        _lib.check(st, "mspl_nid_fwd")
+        ctx.save_for_backward(cam, lab, state)
+        ctx.cfg = (int(image_bins), int(label_bins), float(bw_camera), float(bw_label))
+        return state[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        cam, lab, state = ctx.saved_tensors
+        k, lb, bwc, bwl = ctx.cfg
+        b, c, h, w = lab.shape
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        d_label = torch.empty_like(lab)
+        with torch.cuda.device(lab.device):
+            st = _lib.load().mspl_nid_bwd(_ptr(cam), _ptr(lab), _ptr(g), b, c, h * w, k, lb, bwc, bwl, _ptr(state), _ptr(d_label),
+                                          _stream(lab.device))
+        _lib.check(st, "mspl_nid_bwd")
+        return None, d_label, None, None, None, None
+
+
+def nid_loss(camera, label, image_bins=16, label_bins=4, bw_camera=0.005, bw_label=0.001):
+    """NIDLoss.forward (loss_fns/segmentation_loss.py:101-118): (NID(grey(camera), soft-argmax(label)) - 0.95) * 20,
+    differentiable w.r.t. the label logits."""
+    if image_bins > 32 or label_bins > 8:
+        raise NotImplementedError("nid_loss supports up to 32 image bins and 8 label bins")
+    return _NidLoss.apply(camera, label, image_bins, label_bins, bw_camera, bw_label)

@@ -202,6 +202,39 @@ def golden_miou(ref):
     np.savez_compressed(os.path.join(GOLDEN_DIR, "miou.npz"), **out)
 
 
+def golden_nid(ref):
+    """NIDLoss forward + autograd backward (loss_fns/segmentation_loss.py:54-144).  The reference hard-codes .to('cuda');
+    in this GPU-less container Tensor.to is wrapped for the duration of the calls so that 'cuda' means 'cpu'."""
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple('cpu' if (isinstance(x, str) and x.startswith('cuda')) else x for x in a)
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to_cpu
+    try:
+        gen = torch.Generator().manual_seed(3)
+        out = {}
+        cases = {"hard": dict(scale=3.0, kw={}),                                      # soft-argmax saturated: gradient vanishes
+                 "soft": dict(scale=0.004, kw=dict(bw_label=0.05)),                   # soft labels, wide label windows: dense gradient
+                 "bins8": dict(scale=0.004, kw=dict(image_bin=8, label_bin=4, bw_camera=0.02, bw_label=0.1))}
+        for tag, cfg in cases.items():
+            b, c, h, w = 3, 5, 12, 20
+            camera = torch.rand(b, 3, h, w, generator=gen) * 1.2 - 0.1                    # some intensities outside [0,1]
+            label = cfg["scale"] * torch.randn(b, c, h, w, generator=gen)
+            kw = dict(image_bin=16, label_bin=5)
+            kw.update(cfg["kw"])
+            crit = ref.seg_loss.NIDLoss(**kw)
+            lab = label.clone().requires_grad_(True)
+            loss = crit(camera, lab)
+            grad, = torch.autograd.grad(loss, lab)
+            out["camera_" + tag], out["label_" + tag] = camera.numpy(), label.numpy()
+            out["loss_" + tag], out["grad_" + tag] = loss.detach().numpy(), grad.numpy()
+            out["cfg_" + tag] = np.array([kw["image_bin"], kw["label_bin"], kw.get("bw_camera", 0.005), kw.get("bw_label", 0.001)])
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "nid.npz"), **out)
+    finally:
+        torch.Tensor.to = orig_to
+
+
 def main():
     ref = load_reference()
     if ref is None:
@@ -209,7 +242,7 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou):
+    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou, golden_nid):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
     for f in sorted(os.listdir(GOLDEN_DIR)):

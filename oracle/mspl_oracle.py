@@ -16,6 +16,7 @@ reference functions on the path (paths relative to the reference tree):
   * ``UncertaintyWeightedSegmentationLoss`` loss_fns/segmentation_loss.py:146-175
   * the training-loss combination       uest_seg_multi_os.py:1020-1023
   * ``MIOU.get_iou``                    utilities/metrics/segmentation_miou.py:13-44
+  * ``NIDLoss`` / ``SoftArgMax``        loss_fns/segmentation_loss.py:54-144
 
 Parity status.  The functions above are PINNED: tests/test_oracle_vs_reference.py runs them against
 the live reference in the build container, and tests/golden/*.npz hold outputs generated from the
@@ -203,6 +204,48 @@ def miou_get_iou(output, target, num_classes=21, epsilon=1e-6):
     area_mask = torch.histc(target.float(), bins=num_classes, min=1, max=num_classes)
     area_union = area_pred + area_mask - area_inter + epsilon
     return area_inter.numpy(), area_union.numpy()
+
+
+def soft_arg_max(A, beta=500, epsilon=1e-12):
+    """SoftArgMax.soft_arg_max, loss_fns/segmentation_loss.py:124-141 (device-agnostic): sum_i i * softmax(beta*A)_i."""
+    A_max = torch.max(A, dim=1, keepdim=True)[0]
+    A_exp = torch.exp((A - A_max) * beta)
+    A_softmax = A_exp / (torch.sum(A_exp, dim=1, keepdim=True) + epsilon)
+    indices = torch.arange(start=0, end=A.size()[1]).float().reshape(1, A.size()[1], 1, 1).to(A.dtype)
+    return F.conv2d(A_softmax, indices)
+
+
+def nid_loss(camera, label, image_bin=16, label_bin=4, bw_camera=0.005, bw_label=0.001, eps=1e-7):
+    """NIDLoss.forward, loss_fns/segmentation_loss.py:54-118, without its hard-coded .to('cuda') calls.
+    camera (B,3,H,W), label (B,C,H,W) logits.  Note the reference's quirk, kept here: the per-bin window responses are
+    summed over the BATCH first (P_c is K x num_pixel), so the joint histogram couples images at the same pixel position."""
+    camera_gray = torch.sum(camera, 1) / 3
+    label_amax = soft_arg_max(label)
+    label_amax = label_amax.reshape(label_amax.size()[0], label_amax.size()[2], label_amax.size()[3])
+    num_pixel = camera_gray.size()[1] * camera_gray.size()[2]
+    batch_size = camera_gray.size()[0]
+    camera_1d = camera_gray.reshape(batch_size, -1)
+    label_1d = torch.reshape(label_amax, (batch_size, -1))
+    P_c = torch.zeros(image_bin, num_pixel, dtype=camera.dtype)
+    P_l = torch.zeros(label_bin, num_pixel, dtype=camera.dtype)
+    L_c = 1 / image_bin
+    L_l = 1
+    for k in range(0, image_bin):
+        mu_k = L_c * (k + 1 / 2)
+        PI_c = torch.sigmoid((camera_1d - mu_k + L_c / 2) / bw_camera) - torch.sigmoid((camera_1d - mu_k - L_c / 2) / bw_camera)
+        P_c[k] = torch.sum(PI_c, 0)
+        if k < label_bin:
+            PI_l = torch.sigmoid((label_1d - k + L_l / 2) / bw_label) - torch.sigmoid((label_1d - k - L_l / 2) / bw_label)
+            P_l[k] = torch.sum(PI_l, 0)
+    norm = num_pixel * batch_size
+    p_cl, p_c, p_l = torch.mm(P_c, torch.t(P_l)) / norm, torch.sum(P_c, 1) / norm, torch.sum(P_l, 1) / norm
+    p_cl = p_cl / p_cl.sum()
+    p_c = (p_c / p_c.sum()).reshape(-1, 1)
+    p_l = (p_l / p_l.sum()).reshape(-1, 1)
+    I = torch.sum(p_cl * (torch.log(p_cl + eps) - torch.log(torch.mm(p_c, torch.t(p_l)) + eps)))
+    H = -torch.sum(p_cl * torch.log(p_cl + eps))
+    nid = 1 - I / H
+    return (nid - 0.95) * 20
 
 
 # --------------------------------------------------------------------------------------------

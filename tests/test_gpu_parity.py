@@ -677,3 +677,44 @@ def test_tma_and_scalar_kernels_agree_bitwise_at_scale(ops, dev):
         # and run-to-run determinism of the asynchronous pipeline
         a2 = ops.fuse_sources(mains, auxs, luts, policy=policy)
         assert torch.equal(a.label, a2.label) and torch.equal(a.conf, a2.conf) and torch.equal(a.unc, a2.unc)
+
+
+@pytest.mark.parametrize("tag", ["hard", "soft", "bins8"])
+def test_nid_loss_matches_reference_golden(dev, golden, tag):
+    """NIDLoss forward and backward against the live-reference fixture (loss within 1e-4 absolute -- it is (NID - 0.95) * 20,
+    a difference of O(1) quantities; gradients 1e-3 relative with a 1e-4 * max|grad| floor: they pass through
+    sigmoid(x / bw) windows with bw down to 1e-3, i.e. slopes of 1e3, in fp32)."""
+    from mspl_b200.loss_fns.segmentation_loss import NIDLoss
+    g = golden("nid.npz")
+    k, lb, bwc, bwl = g["cfg_" + tag]
+    crit = NIDLoss(image_bin=int(k), label_bin=int(lb), bw_camera=float(bwc), bw_label=float(bwl))
+    camera = _t(g["camera_" + tag]).to(dev)
+    label = _t(g["label_" + tag]).to(dev).requires_grad_(True)
+    loss = crit(camera, label)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_" + tag])) <= 1e-4
+    want = _t(g["grad_" + tag])
+    scale = float(want.abs().max())
+    if scale == 0.0:
+        assert float(label.grad.abs().max()) < 1e-6
+    else:
+        torch.testing.assert_close(label.grad.cpu(), want, rtol=1e-3, atol=1e-4 * scale)
+    # an upstream gradient is applied on the device
+    label2 = _t(g["label_" + tag]).to(dev).requires_grad_(True)
+    (crit(camera, label2) * 0.5).backward()
+    torch.testing.assert_close(label2.grad, label.grad * 0.5, rtol=1e-6, atol=0)
+
+
+def test_nid_loss_full_size_vs_oracle(dev):
+    from mspl_b200.loss_fns.segmentation_loss import NIDLoss
+    gen = torch.Generator().manual_seed(6)
+    camera = torch.rand(4, 3, 64, 96, generator=gen)
+    label = 0.004 * torch.randn(4, 5, 64, 96, generator=gen)
+    lab = label.clone().requires_grad_(True)
+    want = O.nid_loss(camera, lab, 16, 5, 0.005, 0.05)
+    gw, = torch.autograd.grad(want, lab)
+    ld = label.to(dev).requires_grad_(True)
+    got = NIDLoss(16, 5, 0.005, 0.05)(camera.to(dev), ld)
+    got.backward()
+    assert abs(got.item() - want.item()) <= 1e-4
+    torch.testing.assert_close(ld.grad.cpu(), gw, rtol=1e-3, atol=1e-4 * float(gw.abs().max()))

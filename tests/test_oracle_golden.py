@@ -159,3 +159,15 @@ def test_miou_golden(golden):
         assert np.array_equal(inter, g["inter_%d" % nc]) and np.array_equal(union, g["union_%d" % nc])
         inter, union = O.miou_get_iou(_t(g["pred_%d" % nc]), _t(g["target_%d" % nc]), nc)
         assert np.array_equal(inter, g["inter_lab_%d" % nc]) and np.array_equal(union, g["union_lab_%d" % nc])
+
+
+def test_nid_loss_golden(golden):
+    g = golden("nid.npz")
+    for tag in ("hard", "soft", "bins8"):
+        k, lb, bwc, bwl = g["cfg_" + tag]
+        lab = _t(g["label_" + tag]).clone().requires_grad_(True)
+        loss = O.nid_loss(_t(g["camera_" + tag]), lab, int(k), int(lb), float(bwc), float(bwl))
+        grad, = torch.autograd.grad(loss, lab)
+        _same(loss.detach().numpy(), g["loss_" + tag], rtol=1e-5, atol=1e-5)
+        scale = max(float(np.abs(g["grad_" + tag]).max()), 1e-12)
+        _same(grad.numpy(), g["grad_" + tag], rtol=1e-4, atol=1e-5 * scale)

@@ -111,3 +111,26 @@ def test_miou_matches_reference(ref):
         want = MIOU(num_classes=nc).get_iou(logits.clone(), target.clone())
         got = O.miou_get_iou(logits, target, nc)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_nid_loss_matches_reference(ref):
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):       # the reference hard-codes .to('cuda')
+        a = tuple('cpu' if (isinstance(x, str) and x.startswith('cuda')) else x for x in a)
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to_cpu
+    try:
+        gen = torch.Generator().manual_seed(23)
+        camera = torch.rand(2, 3, 10, 14, generator=gen)
+        label = 0.004 * torch.randn(2, 5, 10, 14, generator=gen)
+        a = label.clone().requires_grad_(True)
+        want = ref.seg_loss.NIDLoss(image_bin=16, label_bin=5, bw_label=0.05)(camera, a)
+        gw, = torch.autograd.grad(want, a)
+    finally:
+        torch.Tensor.to = orig_to
+    b = label.clone().requires_grad_(True)
+    got = O.nid_loss(camera, b, 16, 5, 0.005, 0.05)
+    gg, = torch.autograd.grad(got, b)
+    _close(got.detach(), want.detach(), rtol=1e-6, atol=1e-6)
+    _close(gg, gw, rtol=1e-5, atol=1e-6)

@@ -117,10 +117,29 @@ def lowres_section(dev, iters):
     report("k1_fullres_only_all_%dimg" % n, n * h * w, 313, med3, best3)
 
 
+def nid_section(dev, iters):
+    """NIDLoss forward + backward at the training batch (64 x 480x256, 16 intensity bins, 5 label bins)."""
+    from mspl_b200.loss_fns.segmentation_loss import NIDLoss
+    b, h, w = 64, 256, 480
+    g = torch.Generator(device=dev).manual_seed(2)
+    camera = torch.rand((b, 3, h, w), device=dev, generator=g)
+    label = 3 * torch.randn((b, 5, h, w), device=dev, generator=g)
+    crit = NIDLoss(image_bin=16, label_bin=5)
+
+    def step():
+        lab = label.detach().requires_grad_(True)
+        crit(camera, lab).backward()
+    med, best = timed(step, max(3, iters // 2))
+    report("nid_loss_b64_fwd_bwd", b * h * w, 4 * (3 + 5) * 2 + 4 * 5, med, best,
+           note="one fused pass per direction; compute-bound (2 x (32 + 10) sigmoids per pixel and image)")
+    med, best = timed(lambda: crit(camera, label), max(3, iters // 2))
+    report("nid_loss_b64_fwd_only", b * h * w, 4 * (3 + 5), med, best)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io", "lowres"))
+    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io", "lowres", "nid"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     iters = 5 if args.quick else 20
@@ -166,7 +185,9 @@ def main():
         label_io_section(dev)
     if args.section in ("all", "lowres"):
         lowres_section(dev, iters)
-    if args.section in ("loss", "io", "lowres"):
+    if args.section in ("all", "nid"):
+        nid_section(dev, iters)
+    if args.section in ("loss", "io", "lowres", "nid"):
         return
     # ---- non-headline policies on the 13/20/5 configuration -----------------------------------------------------------
     n = 100 if args.quick else 400
