@@ -34,7 +34,8 @@ struct NidState {                           // forward -> backward hand-over (de
     float Gl[kNidMaxLabelBins];             // d loss / d l[c]      (l = un-normalised label marginal)
 };
 
-MSPL_DEVINL float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x) through MUFU.EX2 + MUFU.RCP (relative error ~2^-22; saturates cleanly to 0 / 1 for large |x|)
+MSPL_DEVINL float sigmoidf(float x) { return rcp_fast(1.0f + ex2_approx(-x * kLog2e)); }
 
 // soft label of one pixel: sum_i i * e_i / (sum e + 1e-12), e_i = exp((A_i - max A) * 500)        (SoftArgMax, :124-141)
 MSPL_DEVINL float soft_label(const float* __restrict__ px, int C, int64_t hw, float* sum_e_out) {
@@ -42,18 +43,12 @@ MSPL_DEVINL float soft_label(const float* __restrict__ px, int C, int64_t hw, fl
     for (int i = 0; i < C; ++i) mx = fmaxf(mx, __ldg(px + i * hw));
     float se = 0.f, sie = 0.f;
     for (int i = 0; i < C; ++i) {
-        const float e = expf((__ldg(px + i * hw) - mx) * 500.0f);
+        const float e = ex2_approx((__ldg(px + i * hw) - mx) * (500.0f * kLog2e));
         se += e;
         sie = fmaf((float)i, e, sie);
     }
     if (sum_e_out) *sum_e_out = se;
     return sie / (se + 1e-12f);
-}
-
-// window responses of one value: PI[k] = sigmoid((v - mu_k + L/2)/bw) - sigmoid((v - mu_k - L/2)/bw), in the reference's
-// operation order (:84-88)
-MSPL_DEVINL float window(float v, float mu, float half, float bw) {
-    return sigmoidf((v - mu + half) / bw) - sigmoidf((v - mu - half) / bw);
 }
 
 __global__ void __launch_bounds__(kNidThreads) nid_forward_kernel(const float* __restrict__ camera, const float* __restrict__ label,
@@ -63,7 +58,7 @@ __global__ void __launch_bounds__(kNidThreads) nid_forward_kernel(const float* _
     __shared__ bool s_last;
     for (int i = threadIdx.x; i < kNidSlots; i += kNidThreads) s_acc[i] = 0.0;
     __syncthreads();
-    const float Lc = 1.0f / (float)K;
+    const float Lc = 1.0f / (float)K, inv_bwc = 1.0f / bw_c, inv_bwl = 1.0f / bw_l;
     const int lane = threadIdx.x & 31;
     for (int64_t base = (int64_t)blockIdx.x * kNidThreads; base < hw; base += (int64_t)gridDim.x * kNidThreads) {
         const int64_t pix = base + threadIdx.x;
@@ -78,12 +73,25 @@ __global__ void __launch_bounds__(kNidThreads) nid_forward_kernel(const float* _
                 const float* cam = camera + ((int64_t)b * 3) * hw + pix;
                 const float g = (__ldg(cam) + __ldg(cam + hw) + __ldg(cam + 2 * hw)) / 3.0f;        // get_grayscale (:65-66)
                 const float lab = soft_label(label + ((int64_t)b * C) * hw + pix, C, hw, nullptr);
+                // neighbouring windows share an edge: PI[k] = s((v - k L)/bw) - s((v - (k+1) L)/bw), K+1 sigmoids instead of 2K
+                float lo = sigmoidf(g * inv_bwc);
 #pragma unroll
-                for (int k = 0; k < kNidMaxImageBins; ++k)
-                    if (k < K) Pc[k] += window(g, Lc * ((float)k + 0.5f), Lc * 0.5f, bw_c);
+                for (int k = 0; k < kNidMaxImageBins; ++k) {
+                    if (k < K) {
+                        const float hi = sigmoidf((g - Lc * (float)(k + 1)) * inv_bwc);
+                        Pc[k] += lo - hi;
+                        lo = hi;
+                    }
+                }
+                lo = sigmoidf((lab + 0.5f) * inv_bwl);
 #pragma unroll
-                for (int c = 0; c < kNidMaxLabelBins; ++c)
-                    if (c < Lb) Pl[c] += window(lab, (float)c, 0.5f, bw_l);
+                for (int c = 0; c < kNidMaxLabelBins; ++c) {
+                    if (c < Lb) {
+                        const float hi = sigmoidf((lab - 0.5f - (float)c) * inv_bwl);
+                        Pl[c] += lo - hi;
+                        lo = hi;
+                    }
+                }
             }
         }
         // warp-reduce the outer product and the marginals, one shared-memory add per warp and entry
@@ -176,22 +184,34 @@ __global__ void __launch_bounds__(kNidThreads) nid_backward_kernel(const float* 
     if (threadIdx.x < kNidMaxLabelBins) s_Gl[threadIdx.x] = state->Gl[threadIdx.x];
     __syncthreads();
     const float up = grad_loss[0];
-    const float Lc = 1.0f / (float)K;
+    const float Lc = 1.0f / (float)K, inv_bwc = 1.0f / bw_c, inv_bwl = 1.0f / bw_l;
     for (int64_t pix = (int64_t)blockIdx.x * kNidThreads + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * kNidThreads) {
         float W[kNidMaxLabelBins];                    // d loss / d P_l[c, pix] = sum_k GJ[k][c] P_c[k, pix] + Gl[c]
 #pragma unroll
         for (int c = 0; c < kNidMaxLabelBins; ++c) W[c] = c < Lb ? s_Gl[c] : 0.f;
-        for (int k = 0; k < K; ++k) {
-            float pc = 0.f;
-            for (int b = 0; b < B; ++b) {
-                const float* cam = camera + ((int64_t)b * 3) * hw + pix;
-                const float g = (__ldg(cam) + __ldg(cam + hw) + __ldg(cam + 2 * hw)) / 3.0f;
-                pc += window(g, Lc * ((float)k + 0.5f), Lc * 0.5f, bw_c);
-            }
+        float Pc[kNidMaxImageBins];
 #pragma unroll
-            for (int c = 0; c < kNidMaxLabelBins; ++c)
-                if (c < Lb) W[c] = fmaf(s_GJ[k * kNidMaxLabelBins + c], pc, W[c]);
+        for (int k = 0; k < kNidMaxImageBins; ++k) Pc[k] = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float* cam = camera + ((int64_t)b * 3) * hw + pix;
+            const float g = (__ldg(cam) + __ldg(cam + hw) + __ldg(cam + 2 * hw)) / 3.0f;
+            float lo = sigmoidf(g * inv_bwc);
+#pragma unroll
+            for (int k = 0; k < kNidMaxImageBins; ++k) {
+                if (k < K) {
+                    const float hi = sigmoidf((g - Lc * (float)(k + 1)) * inv_bwc);
+                    Pc[k] += lo - hi;
+                    lo = hi;
+                }
+            }
         }
+#pragma unroll
+        for (int k = 0; k < kNidMaxImageBins; ++k)
+            if (k < K) {
+#pragma unroll
+                for (int c = 0; c < kNidMaxLabelBins; ++c)
+                    if (c < Lb) W[c] = fmaf(s_GJ[k * kNidMaxLabelBins + c], Pc[k], W[c]);
+            }
         for (int b = 0; b < B; ++b) {
             const float* px = label + ((int64_t)b * C) * hw + pix;
             float se;
@@ -200,8 +220,8 @@ __global__ void __launch_bounds__(kNidThreads) nid_backward_kernel(const float* 
 #pragma unroll
             for (int c = 0; c < kNidMaxLabelBins; ++c) {
                 if (c < Lb) {
-                    const float sa = sigmoidf((lab - (float)c + 0.5f) / bw_l), sb = sigmoidf((lab - (float)c - 0.5f) / bw_l);
-                    dlab = fmaf(W[c], (sa * (1.0f - sa) - sb * (1.0f - sb)) / bw_l, dlab);
+                    const float sa = sigmoidf((lab - (float)c + 0.5f) * inv_bwl), sb = sigmoidf((lab - (float)c - 0.5f) * inv_bwl);
+                    dlab = fmaf(W[c], (sa * (1.0f - sa) - sb * (1.0f - sb)) * inv_bwl, dlab);
                 }
             }
             dlab *= up;
@@ -209,7 +229,7 @@ __global__ void __launch_bounds__(kNidThreads) nid_backward_kernel(const float* 
             for (int i = 0; i < C; ++i) mx = fmaxf(mx, __ldg(px + i * hw));
             const float inv = 1.0f / (se + 1e-12f);
             for (int j = 0; j < C; ++j) {             // d lab / d A_j = beta * s_j * (j - lab)
-                const float sj = expf((__ldg(px + j * hw) - mx) * 500.0f) * inv;
+                const float sj = ex2_approx((__ldg(px + j * hw) - mx) * (500.0f * kLog2e)) * inv;
                 d_label[((int64_t)b * C + j) * hw + pix] = dlab * 500.0f * sj * ((float)j - lab);
             }
         }
