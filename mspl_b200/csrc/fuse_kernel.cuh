@@ -57,6 +57,7 @@ template <int P, int K, bool GK, bool TOP2>
 struct PixelFusion {
     float usum[P], csum[P], Fk[GK ? K : 1][P];
     uint32_t votes[P];
+    int last_lab[P];        // label proposed by the most recent source (unanimity shortcut in finish())
     bool marg[P];
 
     MSPL_DEVINL void reset() {
@@ -86,6 +87,7 @@ struct PixelFusion {
             if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
             const int lab = s_lut_s[st.amax[p]];
             votes[p] += 1u << (4 * lab);
+            last_lab[p] = lab;
             if (GK) {
 #pragma unroll
                 for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
@@ -111,6 +113,7 @@ struct PixelFusion {
             if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
             const int lab = s_lut_s[st.amax[p]];
             votes[p] += 1u << (4 * lab);
+            last_lab[p] = lab;
             if (GK) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
@@ -143,10 +146,17 @@ struct PixelFusion {
             } else {
                 int bk = 0;
                 uint32_t bc = votes[p] & 15u;
+                if (!GK && prm.vote_t == prm.S) {
+                    // unanimity required ('all'): the label survives only if every source proposed it, so looking at the
+                    // last proposal's count is enough -- no scan over the classes
+                    bk = last_lab[p];
+                    bc = (votes[p] >> (4 * bk)) & 15u;
+                } else {
 #pragma unroll
-                for (int k = 1; k < K; ++k) {        // merge_outputs: most votes, lowest class on ties (:713)
-                    const uint32_t c = (votes[p] >> (4 * k)) & 15u;
-                    if (c > bc) { bc = c; bk = k; }
+                    for (int k = 1; k < K; ++k) {        // merge_outputs: most votes, lowest class on ties (:713)
+                        const uint32_t c = (votes[p] >> (4 * k)) & 15u;
+                        if (c > bc) { bc = c; bk = k; }
+                    }
                 }
                 label[p] = ((int)bc < prm.vote_t) ? ignore : bk;     // (:716)
                 // every source voted for `label`, so G_s[label] is that source's max probability -- except for target class 0,
@@ -373,6 +383,20 @@ struct TmaCfg {
     static size_t smem_bytes(int K) { return kRingBytes + 2 * NSTAGE * sizeof(uint64_t) + fuse_tally_smem_bytes(K) + 128; }
 };
 
+// (image, tile inside the image) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a 64-bit division per tile.
+struct TileWalker {
+    int64_t image, tile_in_image;
+    int64_t step_images, step_tiles, tpi;
+    MSPL_DEVINL TileWalker(int64_t first, int64_t stride, int64_t tiles_per_image)
+        : image(first / tiles_per_image), tile_in_image(first % tiles_per_image), step_images(stride / tiles_per_image),
+          step_tiles(stride % tiles_per_image), tpi(tiles_per_image) {}
+    MSPL_DEVINL void next() {
+        image += step_images;
+        tile_in_image += step_tiles;
+        if (tile_in_image >= tpi) { tile_in_image -= tpi; ++image; }
+    }
+};
+
 // Producer warp of the TMA-staged kernels: walks this CTA's tiles in (tile, source, chunk) order and fills the ring.
 template <int NCW, int P, int CH, int NSTAGE>
 MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t* full, uint64_t* empty, int lane) {
@@ -385,9 +409,10 @@ MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t*
     const uint64_t policy = tma::evict_first_policy();
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t n = tile / tpi;
-        const int64_t off = (tile - n * tpi) * TP;
+    TileWalker walk(blockIdx.x, gridDim.x, tpi);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, walk.next()) {
+        const int64_t n = walk.image;
+        const int64_t off = walk.tile_in_image * TP;
         const uint32_t row_bytes = (uint32_t)((hw - off < TP ? hw - off : TP) * sizeof(float));
         for (int s = 0; s < S; ++s) {
             const int C = prm.C[s];
@@ -456,9 +481,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
         int stage = 0;
         uint32_t phase = 0;
         const int px = (warp * 32 + lane) * P;          // this thread's first pixel inside the tile
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t n = tile / tpi;
-            const int64_t off = (tile - n * tpi) * TP + px;
+        TileWalker walk(blockIdx.x, gridDim.x, tpi);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, walk.next()) {
+            const int64_t n = walk.image;
+            const int64_t off = walk.tile_in_image * TP + px;
             const bool active = off < hw;                 // partial last tile: the ring holds stale values past the image
             PixelFusion<P, KT, GK, TOP2> fus;
             fus.reset();
