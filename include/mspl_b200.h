@@ -32,11 +32,11 @@ extern "C" {
 #define MSPL_API
 #endif
 
-#define MSPL_ABI_VERSION 1
+#define MSPL_ABI_VERSION 2
 #define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
 #define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
 #define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14) */
-#define MSPL_RADIX_BINS 2048    /* bins of one radix-select histogram pass (11 bits)                */
+#define MSPL_RADIX_BINS 2048    /* bins of one histogram pass: linear conf bins, or 11 bits of the key */
 #define MSPL_RADIX_PASSES 3     /* 11 + 11 + 10 bits of the order-preserving fp32 key               */
 
 typedef enum mspl_status {
@@ -79,8 +79,8 @@ MSPL_API int mspl_softmax_kld(const float* main_logits, const float* aux_logits,
  *   label      (num_images*pixels) u8             conf, unc   same shape f32, NULLable
  *   kld_per_source  HOST array of S device pointers (or NULL; entries may be NULL): per-source KLD maps
  *   class_hist      K u64, += number of pixels per label (the reference's class_array)
- *   conf_hist       K*MSPL_RADIX_BINS u64 or NULL, += pass-0 histogram of conf keys per label, restricted to
- *                   pixels with (pixel_index_in_image % ds_rate) == 0
+ *   conf_hist       K*MSPL_RADIX_BINS u64 or NULL, += linear histogram of conf per label (bin = min(2047, floor(conf*2048)),
+ *                   the input of mspl_bracket_select), restricted to pixels with (pixel_index_in_image % ds_rate) == 0
  *   marginal_count  u64 or NULL, += pixels where some source's top-2 softmax margin is < 1e-6 (and, for
  *                   MSPL_POLICY_PROB, the top-2 margin of F): the only pixels whose label may legitimately
  *                   differ from the reference's argmax-of-softmax */
@@ -113,21 +113,54 @@ MSPL_API int mspl_fuse_sources_lowres(int num_sources, const float* const* main_
 MSPL_API int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,
                      int vote_t, int ignore_label, uint8_t* merged, void* stream);
 
-/* ---- K2: class-balanced thresholds by radix select ([NEW]; CBST/CRST vestiges at
+/* ---- K2/K3: class-balanced thresholds and selection ([NEW]; CBST/CRST vestiges at
  * uest_seg_multi_os.py:88-107, 216-219 -- no reference implementation) --------------------------------
- * thresh[k] = 1.0 if floor(n_k*portion)==0 else the floor(n_k*portion)-th largest conf among kept pixels
- * of class k.  Protocol: zero `hist` (K*MSPL_RADIX_BINS u64) and `state`; pass 0 histogram (fused into
- * mspl_fuse_sources, or mspl_radix_hist_pass(pass=0)); [all-reduce hist over ranks]; mspl_radix_select
- * (pass=0); then for pass = 1, 2: mspl_radix_hist_pass; [all-reduce]; mspl_radix_select.  After pass 2,
- * thresh is final.  mspl_radix_select zeroes `hist` for the next pass.  No host synchronisation needed. */
+ * thresh[k] = 1.0 if floor(n_k*portion)==0 else the floor(n_k*portion)-th largest conf among the pixels of class k
+ * with (pixel_index_in_image % ds_rate) == 0;  final = label if (label != ignore_label && conf >= thresh[label])
+ * else ignore_label.  Exact order statistics, no sort, no host synchronisation.  Two protocols:
+ *
+ * (1) Bracketed -- what the pipeline runs: ONE pass over (label, conf), 6 B/pixel.
+ *   hist (K*MSPL_RADIX_BINS u64, zeroed) holds the LINEAR confidence histogram: bin = clamp(floor(conf*2048), 0, 2047);
+ *   mspl_fuse_sources accumulates it as `conf_hist`, or call mspl_conf_hist.            [all-reduce hist over ranks]
+ *   mspl_bracket_select: per class, the bin holding the j-th largest conf -> bracket[k] = {lo, hi} (2K f32), the rank left
+ *     inside the bin in `state` (mspl_radix_state_bytes, zeroed), kept_count[k] = n_k, thresh[k] = 1.0 for j == 0; zeroes hist.
+ *     The ignore class is never selected, so its threshold is left unresolved: thresh[ignore_label] = +inf (with the vote
+ *     policies all its pixels have conf == 0 and would all be candidates); ignore_label = -1 resolves every class, which
+ *     mspl_bracket_classify accepts only in thresholds-only mode (final_label, ignore_mask, final_hist all NULL).
+ *   mspl_bracket_classify: conf >= hi: kept; conf < lo: ignored; otherwise the pixel index is appended to cand_index
+ *     (u32, capacity num_pixels; *cand_count u64 zeroed by the caller) and provisionally ignored.  Writes final_label /
+ *     ignore_mask (either may be NULL) and += final_hist (K u64, NULLable).  num_pixels < 2^32.
+ *   for pass = 0, 1, 2: mspl_cand_hist_pass (radix histogram of the candidates only); [all-reduce hist];
+ *     mspl_cand_select (zeroes hist; after pass 2 thresh is final).
+ *   mspl_cand_apply: candidates with conf >= thresh[label] get their label back (final_label, ignore_mask, final_hist).
+ *
+ * (2) Generic radix -- 3 full passes over the order-preserving fp32 key (11+11+10 bits), 16 B/pixel with
+ *   mspl_apply_thresholds: zero `hist` and `state`; for pass = 0, 1, 2: mspl_radix_hist_pass; [all-reduce hist];
+ *   mspl_radix_select (zeroes hist).  Independent of (1); the test-suite checks that both give the same bits. */
 MSPL_API size_t mspl_radix_state_bytes(int num_target_classes);
+MSPL_API int mspl_conf_hist(const uint8_t* label, const float* conf, int64_t num_pixels, int64_t pixels_per_image,
+                   int num_target_classes, unsigned long long* hist, int ds_rate, void* stream);
+MSPL_API int mspl_bracket_select(unsigned long long* hist, int num_target_classes, double portion, int ignore_label,
+                        void* state, float* bracket, float* thresh, unsigned long long* kept_count, void* stream);
+MSPL_API int mspl_bracket_classify(const uint8_t* label, const float* conf, const float* bracket, int64_t num_pixels,
+                          int num_target_classes, int ignore_label, uint8_t* final_label, uint8_t* ignore_mask,
+                          unsigned long long* final_hist, uint32_t* cand_index, unsigned long long* cand_count,
+                          void* stream);
+MSPL_API int mspl_cand_hist_pass(const uint8_t* label, const float* conf, const uint32_t* cand_index,
+                        const unsigned long long* cand_count, int64_t pixels_per_image, int num_target_classes,
+                        int pass, const void* state, unsigned long long* hist, int ds_rate, void* stream);
+MSPL_API int mspl_cand_select(unsigned long long* hist, int num_target_classes, int pass, void* state, float* thresh,
+                     void* stream);
+MSPL_API int mspl_cand_apply(const uint8_t* label, const float* conf, const float* thresh, const uint32_t* cand_index,
+                    const unsigned long long* cand_count, int num_target_classes, int ignore_label,
+                    uint8_t* final_label, uint8_t* ignore_mask, unsigned long long* final_hist, void* stream);
 MSPL_API int mspl_radix_hist_pass(const uint8_t* label, const float* conf, int64_t num_pixels,
                          int64_t pixels_per_image, int num_target_classes, int pass, const void* state,
                          unsigned long long* hist, int ds_rate, void* stream);
 MSPL_API int mspl_radix_select(unsigned long long* hist, int num_target_classes, int pass, double portion,
                       void* state, float* thresh, unsigned long long* kept_count, void* stream);
 
-/* ---- K3: thresholding / ignore mask ([NEW]) --------------------------------------------------------
+/* ---- K3 stand-alone: thresholding / ignore mask with given thresholds ([NEW]) ----------------------------
  * final = label if (label != ignore_label && conf >= thresh[label]) else ignore_label.
  * ignore_mask (u8, 1 where final == ignore_label) and final_hist (K u64, +=) may be NULL. */
 MSPL_API int mspl_apply_thresholds(const uint8_t* label, const float* conf, const float* thresh,

@@ -71,6 +71,13 @@ MSPL_DEVINL uint32_t radix_prefix(uint32_t key, int pass) {
     return pass == 0 ? 0u : pass == 1 ? (key >> 21) : (key >> 10);
 }
 
+// Bin of the LINEAR confidence histogram (MSPL_RADIX_BINS equal steps over [0,1], clamped): monotone non-decreasing in f
+// for every float (x2048 is exact), so "bin above / below the class's selected bin" brackets the order statistic.
+// bin(f) >= b  <=>  f >= b/2048 for 1 <= b <= 2047 (both sides exact in fp32).  NaN lands in bin 0.
+MSPL_DEVINL uint32_t conf_bin(float f) {
+    return (uint32_t)max(0, min(MSPL_RADIX_BINS - 1, __float2int_rd(f * (float)MSPL_RADIX_BINS)));
+}
+
 MSPL_DEVINL double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

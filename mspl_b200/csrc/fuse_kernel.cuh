@@ -200,7 +200,7 @@ struct Tally {
                 const bool keep = active && (prm.ds_rate <= 1 || ((off + p) % prm.ds_rate) == 0);
                 // vote policies give ignore-labelled pixels conf == 0: one known bin, counted without atomics
                 if (prm.policy != MSPL_POLICY_PROB && label[p] == prm.ignore) n_ignore_zero += keep;
-                else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + (float_to_key(conf[p]) >> 21)], 1u);
+                else if (keep) atomicAdd(&s_hist[label[p] * MSPL_RADIX_BINS + conf_bin(conf[p])], 1u);
             }
         }
         if ((pending += P) > 255 - P) spill();
@@ -216,7 +216,7 @@ struct Tally {
             if (leader && w) atomicAdd(&s_cls[k], w);
         }
         const uint32_t wz = __reduce_add_sync(0xffffffffu, n_ignore_zero);
-        if (leader && wz) atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + (float_to_key(0.f) >> 21)], wz);
+        if (leader && wz) atomicAdd(&s_hist[prm.ignore * MSPL_RADIX_BINS + conf_bin(0.f)], wz);
         const uint32_t wm = __reduce_add_sync(0xffffffffu, n_marginal);
         if (leader && wm && prm.marginal) atomicAdd(prm.marginal, (unsigned long long)wm);
         __syncthreads();

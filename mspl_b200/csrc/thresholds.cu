@@ -1,6 +1,14 @@
-// K2 (class-balanced thresholds by 3-pass radix select over shared-memory histograms) and
-// K3 (threshold / ignore-mask application).  [NEW] stages: the reference only keeps the CBST/CRST flags
-// (uest_seg_multi_os.py:88-107, 216-219); their definition is SURVEY.md section 8 A4'' (restated in DESIGN.md).
+// K2 (class-balanced thresholds: exact per-class order statistics without a sort) and K3 (threshold / ignore-mask
+// application).  [NEW] stages: the reference only keeps the CBST/CRST flags (uest_seg_multi_os.py:88-107, 216-219); their
+// definition is SURVEY.md section 8 A4'' (restated in DESIGN.md).
+//
+// Two protocols over the same definition:
+//  * bracketed (production): K1 already accumulated a LINEAR 2,048-bin histogram of conf per class.  bracket_select finds,
+//    per class, the bin holding the j-th largest conf; ONE pass over (label, conf) then settles every pixel outside that
+//    bin (keep / ignore), writes the final map and appends the few pixels inside it to a candidate list; a 3-pass radix
+//    select over the candidates alone gives the exact threshold and cand_apply patches their labels.  6 B/pixel.
+//  * generic radix (mspl_radix_*): 3 full passes over (label, conf) on the order-preserving key + mspl_apply_thresholds,
+//    16 B/pixel; kept as the independent cross-check of the bracketed protocol and for callers with their own state.
 #include "common.cuh"
 
 namespace mspl {
@@ -41,7 +49,15 @@ MSPL_DEVINL void store_bytes(uint8_t* __restrict__ dst, int64_t i0, const uint8_
     else dst[i0] = v[0];
 }
 
-// Histogram of the PASS-th digit of the conf keys whose higher bits equal the class's resolved prefix.
+constexpr int kLinearPass = 3;     // PASS value of the linear-bin histogram (conf_bin) that starts the bracketed protocol
+
+template <int PASS> MSPL_DEVINL uint32_t pass_digit(uint32_t key, float conf) {
+    return PASS == kLinearPass ? conf_bin(conf) : radix_digit(key, PASS);
+}
+template <int PASS> MSPL_DEVINL uint32_t pass_prefix(uint32_t key) { return PASS == kLinearPass ? 0u : radix_prefix(key, PASS); }
+
+// Histogram of the PASS-th digit of the conf keys whose higher bits equal the class's resolved prefix
+// (PASS == kLinearPass: the linear conf_bin histogram of every pixel of classes [0,K); `state` unused).
 // Instruction-lean inner loop (5 B/pixel leaves ~25 issue slots per pixel at full HBM rate): one shared-memory lookup
 // per pixel returns the class's prefix, or an impossible value for classes that are done / out of range.
 template <int VEC, int PASS>
@@ -55,7 +71,8 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
     for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
     if (threadIdx.x <= MSPL_MAX_CLASSES) {
         const int k = threadIdx.x;
-        s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;    // no key prefix has all 32 bits set
+        if (PASS == kLinearPass) s_prefix[k] = k < K ? 0u : 0xffffffffu;
+        else s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;    // no key prefix has all 32 bits set
     }
     __syncthreads();
     // conf == +0 is by far the most common duplicate (every ignore-labelled pixel of the vote policies): those are counted
@@ -84,11 +101,11 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
             for (int v = 0; v < VEC; ++v) {
                 const uint32_t lab = min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES);
                 const uint32_t key = float_to_key(c[u][v]);
-                bool match = radix_prefix(key, PASS) == s_prefix[lab];
+                bool match = pass_prefix<PASS>(key) == s_prefix[lab];
                 if (ds_rate > 1) match = match && (((g0 + u * kHistThreads) * VEC + v) % hw) % ds_rate == 0;
                 if (match) {
                     if (key == zero_key) zpacked += 1ull << (8 * lab);
-                    else atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, PASS)], 1u);
+                    else atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + pass_digit<PASS>(key, c[u][v])], 1u);
                 }
             }
         }
@@ -103,67 +120,88 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
     for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
         zcnt[k] += (uint32_t)(zpacked >> (8 * k)) & 0xffu;
         const uint32_t w = __reduce_add_sync(0xffffffffu, zcnt[k]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[k * MSPL_RADIX_BINS + radix_digit(zero_key, PASS)], w);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[k * MSPL_RADIX_BINS + pass_digit<PASS>(zero_key, 0.f)], w);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += kHistThreads)
         if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
 }
 
-// One CTA per class: locate the bin holding the rank-th largest key, extend the prefix, zero the histogram row.
+// Suffix scan helper of the select kernels: the CTA's 256 threads each own nb/256 consecutive bins of s_h (already in shared
+// memory); returns through (above, mine, total) the count in the bins above this thread's range, in its range, and overall.
+MSPL_DEVINL void suffix_counts(const unsigned long long* s_h, int per, unsigned long long* s_warp, unsigned long long& above,
+                               unsigned long long& mine, unsigned long long& total) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    mine = 0;
+    for (int i = 0; i < per; ++i) mine += s_h[t * per + i];
+    unsigned long long incl = mine;                       // inclusive suffix sum inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+    }
+    if (lane == 0) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long higher = 0;
+    total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) {
+        total += s_warp[w2];
+        if (w2 > warp) higher += s_warp[w2];
+    }
+    above = higher + incl - mine;
+}
+
+// One CTA (256 threads) per class: locate the bin holding the rank-th largest key, extend the prefix, zero the histogram
+// row.  INIT: derive the rank from the row total (the first pass of the generic protocol).
+template <bool INIT>
 __global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* __restrict__ hist, int pass, double portion,
                                                            RadixState* __restrict__ state, float* __restrict__ thresh,
                                                            unsigned long long* __restrict__ kept_count) {
+    __shared__ unsigned long long s_h[MSPL_RADIX_BINS];
+    __shared__ unsigned long long s_warp[8];
+    __shared__ RadixState s_st;
     const int k = blockIdx.x;
     unsigned long long* h = hist + (size_t)k * MSPL_RADIX_BINS;
     const int nb = pass == 2 ? 1024 : MSPL_RADIX_BINS;
     const int bits = pass == 2 ? 10 : 11;
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const int per = nb / 32;
-        unsigned long long mine = 0;
-        for (int i = 0; i < per; ++i) mine += h[lane * per + i];
-        // above = sum over lanes > lane (suffix sum); total = sum over all lanes
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += t;
-        }
-        const unsigned long long above = incl - mine;
-        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 0);
-        RadixState st = state[k];
-        if (pass == 0) {
-            st.count = total;
-            unsigned long long j = (unsigned long long)((double)total * portion);   // floor(n_k * p), as int(n*p)
-            if (j > total) j = total;
-            st.rank = j;
-            st.prefix = 0;
-            st.done = (j == 0);
-            if (lane == 0) {
-                if (st.done) thresh[k] = 1.0f;
-                if (kept_count) kept_count[k] = total;
-            }
-        }
-        if (!st.done) {
-            if (above < st.rank && st.rank <= above + mine) {       // exactly one lane
-                unsigned long long acc = above;
-                int d = lane * per + per - 1;
-                for (; d > lane * per; --d) {
-                    if (acc + h[d] >= st.rank) break;
-                    acc += h[d];
-                }
-                st.rank -= acc;
-                st.prefix = (st.prefix << bits) | (uint32_t)d;
+    const int per = nb / 256;
+    for (int i = threadIdx.x; i < MSPL_RADIX_BINS; i += 256) {
+        s_h[i] = h[i];
+        h[i] = 0;
+    }
+    if (threadIdx.x == 0) s_st = state[k];
+    __syncthreads();
+    unsigned long long above, mine, total;
+    suffix_counts(s_h, per, s_warp, above, mine, total);
+    RadixState st = s_st;
+    if (INIT) {
+        st.count = total;
+        unsigned long long j = (unsigned long long)((double)total * portion);   // floor(n_k * p), as int(n*p)
+        if (j > total) j = total;
+        st.rank = j;
+        st.prefix = 0;
+        st.done = (j == 0);
+        if (threadIdx.x == 0) {
+            if (st.done) {
+                thresh[k] = 1.0f;
                 state[k] = st;
-                if (pass == 2) thresh[k] = key_to_float(st.prefix);
             }
-        } else if (lane == 0) {
-            state[k] = st;
+            if (kept_count) kept_count[k] = total;
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < MSPL_RADIX_BINS; i += blockDim.x) h[i] = 0;
+    if (!st.done && above < st.rank && st.rank <= above + mine) {       // exactly one thread
+        unsigned long long acc = above;
+        int d = threadIdx.x * per + per - 1;
+        for (; d > threadIdx.x * per; --d) {
+            if (acc + s_h[d] >= st.rank) break;
+            acc += s_h[d];
+        }
+        st.rank -= acc;
+        st.prefix = (st.prefix << bits) | (uint32_t)d;
+        state[k] = st;
+        if (pass == 2) thresh[k] = key_to_float(st.prefix);
+    }
 }
 
 template <int VEC>
@@ -225,6 +263,219 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
     }
 }
 
+// ---- bracketed protocol ---------------------------------------------------------------------------------------------------
+// One CTA per class on the (all-reduced) linear histogram: j = floor(n_k * portion); the bin b holding the j-th largest conf
+// brackets the threshold: conf >= hi = (b+1)/2048 is certainly kept, conf < lo = b/2048 certainly dropped, and the pixels
+// in between are the candidates among which the (j - #above)-th largest is the threshold.  Leaves `state` ready for the
+// candidate radix passes and zeroes the histogram row.
+__global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long* __restrict__ hist, double portion, int ignore,
+                                                             RadixState* __restrict__ state, float2* __restrict__ bracket,
+                                                             float* __restrict__ thresh, unsigned long long* __restrict__ kept_count) {
+    __shared__ unsigned long long s_h[MSPL_RADIX_BINS];
+    __shared__ unsigned long long s_warp[8];
+    const int k = blockIdx.x;
+    unsigned long long* h = hist + (size_t)k * MSPL_RADIX_BINS;
+    constexpr int per = MSPL_RADIX_BINS / 256;
+    for (int i = threadIdx.x; i < MSPL_RADIX_BINS; i += 256) {
+        s_h[i] = h[i];
+        h[i] = 0;
+    }
+    __syncthreads();
+    unsigned long long above, mine, total;
+    suffix_counts(s_h, per, s_warp, above, mine, total);
+    unsigned long long j = (unsigned long long)((double)total * portion);       // floor(n_k * p), as int(n*p)
+    if (j > total) j = total;
+    if (j == 0 || k == ignore) {
+        if (threadIdx.x == 0) {
+            RadixState st;
+            st.rank = 0; st.count = total; st.prefix = 0; st.done = 1;
+            state[k] = st;
+            // j == 0: keep iff conf >= 1.0, no candidates.  The ignore class is never selected: its threshold stays unresolved
+            // (+inf) -- with the vote policies all of its pixels share conf == 0 and would all be candidates.
+            const float t = k == ignore ? INFINITY : 1.0f;
+            thresh[k] = t;
+            bracket[k] = make_float2(t, t);
+            if (kept_count) kept_count[k] = total;
+        }
+        return;
+    }
+    if (above < j && j <= above + mine) {               // exactly one thread
+        unsigned long long acc = above;
+        int b = threadIdx.x * per + per - 1;
+        for (; b > threadIdx.x * per; --b) {
+            if (acc + s_h[b] >= j) break;
+            acc += s_h[b];
+        }
+        RadixState st;
+        st.rank = j - acc; st.count = total; st.prefix = 0; st.done = 0;
+        state[k] = st;
+        bracket[k] = make_float2(b == 0 ? -INFINITY : (float)b * (1.0f / MSPL_RADIX_BINS),
+                                 b == MSPL_RADIX_BINS - 1 ? INFINITY : (float)(b + 1) * (1.0f / MSPL_RADIX_BINS));
+        if (kept_count) kept_count[k] = total;
+    }
+}
+
+constexpr int kCandBuf = 768;                                  // per-warp staging entries
+constexpr int kCandFlushAt = kCandBuf - 32 * 4 * kUnroll;      // a warp adds at most 32 lanes x VEC x kUnroll per iteration
+static_assert(kCandFlushAt > 0, "per-warp candidate staging must hold one iteration's worst case");
+
+// The one full pass of the bracketed protocol: settle every pixel outside its class's bracket, stage the candidates.
+// Candidates get the ignore label for now (and count as ignored); cand_apply patches the ones that reach the threshold.
+// Appends are staged per warp in shared memory and flushed with one global atomic per ~kCandFlushAt entries, so the list
+// costs nothing when candidates are rare and stays correct (just slower) when every pixel is one.
+template <int VEC>
+__global__ void __launch_bounds__(256) bracket_classify_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                               const float2* __restrict__ bracket, int64_t npix, int K, int ignore,
+                                                               uint8_t* __restrict__ final_label, uint8_t* __restrict__ ignore_mask,
+                                                               unsigned long long* __restrict__ final_hist,
+                                                               uint32_t* __restrict__ cand_index,
+                                                               unsigned long long* __restrict__ cand_count) {
+    __shared__ float2 s_br[MSPL_MAX_CLASSES + 1];       // (+inf,+inf) for the ignore class and labels outside [0,K): never kept
+    __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
+    __shared__ uint32_t s_buf[8][kCandBuf];
+    __shared__ uint32_t s_fill[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x <= MSPL_MAX_CLASSES) {
+        const int k = threadIdx.x;
+        s_br[k] = (k < K && k != ignore) ? bracket[k] : make_float2(INFINITY, INFINITY);
+        if (k < MSPL_MAX_CLASSES) s_cls[k] = 0;
+    }
+    if (threadIdx.x < 8) s_fill[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t cnt[MSPL_MAX_CLASSES] = {};
+    unsigned long long packed = 0;          // 8 bits per class, spilled into cnt[] before it can overflow
+    int pending = 0;
+    auto flush = [&](uint32_t fill) {       // whole warp; fill is warp-uniform
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < fill; i += 32) cand_index[base + i] = s_buf[warp][i];
+        __syncwarp();
+        if (lane == 0) s_fill[warp] = 0;
+        __syncwarp();
+    };
+    const int64_t n_groups = (npix + VEC - 1) / VEC;
+    // warp-uniform trip count (the staging flush is a warp-collective): iterate on the warp's first group
+    for (int64_t w0 = blockIdx.x * (int64_t)(256 * kUnroll) + warp * 32; w0 < n_groups; w0 += (int64_t)gridDim.x * 256 * kUnroll) {
+        const int64_t g0 = w0 + lane;
+        uint8_t l[kUnroll][VEC];
+        float c[kUnroll][VEC];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (g < n_groups) load_label_conf<VEC>(label, conf, g * VEC, l[u], c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * 256;
+            if (g < n_groups) {
+                uint8_t f[VEC], mk[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float2 br = s_br[min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES)];
+                    const bool keep = c[u][v] >= br.y;
+                    if (c[u][v] >= br.x && !keep) {         // inside the bracket: candidate
+                        const uint32_t slot = atomicAdd(&s_fill[warp], 1u);
+                        s_buf[warp][slot] = (uint32_t)(g * VEC + v);
+                    }
+                    f[v] = keep ? l[u][v] : (uint8_t)ignore;
+                    mk[v] = keep ? 0 : 1;
+                    if (final_hist) packed += 1ull << (8 * f[v]);
+                }
+                if (final_label) store_bytes<VEC>(final_label, g * VEC, f);
+                if (ignore_mask) store_bytes<VEC>(ignore_mask, g * VEC, mk);
+            }
+        }
+        if ((pending += VEC * kUnroll) > 255 - VEC * kUnroll) {
+#pragma unroll
+            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+            packed = 0;
+            pending = 0;
+        }
+        __syncwarp();
+        const uint32_t fill = s_fill[warp];
+        if (fill > (uint32_t)kCandFlushAt) flush(fill);
+    }
+    __syncwarp();
+    const uint32_t fill = s_fill[warp];
+    if (fill) flush(fill);
+    if (final_hist) {
+#pragma unroll
+        for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
+            cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+            const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[k]);
+            if (lane == 0 && w) atomicAdd(&s_cls[k], w);
+        }
+        __syncthreads();
+        if (threadIdx.x < K && s_cls[threadIdx.x]) atomicAdd(final_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+    }
+}
+
+// Radix pass over the candidate list only (gathers label/conf through the index): same digits, prefixes and state as
+// radix_hist_kernel, so radix_select_kernel<false> continues from the rank bracket_select left in `state`.
+template <int PASS>
+__global__ void __launch_bounds__(kHistThreads) cand_hist_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                                 const uint32_t* __restrict__ cand_index,
+                                                                 const unsigned long long* __restrict__ cand_count, int64_t hw, int K,
+                                                                 const RadixState* __restrict__ state,
+                                                                 unsigned long long* __restrict__ hist, int ds_rate) {
+    extern __shared__ uint32_t s_hist[];
+    __shared__ uint32_t s_prefix[MSPL_MAX_CLASSES + 1];
+    const unsigned long long n = *cand_count;
+    if ((unsigned long long)blockIdx.x * kHistThreads >= n) return;
+    const int nbins = K * MSPL_RADIX_BINS;
+    for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
+    if (threadIdx.x <= MSPL_MAX_CLASSES) {
+        const int k = threadIdx.x;
+        s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;
+    }
+    __syncthreads();
+    for (unsigned long long i = (unsigned long long)blockIdx.x * kHistThreads + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * kHistThreads) {
+        const uint32_t idx = cand_index[i];
+        const uint32_t lab = min((uint32_t)label[idx], (uint32_t)MSPL_MAX_CLASSES);
+        const uint32_t key = float_to_key(conf[idx]);
+        bool match = radix_prefix(key, PASS) == s_prefix[lab];
+        if (ds_rate > 1) match = match && ((int64_t)idx % hw) % ds_rate == 0;
+        if (match) atomicAdd(&s_hist[lab * MSPL_RADIX_BINS + radix_digit(key, PASS)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += kHistThreads)
+        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+}
+
+// Patch the candidates that reach their class's threshold: they were written (and counted) as ignored by the classify pass.
+__global__ void __launch_bounds__(256) cand_apply_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                         const float* __restrict__ thresh, const uint32_t* __restrict__ cand_index,
+                                                         const unsigned long long* __restrict__ cand_count, int K, int ignore,
+                                                         uint8_t* __restrict__ final_label, uint8_t* __restrict__ ignore_mask,
+                                                         unsigned long long* __restrict__ final_hist) {
+    __shared__ float s_thresh[MSPL_MAX_CLASSES + 1];
+    __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
+    const unsigned long long n = *cand_count;
+    if ((unsigned long long)blockIdx.x * 256 >= n) return;
+    if (threadIdx.x <= MSPL_MAX_CLASSES) {
+        const int k = threadIdx.x;
+        s_thresh[k] = (k < K && k != ignore) ? thresh[k] : INFINITY;
+        if (k < MSPL_MAX_CLASSES) s_cls[k] = 0;
+    }
+    __syncthreads();
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256) {
+        const uint32_t idx = cand_index[i];
+        const uint32_t lab = min((uint32_t)label[idx], (uint32_t)MSPL_MAX_CLASSES);
+        if (conf[idx] >= s_thresh[lab]) {
+            if (final_label) final_label[idx] = (uint8_t)lab;
+            if (ignore_mask) ignore_mask[idx] = 0;
+            atomicAdd(&s_cls[lab], 1u);
+        }
+    }
+    __syncthreads();
+    if (final_hist && threadIdx.x < K && s_cls[threadIdx.x]) {
+        atomicAdd(final_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+        if (ignore < K) atomicAdd(final_hist + ignore, 0ull - (unsigned long long)s_cls[threadIdx.x]);   // had been counted as ignored
+    }
+}
+
 // Persistent grid of exactly the CTAs that can be resident at once (these kernels are latency-bound: a partial second
 // wave would run at a fraction of the occupancy).
 template <typename Kern>
@@ -277,8 +528,9 @@ extern "C" int mspl_radix_select(unsigned long long* hist, int num_target_classe
     if (!hist || !state || !thresh || K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES) return MSPL_ERR_BAD_ARG;
     if (!(portion >= 0.0)) return MSPL_ERR_BAD_ARG;
     if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
-    radix_select_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, pass, portion, static_cast<RadixState*>(state),
-                                                                          thresh, kept_count);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pass == 0) radix_select_kernel<true><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count);
+    else radix_select_kernel<false><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count);
     return launch_status();
 }
 
@@ -303,5 +555,112 @@ extern "C" int mspl_apply_thresholds(const uint8_t* label, const float* conf, co
     else
         apply_thresholds_kernel<1><<<(unsigned)grid, 256, 0, st>>>(label, conf, thresh, num_pixels, K, ignore_label, final_label,
                                                                   ignore_mask, final_hist);
+    return launch_status();
+}
+
+// ---- bracketed protocol entry points ----------------------------------------------------------------------------------
+extern "C" int mspl_conf_hist(const uint8_t* label, const float* conf, int64_t num_pixels, int64_t pixels_per_image,
+                              int num_target_classes, unsigned long long* hist, int ds_rate, void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !hist || num_pixels < 0 || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ds_rate < 1) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(conf, 4) || !aligned_to(hist, 8)) return MSPL_ERR_ALIGN;
+    if (num_pixels == 0) return MSPL_OK;
+    const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
+    const int vec = (num_pixels % 4 == 0 && aligned_to(label, 4) && aligned_to(conf, 16)) ? 4 : 1;
+    auto kern = vec == 4 ? radix_hist_kernel<4, kLinearPass> : radix_hist_kernel<1, kLinearPass>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
+    const int64_t grid = resident_grid(kern, num_pixels / vec / kUnroll + 1, kHistThreads, smem);
+    kern<<<(unsigned)grid, kHistThreads, smem, static_cast<cudaStream_t>(stream)>>>(label, conf, num_pixels, pixels_per_image, K,
+                                                                                    nullptr, hist, ds_rate);
+    return launch_status();
+}
+
+extern "C" int mspl_bracket_select(unsigned long long* hist, int num_target_classes, double portion, int ignore_label, void* state,
+                                   float* bracket, float* thresh, unsigned long long* kept_count, void* stream) {
+    const int K = num_target_classes;
+    if (!hist || !state || !bracket || !thresh || K < 1 || K > MSPL_MAX_CLASSES || !(portion >= 0.0)) return MSPL_ERR_BAD_ARG;
+    if (ignore_label < -1 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(bracket, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
+    bracket_select_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, portion, ignore_label, static_cast<RadixState*>(state),
+                                                                            reinterpret_cast<float2*>(bracket), thresh, kept_count);
+    return launch_status();
+}
+
+extern "C" int mspl_bracket_classify(const uint8_t* label, const float* conf, const float* bracket, int64_t num_pixels,
+                                     int num_target_classes, int ignore_label, uint8_t* final_label, uint8_t* ignore_mask,
+                                     unsigned long long* final_hist, uint32_t* cand_index, unsigned long long* cand_count,
+                                     void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !bracket || !cand_index || !cand_count || num_pixels < 0) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ignore_label < -1 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (ignore_label < 0 && (final_label || ignore_mask || final_hist)) return MSPL_ERR_BAD_ARG;   // thresholds-only mode
+    if (num_pixels > 0xffffffffll) return MSPL_ERR_UNSUPPORTED;          // candidate indices are 32-bit
+    if (!aligned_to(conf, 4) || !aligned_to(bracket, 8) || !aligned_to(cand_index, 4) || !aligned_to(cand_count, 8) ||
+        (final_hist && !aligned_to(final_hist, 8)))
+        return MSPL_ERR_ALIGN;
+    if (num_pixels == 0) return MSPL_OK;
+    auto ok = [&](size_t a) {
+        return aligned_to(label, a) && aligned_to(conf, 4 * a) && (!final_label || aligned_to(final_label, a)) &&
+               (!ignore_mask || aligned_to(ignore_mask, a));
+    };
+    const int vec = (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float2* br = reinterpret_cast<const float2*>(bracket);
+    if (vec == 4) {
+        const int64_t grid = resident_grid(bracket_classify_kernel<4>, num_pixels / vec / kUnroll + 1, 256, 0);
+        bracket_classify_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, br, num_pixels, K, ignore_label, final_label,
+                                                                  ignore_mask, final_hist, cand_index, cand_count);
+    } else {
+        const int64_t grid = resident_grid(bracket_classify_kernel<1>, num_pixels / vec / kUnroll + 1, 256, 0);
+        bracket_classify_kernel<1><<<(unsigned)grid, 256, 0, st>>>(label, conf, br, num_pixels, K, ignore_label, final_label,
+                                                                  ignore_mask, final_hist, cand_index, cand_count);
+    }
+    return launch_status();
+}
+
+extern "C" int mspl_cand_hist_pass(const uint8_t* label, const float* conf, const uint32_t* cand_index,
+                                   const unsigned long long* cand_count, int64_t pixels_per_image, int num_target_classes, int pass,
+                                   const void* state, unsigned long long* hist, int ds_rate, void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !cand_index || !cand_count || !state || !hist || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES || ds_rate < 1) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(conf, 4) || !aligned_to(cand_index, 4) || !aligned_to(cand_count, 8) || !aligned_to(hist, 8) || !aligned_to(state, 8))
+        return MSPL_ERR_ALIGN;
+    const size_t smem = sizeof(uint32_t) * (size_t)K * MSPL_RADIX_BINS;
+    auto kern = pass == 0 ? cand_hist_kernel<0> : pass == 1 ? cand_hist_kernel<1> : cand_hist_kernel<2>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
+    kern<<<2 * kNumSMs, kHistThreads, smem, static_cast<cudaStream_t>(stream)>>>(label, conf, cand_index, cand_count, pixels_per_image,
+                                                                               K, static_cast<const RadixState*>(state), hist, ds_rate);
+    return launch_status();
+}
+
+extern "C" int mspl_cand_select(unsigned long long* hist, int num_target_classes, int pass, void* state, float* thresh, void* stream) {
+    const int K = num_target_classes;
+    if (!hist || !state || !thresh || K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
+    radix_select_kernel<false><<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, pass, 0.0, static_cast<RadixState*>(state),
+                                                                                 thresh, nullptr);
+    return launch_status();
+}
+
+extern "C" int mspl_cand_apply(const uint8_t* label, const float* conf, const float* thresh, const uint32_t* cand_index,
+                               const unsigned long long* cand_count, int num_target_classes, int ignore_label, uint8_t* final_label,
+                               uint8_t* ignore_mask, unsigned long long* final_hist, void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !thresh || !cand_index || !cand_count) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ignore_label < 0 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (!final_label && !ignore_mask && !final_hist) return MSPL_OK;
+    if (!aligned_to(conf, 4) || !aligned_to(thresh, 4) || !aligned_to(cand_index, 4) || !aligned_to(cand_count, 8) ||
+        (final_hist && !aligned_to(final_hist, 8)))
+        return MSPL_ERR_ALIGN;
+    cand_apply_kernel<<<2 * kNumSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(label, conf, thresh, cand_index, cand_count, K,
+                                                                                 ignore_label, final_label, ignore_mask, final_hist);
     return launch_status();
 }

@@ -227,15 +227,89 @@ def softmax_kld(main, aux, want_prob=True, want_kld=True):
     return prob, kld
 
 
-def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None):
-    """K2: class-balanced thresholds by 3-pass radix select; exact order statistics, no sort, no host sync.
+def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_label=4, conf_hist=None, all_reduce=None,
+                     want_final=True, want_mask=False, final_hist=None):
+    """K2+K3, bracketed protocol: class-balanced thresholds AND the thresholded label map in ONE pass over (label, conf).
 
-    label (N,H,W) u8, conf (N,H,W) f32.  conf_hist: the pass-0 histogram already accumulated by fuse_sources
-    (it is consumed: zeroed on return); if None, pass 0 is computed here.  all_reduce: optional callable applied
-    in place to each pass's (K, 2048) int64 histogram (e.g. ``lambda h: dist.all_reduce(h)``) so that every rank
-    selects the same bins -- thresholds are then identical for 1 or N GPUs.
-    Returns (thresh f32 (K,), kept_count int64 (K,)).
-    """
+    label (N,H,W) u8, conf (N,H,W) f32.  conf_hist: the linear confidence histogram already accumulated by fuse_sources
+    (consumed: zeroed on return); if None it is computed here (one more 5 B/pixel pass).  all_reduce: optional callable
+    applied in place to each (K, 2048) int64 histogram (``lambda h: dist.all_reduce(h)``) so that every rank selects the
+    same bins -- thresholds are then identical for 1 or N GPUs.  No host synchronisation.
+    The ignore class is never selected, so its threshold is not resolved: thresh[ignore_label] = +inf (kept_count[ignore_label]
+    is still its pixel count).  ignore_label=None resolves every class; no map can be written then (thresholds only).
+    Returns (thresh f32 (K,), kept_count i64 (K,), final u8 or None, mask u8 or None, final_hist i64 (K,) or None)."""
+    label = _require_cuda(label, "label", torch.uint8)
+    conf = _require_cuda(conf, "conf", torch.float32)
+    if label.shape != conf.shape or label.dim() < 2:
+        raise ValueError("label/conf must share a (..., H, W) shape")
+    dev = label.device
+    hw = label.shape[-1] * label.shape[-2]
+    npix = label.numel()
+    if npix >= 2 ** 32:
+        raise NotImplementedError("select_and_apply indexes candidates with 32 bits; use cb_thresholds_radix + apply_thresholds")
+    lib = _lib.load()
+    K = num_classes
+    state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
+    thresh = torch.empty(K, dtype=torch.float32, device=dev)
+    bracket = torch.empty((K, 2), dtype=torch.float32, device=dev)
+    kept = torch.zeros(K, dtype=torch.int64, device=dev)
+    cand_index = torch.empty(max(npix, 1), dtype=torch.int32, device=dev)      # u32 indices; worst case every pixel is a candidate
+    cand_count = torch.zeros((), dtype=torch.int64, device=dev)
+    outputs = want_final or want_mask or final_hist is not None
+    if ignore_label is None:
+        if outputs:
+            raise ValueError("a label map / mask / final histogram needs an ignore_label")
+        ign = -1
+    else:
+        ign = int(ignore_label)
+    final = torch.empty_like(label) if want_final else None
+    mask = torch.empty_like(label) if want_mask else None
+    if outputs and final_hist is None:
+        final_hist = torch.zeros(K, dtype=torch.int64, device=dev)
+    hist = conf_hist
+    if hist is not None:
+        _require_cuda(hist, "conf_hist", torch.int64)
+    else:
+        hist = torch.zeros((K, RADIX_BINS), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        if conf_hist is None:
+            _lib.check(lib.mspl_conf_hist(_ptr(label), _ptr(conf), npix, hw, K, _ptr(hist), int(ds_rate), st), "mspl_conf_hist")
+        if all_reduce is not None:
+            all_reduce(hist)
+        _lib.check(lib.mspl_bracket_select(_ptr(hist), K, float(portion), ign, _ptr(state), _ptr(bracket), _ptr(thresh), _ptr(kept),
+                                           st), "mspl_bracket_select")
+        _lib.check(lib.mspl_bracket_classify(_ptr(label), _ptr(conf), _ptr(bracket), npix, K, ign, _ptr(final), _ptr(mask),
+                                             _ptr(final_hist if outputs else None), _ptr(cand_index), _ptr(cand_count), st),
+                   "mspl_bracket_classify")
+        for p in range(RADIX_PASSES):
+            _lib.check(lib.mspl_cand_hist_pass(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, p, _ptr(state),
+                                               _ptr(hist), int(ds_rate), st), "mspl_cand_hist_pass")
+            if all_reduce is not None:
+                all_reduce(hist)
+            _lib.check(lib.mspl_cand_select(_ptr(hist), K, p, _ptr(state), _ptr(thresh), st), "mspl_cand_select")
+        if outputs:
+            _lib.check(lib.mspl_cand_apply(_ptr(label), _ptr(conf), _ptr(thresh), _ptr(cand_index), _ptr(cand_count), K, ign,
+                                           _ptr(final), _ptr(mask), _ptr(final_hist), st), "mspl_cand_apply")
+    return thresh, kept, final, mask, (final_hist if outputs else None)
+
+
+SELECT_AND_APPLY_LAUNCHES = 9      # bracket_select + classify + 3 x (cand_hist + cand_select) + cand_apply
+
+
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None, ignore_label=None):
+    """K2: class-balanced thresholds only (bracketed protocol without writing a label map); see select_and_apply.
+    ignore_label=None resolves the threshold of every class (the definition of the oracle's cb_thresholds); naming the
+    ignore class skips it (thresh = +inf), which is much cheaper when its pixels all share conf == 0 (vote policies).
+    Returns (thresh f32 (K,), kept_count int64 (K,))."""
+    thresh, kept, _, _, _ = select_and_apply(label, conf, portion, ds_rate, num_classes, ignore_label=ignore_label,
+                                             conf_hist=conf_hist, all_reduce=all_reduce, want_final=False, want_mask=False)
+    return thresh, kept
+
+
+def cb_thresholds_radix(label, conf, portion=0.2, ds_rate=1, num_classes=5, all_reduce=None):
+    """K2, generic protocol: 3 full radix passes over the order-preserving key of conf (no linear histogram, no candidate
+    list).  Same definition and the same bits as cb_thresholds; 15 B/pixel instead of 5-6."""
     label = _require_cuda(label, "label", torch.uint8)
     conf = _require_cuda(conf, "conf", torch.float32)
     if label.shape != conf.shape or label.dim() < 2:
@@ -248,17 +322,12 @@ def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=
     state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
     thresh = torch.empty(K, dtype=torch.float32, device=dev)
     kept = torch.zeros(K, dtype=torch.int64, device=dev)
-    hist = conf_hist
-    if hist is not None:
-        _require_cuda(hist, "conf_hist", torch.int64)
-    else:
-        hist = torch.zeros((K, RADIX_BINS), dtype=torch.int64, device=dev)
+    hist = torch.zeros((K, RADIX_BINS), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         st = _stream(dev)
         for p in range(RADIX_PASSES):
-            if p > 0 or conf_hist is None:
-                _lib.check(lib.mspl_radix_hist_pass(_ptr(label), _ptr(conf), npix, hw, K, p, _ptr(state), _ptr(hist),
-                                                    int(ds_rate), st), "mspl_radix_hist_pass")
+            _lib.check(lib.mspl_radix_hist_pass(_ptr(label), _ptr(conf), npix, hw, K, p, _ptr(state), _ptr(hist),
+                                                int(ds_rate), st), "mspl_radix_hist_pass")
             if all_reduce is not None:
                 all_reduce(hist)
             _lib.check(lib.mspl_radix_select(_ptr(hist), K, p, float(portion), _ptr(state), _ptr(thresh), _ptr(kept), st),

@@ -2,8 +2,9 @@
 multi-GPU.  This is the post-network body of generate_pseudo_label_multi_model (uest_seg_multi_os.py:891-950)
 plus the [NEW] class-balanced thresholding stage, as one object whose steps enqueue without host syncs:
 
-    K1 fuse_sources (+ radix pass 0 + class histogram)  ->  [all-reduce histograms]  ->  K2 select / pass 1 / pass 2
-    ->  K3 apply_thresholds (+ final class histogram)  ->  class weights
+    K1 fuse_sources (+ linear confidence histogram + class histogram)  ->  [all-reduce histograms]  ->  bracket select
+    ->  ONE pass over (label, conf): final label map, final class histogram, candidate list  ->  radix select on the
+    candidates ([all-reduce] x3)  ->  candidate patch  ->  class weights
 
 Multi-GPU: one process per GPU; target images are sharded by contiguous index range; the only collective is an
 all-reduce(SUM) of small int64 histograms, so N-GPU results are bit-identical to 1-GPU results.
@@ -93,11 +94,10 @@ class LabelGenerator:
         marginal = self._all_reduce(r.marginal) if r.marginal is not None else None
         if not self.thresholds:
             return LabelJob(r.label, r.label, None, r.conf, r.unc, None, None, class_hist, class_hist, marginal)
-        thresh, kept = ops.cb_thresholds(r.label, r.conf, self.portion, self.ds_rate, self.num_classes,
-                                         conf_hist=r.conf_hist, all_reduce=self._all_reduce if self._world() > 1 else None)
-        self.launches += 5         # radix passes 1-2 (hist) + three selects
-        final, mask, final_hist = ops.apply_thresholds(r.label, r.conf, thresh, self.ignore_label, want_mask=want_mask)
-        self.launches += 1
+        thresh, kept, final, mask, final_hist = ops.select_and_apply(
+            r.label, r.conf, self.portion, self.ds_rate, self.num_classes, self.ignore_label, conf_hist=r.conf_hist,
+            all_reduce=self._all_reduce if self._world() > 1 else None, want_final=True, want_mask=want_mask)
+        self.launches += ops.SELECT_AND_APPLY_LAUNCHES
         final_hist = self._all_reduce(final_hist)
         return LabelJob(r.label, final, mask, r.conf, r.unc, thresh, kept, class_hist, final_hist, marginal)
 
@@ -152,10 +152,10 @@ class LabelGenerator:
             freed[slot].record(compute)
         class_hist = self._all_reduce(class_hist)
         if self.thresholds:
-            thresh, kept = ops.cb_thresholds(label, conf, self.portion, self.ds_rate, K, conf_hist=conf_hist,
-                                             all_reduce=self._all_reduce if self._world() > 1 else None)
-            final, _, final_hist = ops.apply_thresholds(label, conf, thresh, self.ignore_label, want_mask=False)
-            self.launches += 6
+            thresh, kept, final, _, final_hist = ops.select_and_apply(
+                label, conf, self.portion, self.ds_rate, K, self.ignore_label, conf_hist=conf_hist,
+                all_reduce=self._all_reduce if self._world() > 1 else None, want_final=True, want_mask=False)
+            self.launches += ops.SELECT_AND_APPLY_LAUNCHES
             final_hist = self._all_reduce(final_hist)
         else:
             thresh = kept = None

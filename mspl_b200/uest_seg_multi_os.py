@@ -233,11 +233,11 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
         if pending:
             flush(pending, pending_names)
         if use_cb and kept_labels:
-            # conf_hist already holds radix pass 0 of every batch; passes 1-2 need same-sized contiguous maps
+            # conf_hist already holds the linear confidence histogram of every batch; one more pass over the kept maps
+            # settles every pixel outside its class's bracket and the few inside it are resolved from a candidate list
             label_all, conf_all = torch.cat(kept_labels), torch.cat(kept_confs)
-            thresh, _ = ops.cb_thresholds(label_all, conf_all, portion, ds_rate, num_classes, conf_hist=conf_hist)
-            final, _, _ = ops.apply_thresholds(label_all, conf_all, thresh, IGNORE_LABEL, want_mask=False,
-                                               final_hist=class_hist)
+            _, _, final, _, _ = ops.select_and_apply(label_all, conf_all, portion, ds_rate, num_classes, IGNORE_LABEL,
+                                                     conf_hist=conf_hist, want_final=True, final_hist=class_hist)
             pos = 0
             for batch_names in names:
                 save_maps(final[pos:pos + len(batch_names)], batch_names)

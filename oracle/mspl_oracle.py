@@ -319,11 +319,13 @@ def fuse_sources_lowres(mains_lr, auxs_lr, luts, out_size, policy='half', seg_cl
     return fuse_sources([u[0] for u in ups], [u[1] for u in ups], luts, policy, seg_classes, ignore)
 
 
-def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUSE_CLASSES):
+def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUSE_CLASSES, ignore=None):
     """Class-balanced (CBST/CRST-style) per-class confidence thresholds (SURVEY.md section 8 A4'').
 
     For class k: V_k = conf over pixels with label == k, keeping a pixel iff (row*W + col) % ds_rate == 0;
     j = floor(|V_k| * portion); thresh_k = 1.0 if j == 0 else the j-th largest element of V_k.
+    `ignore` (optional): that class is never selected (apply_thresholds), so its threshold is reported as +inf instead of
+    being computed; its count is still returned.
     Returns (thresh f32 (K,), n int64 (K,)) -- an exact order statistic of the given fp32 values.
     """
     label = torch.as_tensor(label)
@@ -336,7 +338,9 @@ def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUS
         v = conf[(label == k) & keep]
         count[k] = v.numel()
         j = int(v.numel() * float(portion))
-        if j > 0:
+        if ignore is not None and k == ignore:
+            thresh[k] = float('inf')
+        elif j > 0:
             thresh[k] = torch.sort(v, descending=True).values[j - 1]
     return thresh, count
 

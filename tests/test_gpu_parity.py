@@ -258,6 +258,118 @@ def test_cb_thresholds_duplicates_and_extremes(ops, dev):
         assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
 
 
+@pytest.mark.parametrize("policy,portion,ds_rate", [("all", 0.2, 1), ("half", 0.2, 1), ("prob", 0.5, 1), ("half", 0.05, 4),
+                                                    ("half", 1.0, 1), ("all", 0.0, 1), ("prob", 1e-4, 3), (2, 0.37, 2)])
+def test_select_and_apply_matches_oracle(ops, dev, policy, portion, ds_rate):
+    """Bracketed protocol (one pass + candidate list) == sort-based definition, bit for bit: thresholds of every non-ignore
+    class, the final map, the mask, both histograms; and == the generic 3-pass radix protocol."""
+    n, h, w = 3, 40, 52
+    mains, auxs = [], []
+    for i, (nm, c) in enumerate(SOURCES):
+        m, a = O.synthetic_logits(n, c, h, w, seed=140 + i)
+        mains.append(m), auxs.append(a)
+    luts = [O.LUTS[nm] for nm, _ in SOURCES]
+    r = _fuse(ops, dev, mains, auxs, luts, policy, ds_rate=ds_rate)
+    lab, conf = r.label.cpu(), r.conf.cpu()
+    th_ref, kept_ref = O.cb_thresholds(lab, conf, portion, ds_rate, ignore=4)
+    f_ref, m_ref = O.apply_thresholds(lab, conf, th_ref)
+    for hist in (None, r.conf_hist):                      # linear histogram computed stand-alone / fused into K1
+        th, kept, final, mask, fh = ops.select_and_apply(r.label, r.conf, portion, ds_rate, 5, 4, conf_hist=hist, want_mask=True)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+        assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+        assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=5))
+    assert int(r.conf_hist.abs().sum()) == 0              # consumed
+    th_radix, kept_radix = ops.cb_thresholds_radix(r.label, r.conf, portion, ds_rate)
+    th_all, kept_all = ops.cb_thresholds(r.label, r.conf, portion, ds_rate)                # every class resolved
+    assert torch.equal(th_radix, th_all) and torch.equal(kept_radix, kept_all)
+    assert torch.equal(th_all.cpu(), O.cb_thresholds(lab, conf, portion, ds_rate)[0])
+    assert torch.equal(th_all[:4].cpu(), th_ref[:4])
+
+
+def test_select_and_apply_degenerate_and_large(ops, dev):
+    """Every pixel a candidate (one shared conf value), values outside [0,1], NaN-free extremes, and a map large enough for
+    several grid-stride iterations and many staging flushes per warp."""
+    gen = torch.Generator().manual_seed(19)
+    cases = []
+    label = torch.randint(0, 5, (2, 64, 80), generator=gen).to(torch.uint8)
+    cases.append((label, torch.full((2, 64, 80), 0.7312), 0.3))                              # one value: all candidates
+    pool = torch.tensor([0.0, 1.0, 0.5, 0.5, 0.25, 1e-40, 3e-39, -0.25, 0.99999994, 0.33333334, 2.5, 1e30, -1e30, 4.8828125e-4])
+    cases.append((label, pool[torch.randint(0, pool.numel(), (2, 64, 80), generator=gen)], 0.37))
+    big_label = torch.randint(0, 5, (12, 512, 1024), generator=gen).to(torch.uint8)           # 6.3 Mpix > one grid sweep
+    big_conf = torch.rand((12, 512, 1024), generator=gen)
+    big_conf[:, ::2] = (big_conf[:, ::2] * 64).floor() / 64                                  # heavy duplicates on bin edges
+    cases.append((big_label, big_conf, 0.2))
+    cases.append((big_label, torch.full((12, 512, 1024), 0.4), 0.5))                         # 6.3 M candidates
+    for label, conf, p in cases:
+        th_ref, kept_ref = O.cb_thresholds(label, conf, p, ignore=4)
+        f_ref, m_ref = O.apply_thresholds(label, conf, th_ref)
+        th, kept, final, mask, fh = ops.select_and_apply(label.to(dev), conf.to(dev), p, 1, 5, 4, want_mask=True)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+        assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+        assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=5))
+        th_all, _ = ops.cb_thresholds(label.to(dev), conf.to(dev), p)
+        assert torch.equal(th_all.cpu(), O.cb_thresholds(label, conf, p)[0])
+
+
+def test_select_and_apply_odd_sizes(ops, dev):
+    """Pixel counts that are not multiples of 4 and unaligned views take the scalar path."""
+    gen = torch.Generator().manual_seed(23)
+    for shape in ((1, 7, 9), (3, 5, 7), (2, 33, 31)):
+        label = torch.randint(0, 5, shape, generator=gen).to(torch.uint8)
+        conf = torch.rand(shape, generator=gen)
+        th_ref, kept_ref = O.cb_thresholds(label, conf, 0.3, ignore=4)
+        f_ref, m_ref = O.apply_thresholds(label, conf, th_ref)
+        th, kept, final, mask, fh = ops.select_and_apply(label.to(dev), conf.to(dev), 0.3, 1, 5, 4, want_mask=True)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+        assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+
+
+def test_bracketed_protocol_sharded_raw_abi(ops, dev):
+    """Emulates 2 ranks on one GPU through the raw C ABI: the shards' linear histograms and each candidate pass's histograms
+    are summed (the all-reduce) before the selects; candidate lists stay per shard.  Result == unsharded == oracle."""
+    from mspl_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(29)
+    K, h, w = 5, 48, 64
+    label = torch.randint(0, K, (6, h, w), generator=gen).to(torch.uint8).to(dev)
+    conf = torch.rand((6, h, w), generator=gen).to(dev)
+    shards = [(label[:2].contiguous(), conf[:2].contiguous()), (label[2:].contiguous(), conf[2:].contiguous())]
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
+    thresh = torch.empty(K, dtype=torch.float32, device=dev)
+    bracket = torch.empty((K, 2), dtype=torch.float32, device=dev)
+    kept = torch.zeros(K, dtype=torch.int64, device=dev)
+    hist = torch.zeros((K, 2048), dtype=torch.int64, device=dev)
+    fh = torch.zeros(K, dtype=torch.int64, device=dev)
+    for lab, cf in shards:
+        _lib.check(lib.mspl_conf_hist(p(lab), p(cf), lab.numel(), h * w, K, p(hist), 1, st), "conf_hist")
+    _lib.check(lib.mspl_bracket_select(p(hist), K, 0.25, 4, p(state), p(bracket), p(thresh), p(kept), st), "bracket_select")
+    per = []
+    for lab, cf in shards:
+        final = torch.empty_like(lab)
+        cand = torch.empty(lab.numel(), dtype=torch.int32, device=dev)
+        count = torch.zeros((), dtype=torch.int64, device=dev)
+        _lib.check(lib.mspl_bracket_classify(p(lab), p(cf), p(bracket), lab.numel(), K, 4, p(final), None, p(fh), p(cand), p(count), st),
+                   "classify")
+        per.append((lab, cf, final, cand, count))
+    for ps in range(3):
+        for lab, cf, final, cand, count in per:
+            _lib.check(lib.mspl_cand_hist_pass(p(lab), p(cf), p(cand), p(count), h * w, K, ps, p(state), p(hist), 1, st), "cand_hist")
+        _lib.check(lib.mspl_cand_select(p(hist), K, ps, p(state), p(thresh), st), "cand_select")
+    for lab, cf, final, cand, count in per:
+        _lib.check(lib.mspl_cand_apply(p(lab), p(cf), p(thresh), p(cand), p(count), K, 4, p(final), None, p(fh), st), "cand_apply")
+    th_ref, kept_ref = O.cb_thresholds(label.cpu(), conf.cpu(), 0.25, ignore=4)
+    f_ref, _ = O.apply_thresholds(label.cpu(), conf.cpu(), th_ref)
+    assert torch.equal(thresh.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
+    assert torch.equal(torch.cat([x[2] for x in per]).cpu(), f_ref)
+    assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=K))
+    assert sum(int(x[4]) for x in per) < label.numel() // 100          # candidates are a tiny fraction of the pixels
+    th1, kept1, final1, _, fh1 = ops.select_and_apply(label, conf, 0.25, 1, K, 4)
+    assert torch.equal(th1, thresh) and torch.equal(final1.cpu(), f_ref) and torch.equal(fh1, fh)
+
+
 def test_thresholds_vs_oracle_conf(ops, dev):
     """End to end against the oracle's own conf: thresholds within 1e-5 relative; final labels equal except at
     near-tie pixels and pixels whose conf sits within 1e-5 relative of its class threshold."""
@@ -640,6 +752,19 @@ def test_c_abi_error_codes(dev):
                                 vp(out3.data_ptr()), None, None, vp(big.data_ptr()), big.numel(), st)
     assert rc == -3                                                          # more classes than the fused loss is built for
     assert lib.mspl_radix_select(None, 5, 0, 0.2, None, None, None, st) == -1
+    assert lib.mspl_bracket_select(None, 5, 0.2, 4, None, None, None, None, st) == -1
+    assert lib.mspl_cand_select(None, 5, 0, None, None, st) == -1
+    lab8 = torch.zeros(64, dtype=torch.uint8, device=dev)
+    cf = torch.zeros(64, device=dev)
+    br = torch.zeros(10, device=dev)
+    cand = torch.zeros(64, dtype=torch.int32, device=dev)
+    cnt = torch.zeros((), dtype=torch.int64, device=dev)
+    # thresholds-only mode (ignore_label = -1) cannot write a label map
+    assert lib.mspl_bracket_classify(vp(lab8.data_ptr()), vp(cf.data_ptr()), vp(br.data_ptr()), 64, 5, -1, vp(lab8.data_ptr()), None,
+                                     None, vp(cand.data_ptr()), vp(cnt.data_ptr()), st) == -1
+    assert lib.mspl_bracket_classify(vp(lab8.data_ptr()), vp(cf.data_ptr()), vp(br.data_ptr()), 2 ** 32, 5, 4, None, None, None,
+                                     vp(cand.data_ptr()), vp(cnt.data_ptr()), st) == -3        # 32-bit candidate indices
+    assert lib.mspl_conf_hist(vp(lab8.data_ptr()), vp(cf.data_ptr()), 64, 64, 9, vp(cnt.data_ptr()), 1, st) == -1
     torch.cuda.synchronize()
 
 

@@ -52,10 +52,14 @@ def test_two_ranks_equal_one(policy, ds_rate):
     from mspl_b200.pipeline import LabelGenerator, shard_range
     mains, auxs, luts = _inputs()
     single = LabelGenerator(luts, policy=policy, portion=0.2, ds_rate=ds_rate, ops=oracle_ops).run(mains, auxs)
-    # the torch-op radix select used by the stand-in equals the sort-based definition
+    # the torch-op bracketed select used by the stand-in equals the sort-based definition
     ref = O.fuse_sources(mains, auxs, luts, policy)
-    th_ref, kept_ref = O.cb_thresholds(ref["label"], ref["conf"], 0.2, ds_rate)
+    th_ref, kept_ref = O.cb_thresholds(ref["label"], ref["conf"], 0.2, ds_rate, ignore=4)
     assert torch.equal(single.thresh, th_ref) and torch.equal(single.kept, kept_ref)
+    f_ref, _ = O.apply_thresholds(ref["label"], ref["conf"], th_ref)
+    assert torch.equal(single.final, f_ref)
+    th_all, _ = oracle_ops.cb_thresholds(ref["label"], ref["conf"], 0.2, ds_rate)          # every class resolved
+    assert torch.equal(th_all, O.cb_thresholds(ref["label"], ref["conf"], 0.2, ds_rate)[0])
 
     world = 2
     mgr = mp.Manager()
