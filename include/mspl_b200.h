@@ -124,6 +124,11 @@ MSPL_API int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t nu
  *   mspl_fuse_sources accumulates it as `conf_hist`, or call mspl_conf_hist.            [all-reduce hist over ranks]
  *   mspl_bracket_select: per class, the bin holding the j-th largest conf -> bracket[k] = {lo, hi} (2K f32), the rank left
  *     inside the bin in `state` (mspl_radix_state_bytes, zeroed), kept_count[k] = n_k, thresh[k] = 1.0 for j == 0; zeroes hist.
+ *     final_hist (K u64, NULLable, needs ignore_label in [0,K)): += the final class counts of the pixels settled outright,
+ *     read off the histogram instead of being counted by the classify pass (pass final_hist = NULL there): class k keeps the
+ *     pixels in the bins above its bracket bin, everything else counts as ignored until mspl_cand_apply patches it.  Only
+ *     valid when the histogram was accumulated with ds_rate == 1 over exactly the pixels to be classified; `local_hist`
+ *     is this rank's own (pre-all-reduce) copy of it, or NULL when `hist` was never all-reduced.
  *     The ignore class is never selected, so its threshold is left unresolved: thresh[ignore_label] = +inf (with the vote
  *     policies all its pixels have conf == 0 and would all be candidates); ignore_label = -1 resolves every class, which
  *     mspl_bracket_classify accepts only in thresholds-only mode (final_label, ignore_mask, final_hist all NULL).
@@ -141,7 +146,8 @@ MSPL_API size_t mspl_radix_state_bytes(int num_target_classes);
 MSPL_API int mspl_conf_hist(const uint8_t* label, const float* conf, int64_t num_pixels, int64_t pixels_per_image,
                    int num_target_classes, unsigned long long* hist, int ds_rate, void* stream);
 MSPL_API int mspl_bracket_select(unsigned long long* hist, int num_target_classes, double portion, int ignore_label,
-                        void* state, float* bracket, float* thresh, unsigned long long* kept_count, void* stream);
+                        void* state, float* bracket, float* thresh, unsigned long long* kept_count,
+                        const unsigned long long* local_hist, unsigned long long* final_hist, void* stream);
 MSPL_API int mspl_bracket_classify(const uint8_t* label, const float* conf, const float* bracket, int64_t num_pixels,
                           int num_target_classes, int ignore_label, uint8_t* final_label, uint8_t* ignore_mask,
                           unsigned long long* final_hist, uint32_t* cand_index, unsigned long long* cand_count,

@@ -25,7 +25,7 @@ SIGNATURES = {
     "mspl_vote_labels": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "mspl_radix_state_bytes": (c_sz, [c_int]),
     "mspl_conf_hist": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp]),
-    "mspl_bracket_select": (c_int, [c_vp, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mspl_bracket_select": (c_int, [c_vp, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_bracket_classify": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_cand_hist_pass": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "mspl_cand_select": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),

@@ -270,9 +270,12 @@ __global__ void __launch_bounds__(256) apply_thresholds_kernel(const uint8_t* __
 // candidate radix passes and zeroes the histogram row.
 __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long* __restrict__ hist, double portion, int ignore,
                                                              RadixState* __restrict__ state, float2* __restrict__ bracket,
-                                                             float* __restrict__ thresh, unsigned long long* __restrict__ kept_count) {
+                                                             float* __restrict__ thresh, unsigned long long* __restrict__ kept_count,
+                                                             const unsigned long long* __restrict__ local_hist,
+                                                             unsigned long long* __restrict__ final_hist) {
     __shared__ unsigned long long s_h[MSPL_RADIX_BINS];
     __shared__ unsigned long long s_warp[8];
+    __shared__ int s_bin;
     const int k = blockIdx.x;
     unsigned long long* h = hist + (size_t)k * MSPL_RADIX_BINS;
     constexpr int per = MSPL_RADIX_BINS / 256;
@@ -280,26 +283,36 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
         s_h[i] = h[i];
         h[i] = 0;
     }
+    if (threadIdx.x == 0) s_bin = MSPL_RADIX_BINS;      // "no bin": nothing of this class is kept outright
     __syncthreads();
     unsigned long long above, mine, total;
     suffix_counts(s_h, per, s_warp, above, mine, total);
     unsigned long long j = (unsigned long long)((double)total * portion);       // floor(n_k * p), as int(n*p)
     if (j > total) j = total;
-    if (j == 0 || k == ignore) {
+    if (k == ignore) {
+        // never selected: threshold left unresolved (+inf) -- with the vote policies all its pixels share conf == 0 and would
+        // all be candidates
         if (threadIdx.x == 0) {
             RadixState st;
             st.rank = 0; st.count = total; st.prefix = 0; st.done = 1;
             state[k] = st;
-            // j == 0: keep iff conf >= 1.0, no candidates.  The ignore class is never selected: its threshold stays unresolved
-            // (+inf) -- with the vote policies all of its pixels share conf == 0 and would all be candidates.
-            const float t = k == ignore ? INFINITY : 1.0f;
-            thresh[k] = t;
-            bracket[k] = make_float2(t, t);
+            thresh[k] = INFINITY;
+            bracket[k] = make_float2(INFINITY, INFINITY);
             if (kept_count) kept_count[k] = total;
         }
-        return;
-    }
-    if (above < j && j <= above + mine) {               // exactly one thread
+    } else if (j == 0) {
+        // threshold 1.0, final already: the pixels that reach it sit in the top bin, which becomes the bracket so that the
+        // candidate patch keeps exactly those with conf >= 1.0
+        if (threadIdx.x == 0) {
+            RadixState st;
+            st.rank = 0; st.count = total; st.prefix = 0; st.done = 1;
+            state[k] = st;
+            thresh[k] = 1.0f;
+            bracket[k] = make_float2((float)(MSPL_RADIX_BINS - 1) * (1.0f / MSPL_RADIX_BINS), INFINITY);
+            if (kept_count) kept_count[k] = total;
+            s_bin = MSPL_RADIX_BINS - 1;
+        }
+    } else if (above < j && j <= above + mine) {        // exactly one thread
         unsigned long long acc = above;
         int b = threadIdx.x * per + per - 1;
         for (; b > threadIdx.x * per; --b) {
@@ -312,19 +325,41 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
         bracket[k] = make_float2(b == 0 ? -INFINITY : (float)b * (1.0f / MSPL_RADIX_BINS),
                                  b == MSPL_RADIX_BINS - 1 ? INFINITY : (float)(b + 1) * (1.0f / MSPL_RADIX_BINS));
         if (kept_count) kept_count[k] = total;
+        s_bin = b;
+    }
+    if (!final_hist) return;
+    // final class counts straight from the histogram of THIS rank's pixels (valid when it was accumulated with ds_rate 1 over
+    // exactly the pixels the classify pass will see): everything above the bracket bin keeps its label, the rest of the
+    // class is ignored until cand_apply patches the candidates that reach the threshold
+    __syncthreads();
+    const int b = s_bin;
+    const unsigned long long* lh = local_hist ? local_hist + (size_t)k * MSPL_RADIX_BINS : nullptr;
+    unsigned long long n_all = 0, n_keep = 0;
+    for (int i = threadIdx.x; i < MSPL_RADIX_BINS; i += 256) {
+        const unsigned long long c = lh ? lh[i] : s_h[i];
+        n_all += c;
+        if (i > b) n_keep += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_all += __shfl_xor_sync(0xffffffffu, n_all, o);
+        n_keep += __shfl_xor_sync(0xffffffffu, n_keep, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_keep) atomicAdd(final_hist + k, n_keep);
+        if (ignore >= 0 && n_all - n_keep) atomicAdd(final_hist + ignore, n_all - n_keep);
     }
 }
 
 constexpr int kCandBuf = 768;                                  // per-warp staging entries
-constexpr int kCandFlushAt = kCandBuf - 32 * 4 * kUnroll;      // a warp adds at most 32 lanes x VEC x kUnroll per iteration
-static_assert(kCandFlushAt > 0, "per-warp candidate staging must hold one iteration's worst case");
 
 // The one full pass of the bracketed protocol: settle every pixel outside its class's bracket, stage the candidates.
 // Candidates get the ignore label for now (and count as ignored); cand_apply patches the ones that reach the threshold.
 // Appends are staged per warp in shared memory and flushed with one global atomic per ~kCandFlushAt entries, so the list
 // costs nothing when candidates are rare and stays correct (just slower) when every pixel is one.
+// Generic form (any alignment, VEC = 1 or 4, counts the final classes itself); see bracket_classify_words_kernel below.
 template <int VEC>
-__global__ void __launch_bounds__(256) bracket_classify_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+__global__ void __launch_bounds__(256, 4) bracket_classify_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
                                                                const float2* __restrict__ bracket, int64_t npix, int K, int ignore,
                                                                uint8_t* __restrict__ final_label, uint8_t* __restrict__ ignore_mask,
                                                                unsigned long long* __restrict__ final_hist,
@@ -334,6 +369,8 @@ __global__ void __launch_bounds__(256) bracket_classify_kernel(const uint8_t* __
     __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
     __shared__ uint32_t s_buf[8][kCandBuf];
     __shared__ uint32_t s_fill[8];
+    constexpr int kCandFlushAt = kCandBuf - 32 * VEC * kUnroll;    // a warp adds at most 32 lanes x VEC x kUnroll per iteration
+    static_assert(kCandFlushAt > 0, "per-warp candidate staging must hold one iteration's worst case");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x <= MSPL_MAX_CLASSES) {
         const int k = threadIdx.x;
@@ -364,27 +401,35 @@ __global__ void __launch_bounds__(256) bracket_classify_kernel(const uint8_t* __
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t g = g0 + u * 256;
             if (g < n_groups) load_label_conf<VEC>(label, conf, g * VEC, l[u], c[u]);
+            else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) l[u][v] = 255;        // class "never kept, never a candidate"
+            }
         }
+        uint32_t cmask = 0;             // bit u*VEC+v: pixel (u, v) lies inside its class's bracket
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t g = g0 + u * 256;
-            if (g < n_groups) {
-                uint8_t f[VEC], mk[VEC];
+            uint8_t f[VEC], mk[VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float2 br = s_br[min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES)];
-                    const bool keep = c[u][v] >= br.y;
-                    if (c[u][v] >= br.x && !keep) {         // inside the bracket: candidate
-                        const uint32_t slot = atomicAdd(&s_fill[warp], 1u);
-                        s_buf[warp][slot] = (uint32_t)(g * VEC + v);
-                    }
-                    f[v] = keep ? l[u][v] : (uint8_t)ignore;
-                    mk[v] = keep ? 0 : 1;
-                    if (final_hist) packed += 1ull << (8 * f[v]);
-                }
+            for (int v = 0; v < VEC; ++v) {
+                const float2 br = s_br[min((uint32_t)l[u][v], (uint32_t)MSPL_MAX_CLASSES)];
+                const bool keep = c[u][v] >= br.y;
+                cmask |= (uint32_t)(c[u][v] >= br.x && !keep) << (u * VEC + v);
+                f[v] = keep ? l[u][v] : (uint8_t)ignore;
+                mk[v] = keep ? 0 : 1;
+                if (final_hist && g < n_groups) packed += 1ull << (8 * f[v]);
+            }
+            if (g < n_groups) {
                 if (final_label) store_bytes<VEC>(final_label, g * VEC, f);
                 if (ignore_mask) store_bytes<VEC>(ignore_mask, g * VEC, mk);
             }
+        }
+        while (cmask) {                 // rare: one divergent region per iteration instead of one per pixel
+            const int bit = __ffs(cmask) - 1;
+            cmask &= cmask - 1;
+            const uint32_t slot = atomicAdd(&s_fill[warp], 1u);
+            s_buf[warp][slot] = (uint32_t)((g0 + (bit / VEC) * 256) * VEC + bit % VEC);
         }
         if ((pending += VEC * kUnroll) > 255 - VEC * kUnroll) {
 #pragma unroll
@@ -400,6 +445,117 @@ __global__ void __launch_bounds__(256) bracket_classify_kernel(const uint8_t* __
     const uint32_t fill = s_fill[warp];
     if (fill) flush(fill);
     if (final_hist) {
+#pragma unroll
+        for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
+            cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+            const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[k]);
+            if (lane == 0 && w) atomicAdd(&s_cls[k], w);
+        }
+        __syncthreads();
+        if (threadIdx.x < K && s_cls[threadIdx.x]) atomicAdd(final_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+    }
+}
+
+// Production form of the classify pass for 4-aligned maps: labels stay packed four to a 32-bit word, the per-class bracket
+// comes from a 256-entry shared table indexed by the label byte (no clamping), the final word is one bitwise select, and the
+// class counts are left to bracket_select / cand_apply (COUNT = false) -- ~3x fewer integer instructions per pixel than the
+// generic kernel above, which matters because these passes are bound by the half-rate integer pipe, not by HBM.
+// Pixels of labels outside [0,K) are written as ignored.
+template <int UNR, bool COUNT>
+__global__ void __launch_bounds__(256, 4) bracket_classify_words_kernel(const uint32_t* __restrict__ label4,
+                                                                      const float4* __restrict__ conf4,
+                                                                      const float2* __restrict__ bracket, uint32_t n_groups, int K,
+                                                                      int ignore, uint32_t* __restrict__ final4,
+                                                                      uint32_t* __restrict__ mask4,
+                                                                      unsigned long long* __restrict__ final_hist,
+                                                                      uint32_t* __restrict__ cand_index,
+                                                                      unsigned long long* __restrict__ cand_count) {
+    constexpr int kCandFlushAt = kCandBuf - 32 * 4 * UNR;
+    static_assert(kCandFlushAt > 0, "per-warp candidate staging must hold one iteration's worst case");
+    __shared__ float2 s_tab[256];
+    __shared__ uint32_t s_cls[MSPL_MAX_CLASSES];
+    __shared__ uint32_t s_buf[8][kCandBuf];
+    __shared__ uint32_t s_fill[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const int k = threadIdx.x;
+        s_tab[k] = (k < K && k != ignore) ? bracket[k] : make_float2(INFINITY, INFINITY);
+        if (k < MSPL_MAX_CLASSES) s_cls[k] = 0;
+        if (k < 8) s_fill[k] = 0;
+    }
+    __syncthreads();
+    const uint32_t ign4 = (uint32_t)(ignore & 0xff) * 0x01010101u;
+    uint32_t cnt[MSPL_MAX_CLASSES] = {};
+    unsigned long long packed = 0;
+    int pending = 0;
+    auto flush = [&](uint32_t fill) {       // whole warp; fill is warp-uniform
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < fill; i += 32) cand_index[base + i] = s_buf[warp][i];
+        __syncwarp();
+        if (lane == 0) s_fill[warp] = 0;
+        __syncwarp();
+    };
+    // group counts fit 32 bits (num_pixels < 2^32); the loop index runs in 64 bits only where it could wrap
+    for (uint64_t w0 = (uint64_t)blockIdx.x * (256 * UNR) + warp * 32; w0 < n_groups; w0 += (uint64_t)gridDim.x * 256 * UNR) {
+        const uint32_t g0 = (uint32_t)w0 + lane;
+        uint32_t lw[UNR];
+        float4 cv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const uint32_t g = g0 + u * 256;
+            if (g < n_groups) {
+                lw[u] = __ldcs(label4 + g);
+                cv[u] = __ldcs(conf4 + g);
+            } else {
+                lw[u] = 0xffffffffu;        // table entry 255: never kept, never a candidate
+                cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t cmask = 0;             // bit 4u+v: pixel (u, v) lies inside its class's bracket
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const uint32_t g = g0 + u * 256;
+            const float c[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
+            uint32_t m = 0;             // 0xff in the bytes that keep their label
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float2 br = s_tab[__byte_perm(lw[u], 0, 0x4440 + v)];
+                const bool keep = c[v] >= br.y;
+                m |= keep ? (0xffu << (8 * v)) : 0u;
+                cmask |= (c[v] >= br.x && !keep) ? (1u << (4 * u + v)) : 0u;
+            }
+            const uint32_t fw = (lw[u] & m) | (ign4 & ~m);
+            if (g < n_groups) {
+                if (final4) __stcs(final4 + g, fw);
+                if (mask4) __stcs(mask4 + g, ~m & 0x01010101u);
+                if (COUNT) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) packed += 1ull << (8 * ((fw >> (8 * v)) & 7u));
+                }
+            }
+        }
+        while (cmask) {                 // rare: one divergent region per iteration instead of one per pixel
+            const int bit = __ffs(cmask) - 1;
+            cmask &= cmask - 1;
+            const uint32_t slot = atomicAdd(&s_fill[warp], 1u);
+            s_buf[warp][slot] = (g0 + (bit >> 2) * 256) * 4 + (bit & 3);
+        }
+        if (COUNT && (pending += 4 * UNR) > 255 - 4 * UNR) {
+#pragma unroll
+            for (int k = 0; k < MSPL_MAX_CLASSES; ++k) cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
+            packed = 0;
+            pending = 0;
+        }
+        __syncwarp();
+        const uint32_t fill = s_fill[warp];
+        if (fill > (uint32_t)kCandFlushAt) flush(fill);
+    }
+    __syncwarp();
+    const uint32_t fill = s_fill[warp];
+    if (fill) flush(fill);
+    if (COUNT) {
 #pragma unroll
         for (int k = 0; k < MSPL_MAX_CLASSES; ++k) {
             cnt[k] += (uint32_t)(packed >> (8 * k)) & 0xffu;
@@ -580,13 +736,18 @@ extern "C" int mspl_conf_hist(const uint8_t* label, const float* conf, int64_t n
 }
 
 extern "C" int mspl_bracket_select(unsigned long long* hist, int num_target_classes, double portion, int ignore_label, void* state,
-                                   float* bracket, float* thresh, unsigned long long* kept_count, void* stream) {
+                                   float* bracket, float* thresh, unsigned long long* kept_count,
+                                   const unsigned long long* local_hist, unsigned long long* final_hist, void* stream) {
     const int K = num_target_classes;
     if (!hist || !state || !bracket || !thresh || K < 1 || K > MSPL_MAX_CLASSES || !(portion >= 0.0)) return MSPL_ERR_BAD_ARG;
     if (ignore_label < -1 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
-    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(bracket, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
+    if (final_hist && (ignore_label < 0 || ignore_label >= K)) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(bracket, 8) || !aligned_to(thresh, 4) ||
+        !aligned_to(local_hist, 8) || !aligned_to(final_hist, 8))
+        return MSPL_ERR_ALIGN;
     bracket_select_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, portion, ignore_label, static_cast<RadixState*>(state),
-                                                                            reinterpret_cast<float2*>(bracket), thresh, kept_count);
+                                                                            reinterpret_cast<float2*>(bracket), thresh, kept_count,
+                                                                            local_hist, final_hist);
     return launch_status();
 }
 
@@ -607,17 +768,23 @@ extern "C" int mspl_bracket_classify(const uint8_t* label, const float* conf, co
         return aligned_to(label, a) && aligned_to(conf, 4 * a) && (!final_label || aligned_to(final_label, a)) &&
                (!ignore_mask || aligned_to(ignore_mask, a));
     };
-    const int vec = (num_pixels % 4 == 0 && ok(4)) ? 4 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2* br = reinterpret_cast<const float2*>(bracket);
-    if (vec == 4) {
-        const int64_t grid = resident_grid(bracket_classify_kernel<4>, num_pixels / vec / kUnroll + 1, 256, 0);
-        bracket_classify_kernel<4><<<(unsigned)grid, 256, 0, st>>>(label, conf, br, num_pixels, K, ignore_label, final_label,
-                                                                  ignore_mask, final_hist, cand_index, cand_count);
+    if (num_pixels % 4 == 0 && ok(4)) {
+        constexpr int kU = 4;
+        const uint32_t n_groups = (uint32_t)(num_pixels / 4);
+        auto launch = [&](auto kern) {
+            const int64_t grid = resident_grid(kern, n_groups / kU + 1, 256, 0);
+            kern<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(label), reinterpret_cast<const float4*>(conf), br,
+                                                 n_groups, K, ignore_label, reinterpret_cast<uint32_t*>(final_label),
+                                                 reinterpret_cast<uint32_t*>(ignore_mask), final_hist, cand_index, cand_count);
+        };
+        if (final_hist) launch(bracket_classify_words_kernel<kU, true>);
+        else launch(bracket_classify_words_kernel<kU, false>);
     } else {
-        const int64_t grid = resident_grid(bracket_classify_kernel<1>, num_pixels / vec / kUnroll + 1, 256, 0);
-        bracket_classify_kernel<1><<<(unsigned)grid, 256, 0, st>>>(label, conf, br, num_pixels, K, ignore_label, final_label,
-                                                                  ignore_mask, final_hist, cand_index, cand_count);
+        const int64_t grid = resident_grid(bracket_classify_kernel<1>, num_pixels / kUnroll + 1, 256, 0);
+        bracket_classify_kernel<1><<<(unsigned)grid, 256, 0, st>>>(label, conf, br, num_pixels, K, ignore_label, final_label, ignore_mask,
+                                                                  final_hist, cand_index, cand_count);
     }
     return launch_status();
 }

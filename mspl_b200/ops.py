@@ -275,13 +275,19 @@ def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_
         st = _stream(dev)
         if conf_hist is None:
             _lib.check(lib.mspl_conf_hist(_ptr(label), _ptr(conf), npix, hw, K, _ptr(hist), int(ds_rate), st), "mspl_conf_hist")
+        # with ds_rate 1 the histogram covers every pixel, so the final class counts can be read off it (this rank's copy of
+        # it, taken before the all-reduce) instead of being counted per pixel by the classify pass
+        from_hist = outputs and int(ds_rate) == 1
+        local_hist = None
         if all_reduce is not None:
+            if from_hist:
+                local_hist = hist.clone()
             all_reduce(hist)
         _lib.check(lib.mspl_bracket_select(_ptr(hist), K, float(portion), ign, _ptr(state), _ptr(bracket), _ptr(thresh), _ptr(kept),
-                                           st), "mspl_bracket_select")
+                                           _ptr(local_hist), _ptr(final_hist if from_hist else None), st), "mspl_bracket_select")
         _lib.check(lib.mspl_bracket_classify(_ptr(label), _ptr(conf), _ptr(bracket), npix, K, ign, _ptr(final), _ptr(mask),
-                                             _ptr(final_hist if outputs else None), _ptr(cand_index), _ptr(cand_count), st),
-                   "mspl_bracket_classify")
+                                             _ptr(final_hist if outputs and not from_hist else None), _ptr(cand_index),
+                                             _ptr(cand_count), st), "mspl_bracket_classify")
         for p in range(RADIX_PASSES):
             _lib.check(lib.mspl_cand_hist_pass(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, p, _ptr(state),
                                                _ptr(hist), int(ds_rate), st), "mspl_cand_hist_pass")

@@ -279,6 +279,10 @@ def test_select_and_apply_matches_oracle(ops, dev, policy, portion, ds_rate):
         assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
         assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=5))
     assert int(r.conf_hist.abs().sum()) == 0              # consumed
+    # a (trivial) all-reduce hook switches the final counts to this rank's saved copy of the histogram: same results
+    th, kept, final, mask, fh = ops.select_and_apply(r.label, r.conf, portion, ds_rate, 5, 4, all_reduce=lambda t: t, want_mask=True)
+    assert torch.equal(th.cpu(), th_ref) and torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+    assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=5))
     th_radix, kept_radix = ops.cb_thresholds_radix(r.label, r.conf, portion, ds_rate)
     th_all, kept_all = ops.cb_thresholds(r.label, r.conf, portion, ds_rate)                # every class resolved
     assert torch.equal(th_radix, th_all) and torch.equal(kept_radix, kept_all)
@@ -325,8 +329,9 @@ def test_select_and_apply_odd_sizes(ops, dev):
 
 
 def test_bracketed_protocol_sharded_raw_abi(ops, dev):
-    """Emulates 2 ranks on one GPU through the raw C ABI: the shards' linear histograms and each candidate pass's histograms
-    are summed (the all-reduce) before the selects; candidate lists stay per shard.  Result == unsharded == oracle."""
+    """Emulates 2 ranks on one GPU through the raw C ABI: every rank keeps its own state / candidate list / final histogram,
+    the linear histogram and each candidate pass's histogram are summed over the ranks (the all-reduce) before each rank's
+    select, and the final class counts are read off each rank's local histogram.  Result == unsharded == oracle."""
     from mspl_b200 import _lib
     import ctypes
     lib = _lib.load()
@@ -334,40 +339,61 @@ def test_bracketed_protocol_sharded_raw_abi(ops, dev):
     K, h, w = 5, 48, 64
     label = torch.randint(0, K, (6, h, w), generator=gen).to(torch.uint8).to(dev)
     conf = torch.rand((6, h, w), generator=gen).to(dev)
-    shards = [(label[:2].contiguous(), conf[:2].contiguous()), (label[2:].contiguous(), conf[2:].contiguous())]
+    conf[0, :4] = 1.0                                          # some pixels exactly at the "threshold 1.0" of tiny classes
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    p = lambda t: ctypes.c_void_p(t.data_ptr())
-    state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
-    thresh = torch.empty(K, dtype=torch.float32, device=dev)
-    bracket = torch.empty((K, 2), dtype=torch.float32, device=dev)
-    kept = torch.zeros(K, dtype=torch.int64, device=dev)
-    hist = torch.zeros((K, 2048), dtype=torch.int64, device=dev)
-    fh = torch.zeros(K, dtype=torch.int64, device=dev)
-    for lab, cf in shards:
-        _lib.check(lib.mspl_conf_hist(p(lab), p(cf), lab.numel(), h * w, K, p(hist), 1, st), "conf_hist")
-    _lib.check(lib.mspl_bracket_select(p(hist), K, 0.25, 4, p(state), p(bracket), p(thresh), p(kept), st), "bracket_select")
-    per = []
-    for lab, cf in shards:
-        final = torch.empty_like(lab)
-        cand = torch.empty(lab.numel(), dtype=torch.int32, device=dev)
-        count = torch.zeros((), dtype=torch.int64, device=dev)
-        _lib.check(lib.mspl_bracket_classify(p(lab), p(cf), p(bracket), lab.numel(), K, 4, p(final), None, p(fh), p(cand), p(count), st),
-                   "classify")
-        per.append((lab, cf, final, cand, count))
-    for ps in range(3):
-        for lab, cf, final, cand, count in per:
-            _lib.check(lib.mspl_cand_hist_pass(p(lab), p(cf), p(cand), p(count), h * w, K, ps, p(state), p(hist), 1, st), "cand_hist")
-        _lib.check(lib.mspl_cand_select(p(hist), K, ps, p(state), p(thresh), st), "cand_select")
-    for lab, cf, final, cand, count in per:
-        _lib.check(lib.mspl_cand_apply(p(lab), p(cf), p(thresh), p(cand), p(count), K, 4, p(final), None, p(fh), st), "cand_apply")
-    th_ref, kept_ref = O.cb_thresholds(label.cpu(), conf.cpu(), 0.25, ignore=4)
-    f_ref, _ = O.apply_thresholds(label.cpu(), conf.cpu(), th_ref)
-    assert torch.equal(thresh.cpu(), th_ref) and torch.equal(kept.cpu(), kept_ref)
-    assert torch.equal(torch.cat([x[2] for x in per]).cpu(), f_ref)
-    assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=K))
-    assert sum(int(x[4]) for x in per) < label.numel() // 100          # candidates are a tiny fraction of the pixels
-    th1, kept1, final1, _, fh1 = ops.select_and_apply(label, conf, 0.25, 1, K, 4)
-    assert torch.equal(th1, thresh) and torch.equal(final1.cpu(), f_ref) and torch.equal(fh1, fh)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    class Rank:
+        def __init__(self, lab, cf):
+            self.lab, self.cf = lab.contiguous(), cf.contiguous()
+            self.state = torch.zeros(lib.mspl_radix_state_bytes(K), dtype=torch.uint8, device=dev)
+            self.thresh = torch.empty(K, dtype=torch.float32, device=dev)
+            self.bracket = torch.empty((K, 2), dtype=torch.float32, device=dev)
+            self.kept = torch.zeros(K, dtype=torch.int64, device=dev)
+            self.hist = torch.zeros((K, 2048), dtype=torch.int64, device=dev)
+            self.fh = torch.zeros(K, dtype=torch.int64, device=dev)
+            self.final = torch.empty_like(self.lab)
+            self.cand = torch.empty(self.lab.numel(), dtype=torch.int32, device=dev)
+            self.count = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def all_reduce(ranks):
+        total = sum(r.hist for r in ranks)
+        for r in ranks:
+            r.hist.copy_(total)
+
+    for portion in (0.25, 1e-5):                               # 1e-5: every class has j == 0 -> threshold 1.0
+        ranks = [Rank(label[:2], conf[:2]), Rank(label[2:], conf[2:])]
+        for r in ranks:
+            _lib.check(lib.mspl_conf_hist(p(r.lab), p(r.cf), r.lab.numel(), h * w, K, p(r.hist), 1, st), "conf_hist")
+            r.local = r.hist.clone()
+        all_reduce(ranks)
+        for r in ranks:
+            _lib.check(lib.mspl_bracket_select(p(r.hist), K, portion, 4, p(r.state), p(r.bracket), p(r.thresh), p(r.kept), p(r.local),
+                                               p(r.fh), st), "bracket_select")
+            _lib.check(lib.mspl_bracket_classify(p(r.lab), p(r.cf), p(r.bracket), r.lab.numel(), K, 4, p(r.final), None, None,
+                                                 p(r.cand), p(r.count), st), "classify")
+        for ps in range(3):
+            for r in ranks:
+                _lib.check(lib.mspl_cand_hist_pass(p(r.lab), p(r.cf), p(r.cand), p(r.count), h * w, K, ps, p(r.state), p(r.hist), 1, st),
+                           "cand_hist")
+            all_reduce(ranks)
+            for r in ranks:
+                _lib.check(lib.mspl_cand_select(p(r.hist), K, ps, p(r.state), p(r.thresh), st), "cand_select")
+        for r in ranks:
+            _lib.check(lib.mspl_cand_apply(p(r.lab), p(r.cf), p(r.thresh), p(r.cand), p(r.count), K, 4, p(r.final), None, p(r.fh), st),
+                       "cand_apply")
+        th_ref, kept_ref = O.cb_thresholds(label.cpu(), conf.cpu(), portion, ignore=4)
+        f_ref, _ = O.apply_thresholds(label.cpu(), conf.cpu(), th_ref)
+        for r in ranks:
+            assert torch.equal(r.thresh.cpu(), th_ref) and torch.equal(r.kept.cpu(), kept_ref)
+            assert torch.equal(r.fh, torch.bincount(r.final.reshape(-1).long(), minlength=K))       # per-rank counts are local
+        assert torch.equal(torch.cat([r.final for r in ranks]).cpu(), f_ref)
+        assert torch.equal(sum(r.fh for r in ranks).cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=K))
+        if portion == 0.25:
+            assert sum(int(r.count) for r in ranks) < label.numel() // 100      # candidates are a tiny fraction of the pixels
+        th1, kept1, final1, _, fh1 = ops.select_and_apply(label, conf, portion, 1, K, 4)
+        assert torch.equal(th1, ranks[0].thresh) and torch.equal(final1.cpu(), f_ref)
+        assert torch.equal(fh1, sum(r.fh for r in ranks))
 
 
 def test_thresholds_vs_oracle_conf(ops, dev):
@@ -752,7 +778,7 @@ def test_c_abi_error_codes(dev):
                                 vp(out3.data_ptr()), None, None, vp(big.data_ptr()), big.numel(), st)
     assert rc == -3                                                          # more classes than the fused loss is built for
     assert lib.mspl_radix_select(None, 5, 0, 0.2, None, None, None, st) == -1
-    assert lib.mspl_bracket_select(None, 5, 0.2, 4, None, None, None, None, st) == -1
+    assert lib.mspl_bracket_select(None, 5, 0.2, 4, None, None, None, None, None, None, st) == -1
     assert lib.mspl_cand_select(None, 5, 0, None, None, st) == -1
     lab8 = torch.zeros(64, dtype=torch.uint8, device=dev)
     cf = torch.zeros(64, device=dev)
