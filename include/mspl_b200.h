@@ -189,6 +189,17 @@ MSPL_API int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logit
                        int64_t pixels_per_image, float alpha, double norm_pixels, float grad_scale,
                        float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* K4-lowres (next-row component): the same loss on the tensors ESPDNetUE hands to its closing
+ * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) calls (model/segmentation/espdnet_ue.py:301-302):
+ * main_lowres (num_images, K, main_h, main_w), aux_lowres (num_images, K, aux_h, aux_w), target (num_images, out_h, out_w).
+ * The interpolation (ATen's upsample_bilinear2d arithmetic) and its transpose run inside the kernel; d_main_lowres /
+ * d_aux_lowres receive the gradients w.r.t. the PRE-upsample tensors (both NULL = forward only).  Upsampling only
+ * (source sizes <= output size); MSPL_ERR_UNSUPPORTED when one output row of gradients does not fit in shared memory. */
+MSPL_API int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* aux_lowres, const int64_t* target,
+                              const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
+                              int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels,
+                              float grad_scale, float* out3, float* d_main_lowres, float* d_aux_lowres,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* In-place x *= *scale unless *scale == 1 (device scalar); lets autograd apply an upstream gradient
  * without a host sync. */
 MSPL_API int mspl_scale_inplace(float* x, int64_t count, const float* scale, void* stream);

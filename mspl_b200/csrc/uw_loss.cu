@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "pixel_math.cuh"
+#include "bilinear.cuh"
 
 namespace mspl {
 
@@ -26,9 +27,9 @@ struct LossWorkspace {            // caller-zeroed once; every launch leaves `ti
 
 // Deterministic two-value reduction: per-thread doubles -> warp shuffle -> block -> per-block slot; the last block
 // to finish adds the slots in index order and writes the means.  No floating-point atomics anywhere.
-template <int NOUT>
+template <int NOUT, int NT = kLossThreads>
 MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv_n, float alpha, float* out) {
-    __shared__ double s_part[kLossThreads / 32][2];
+    __shared__ double s_part[NT / 32][2];
     __shared__ bool s_last;
     s0 = warp_sum(s0);
     s1 = warp_sum(s1);
@@ -36,7 +37,7 @@ MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
-        for (int w = 0; w < kLossThreads / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+        for (int w = 0; w < NT / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
         ws->partial[blockIdx.x][0] = a;
         ws->partial[blockIdx.x][1] = b;
         __threadfence();
@@ -46,7 +47,7 @@ MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv
     if (!s_last) return;
     __threadfence();
     double a = 0, b = 0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kLossThreads) {   // fixed assignment -> fixed order
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += NT) {   // fixed assignment -> fixed order
         a += __ldcg(&ws->partial[i][0]);
         b += __ldcg(&ws->partial[i][1]);
     }
@@ -57,7 +58,7 @@ MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv
     __syncthreads();
     if (threadIdx.x == 0) {
         a = b = 0;
-        for (int w = 0; w < kLossThreads / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
+        for (int w = 0; w < NT / 32; ++w) { a += s_part[w][0]; b += s_part[w][1]; }
         const double ce_mean = a * inv_n, kld_mean = b * inv_n;
         if (NOUT == 3) {
             out[0] = (float)((double)alpha * ce_mean + kld_mean);
@@ -67,6 +68,56 @@ MSPL_DEVINL void finish_loss(double s0, double s1, LossWorkspace* ws, double inv
             out[0] = (float)ce_mean;
         }
         ws->ticket = 0;
+    }
+}
+
+// One pixel of K4 (closed forms in the file header): l = w_t ce e^{-D}, D = KL(softmax m || softmax a), and for BWD the
+// gradients of (gscale/N) * (alpha * sum l + sum D) w.r.t. the K main and aux logits.
+template <int K, bool BWD>
+MSPL_DEVINL void uw_ce_pixel(const float (&m)[K], const float (&a)[K], long long t, const float* s_w, float alpha, float gscale,
+                             float inv_nf, float& l, float& D, float (&gm)[K], float (&ga)[K]) {
+    float z[K], Mm = -INFINITY, Ma = -INFINITY, Mz = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        z[k] = fmaf(0.5f, a[k], m[k]);
+        Mm = fmaxf(Mm, m[k]); Ma = fmaxf(Ma, a[k]); Mz = fmaxf(Mz, z[k]);
+    }
+    float em[K], ea[K], ez[K], Sm = 0.f, Sa = 0.f, Sz = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        em[k] = exp_neg(m[k] - Mm); ea[k] = exp_neg(a[k] - Ma); ez[k] = exp_neg(z[k] - Mz);
+        Sm += em[k]; Sa += ea[k]; Sz += ez[k];
+    }
+    const float rSm = rcp_fast(Sm), rSa = rcp_fast(Sa), rSz = rcp_fast(Sz);
+    const float lRatio = log_fast(Sm * rSa), lSz = log_fast(Sz);     // log Sm - log Sa, log Sz
+    float dl[K];                             // dl_k = log p1_k - log p2_k
+    D = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        dl[k] = ((m[k] - Mm) - (a[k] - Ma)) - lRatio;
+        D = fmaf(em[k] * rSm, dl[k], D);
+    }
+    const int ti = (int)t;
+    const bool valid = t >= 0 && t < K;
+    float wt = 0.f, zt = Mz;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        wt = (valid && ti == k) ? s_w[k] : wt;
+        zt = (valid && ti == k) ? z[k] : zt;
+    }
+    const float ce = wt * (lSz - (zt - Mz));
+    const float eD = exp_neg(-D);
+    l = ce * eD;
+    if (BWD) {
+        const float coef = gscale * alpha * inv_nf * eD * wt;
+        const float gD = gscale * inv_nf * (1.0f - alpha * l);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float p1 = em[k] * rSm, p2 = ea[k] * rSa, q = ez[k] * rSz;
+            const float dz = coef * (q - ((valid && ti == k) ? 1.0f : 0.0f));
+            gm[k] = fmaf(gD, p1 * (dl[k] - D), dz);
+            ga[k] = fmaf(gD, p2 - p1, 0.5f * dz);
+        }
     }
 }
 
@@ -107,49 +158,15 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
         float ce_sum = 0.f, d_sum = 0.f;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            float z[K], Mm = -INFINITY, Ma = -INFINITY, Mz = -INFINITY;
+            float mp[K], ap[K], gmp[K], gap[K], l, D;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                z[k] = fmaf(0.5f, a[k][p], m[k][p]);
-                Mm = fmaxf(Mm, m[k][p]); Ma = fmaxf(Ma, a[k][p]); Mz = fmaxf(Mz, z[k]);
-            }
-            float em[K], ea[K], ez[K], Sm = 0.f, Sa = 0.f, Sz = 0.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                em[k] = exp_neg(m[k][p] - Mm); ea[k] = exp_neg(a[k][p] - Ma); ez[k] = exp_neg(z[k] - Mz);
-                Sm += em[k]; Sa += ea[k]; Sz += ez[k];
-            }
-            const float rSm = rcp_fast(Sm), rSa = rcp_fast(Sa), rSz = rcp_fast(Sz);
-            const float lRatio = log_fast(Sm * rSa), lSz = log_fast(Sz);     // log Sm - log Sa, log Sz
-            float dl[K], D = 0.f;                    // dl_k = log p1_k - log p2_k
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                dl[k] = ((m[k][p] - Mm) - (a[k][p] - Ma)) - lRatio;
-                D = fmaf(em[k] * rSm, dl[k], D);
-            }
-            const int ti = (int)t[p];
-            const bool valid = t[p] >= 0 && t[p] < K;
-            float wt = 0.f, zt = Mz;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                wt = (valid && ti == k) ? s_w[k] : wt;
-                zt = (valid && ti == k) ? z[k] : zt;
-            }
-            const float ce = wt * (lSz - (zt - Mz));
-            const float eD = exp_neg(-D);
-            const float l = ce * eD;
+            for (int k = 0; k < K; ++k) { mp[k] = m[k][p]; ap[k] = a[k][p]; }
+            uw_ce_pixel<K, BWD>(mp, ap, t[p], s_w, alpha, gscale, inv_nf, l, D, gmp, gap);
             ce_sum += l;
             d_sum += D;
             if (BWD) {
-                const float coef = gscale * alpha * inv_nf * eD * wt;
-                const float gD = gscale * inv_nf * (1.0f - alpha * l);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float p1 = em[k] * rSm, p2 = ea[k] * rSa, q = ez[k] * rSz;
-                    const float dz = coef * (q - ((valid && ti == k) ? 1.0f : 0.0f));
-                    gm[k][p] = fmaf(gD, p1 * (dl[k] - D), dz);
-                    ga[k][p] = fmaf(gD, p2 - p1, 0.5f * dz);
-                }
+                for (int k = 0; k < K; ++k) { gm[k][p] = gmp[k]; ga[k][p] = gap[k]; }
             }
         }
         acc_ce += (double)ce_sum;
@@ -163,6 +180,12 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
     }
     finish_loss<3>(acc_ce, acc_d, ws, inv_n, alpha, out3);
 }
+
+}  // namespace mspl
+
+#include "uw_loss_lowres.cuh"
+
+namespace mspl {
 
 // ---- generic runtime-C helpers (compat paths; logits are re-read from L1/L2, HBM sees them once) -------------
 // softmax statistics of one logit vector per pixel: M = max, S = sum e^{x-M}
@@ -517,6 +540,84 @@ extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_log
     LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
     const double inv_n = 1.0 / norm_pixels;
 #define MSPL_CASE(KK) case KK: return launch_uw_ce<KK>(P, bwd, main_logits, aux_logits, target, class_weights, num_images, pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws, st)
+    switch (num_classes) {
+        MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
+    }
+#undef MSPL_CASE
+    return MSPL_ERR_UNSUPPORTED;
+}
+
+template <int K>
+static int launch_uw_ce_lowres(bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, LowresGeom g,
+                               float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
+    int dev = 0, sms = kNumSMs, max_smem = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    size_t smem = 0;
+    for (int tr = 8; tr >= 1; tr >>= 1) {          // tallest tile whose gradients fit in shared memory
+        g.TR = tr;
+        g.nrm = std::min(g.hm, (int)(g.rhm * (float)(tr - 1)) + 3);
+        g.nra = std::min(g.ha, (int)(g.rha * (float)(tr - 1)) + 3);
+        smem = lowres_smem_bytes(g, K, bwd);
+        if (smem <= (size_t)max_smem) break;
+        if (tr == 1) return MSPL_ERR_UNSUPPORTED;   // image too wide for one row of gradients in shared memory
+    }
+    g.tiles_per_img = (g.H + g.TR - 1) / g.TR;
+    const int64_t n_tiles = n * g.tiles_per_img;
+    auto launch = [&](auto kern) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return (int)MSPL_ERR_CUDA;
+        }
+        int per_sm = 1;         // persistent grid of the CTAs that are resident at once (1 with a tile of gradients, more without)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLowresThreads, smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        const int64_t grid = std::min<int64_t>(n_tiles, std::min<int64_t>((int64_t)sms * per_sm, kMaxLossBlocks));
+        kern<<<(unsigned)grid, kLowresThreads, smem, st>>>(m, a, t, cw, n, g, alpha, inv_n, gs, out3, dm, da, ws);
+        return launch_status();
+    };
+    return bwd ? launch(uw_ce_lowres_kernel<K, true>) : launch(uw_ce_lowres_kernel<K, false>);
+}
+
+extern "C" int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* aux_lowres, const int64_t* target,
+                                         const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
+                                         int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels, float grad_scale,
+                                         float* out3, float* d_main_lowres, float* d_aux_lowres, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    if (!main_lowres || !aux_lowres || !target || !class_weights || !out3 || !workspace) return MSPL_ERR_BAD_ARG;
+    if ((d_main_lowres == nullptr) != (d_aux_lowres == nullptr)) return MSPL_ERR_BAD_ARG;
+    if (num_images < 1 || num_classes < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
+    if (main_h < 1 || main_w < 1 || aux_h < 1 || aux_w < 1 || out_h < 1 || out_w < 1) return MSPL_ERR_BAD_ARG;
+    if (workspace_bytes < sizeof(LossWorkspace)) return MSPL_ERR_WORKSPACE;
+    if (num_classes > MSPL_MAX_CLASSES) return MSPL_ERR_UNSUPPORTED;
+    if (main_h > out_h || main_w > out_w || aux_h > out_h || aux_w > out_w) return MSPL_ERR_UNSUPPORTED;   // upsampling only
+    if ((int64_t)out_h * out_w >= (1ll << 24)) return MSPL_ERR_UNSUPPORTED;
+    if (!aligned_to(main_lowres, 4) || !aligned_to(aux_lowres, 4) || !aligned_to(target, 8) || !aligned_to(workspace, 8) ||
+        !aligned_to(d_main_lowres, 4) || !aligned_to(d_aux_lowres, 4))
+        return MSPL_ERR_ALIGN;
+    const bool bwd = d_main_lowres != nullptr;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LowresGeom g{};
+    g.hm = main_h; g.wm = main_w; g.ha = aux_h; g.wa = aux_w; g.H = out_h; g.W = out_w;
+    // ATen's area_pixel_compute_scale for align_corners=True, evaluated in fp32 like the CUDA upsample kernel does
+    auto scale = [](int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; };
+    g.rhm = scale(main_h, out_h); g.rwm = scale(main_w, out_w); g.rha = scale(aux_h, out_h); g.rwa = scale(aux_w, out_w);
+    g.inv_w = 1.0f / (float)out_w;
+    if (bwd) {      // the tiles ADD their shares: start from zero (enqueued on the stream like the kernel itself)
+        const size_t nm = (size_t)num_images * num_classes * main_h * main_w, na = (size_t)num_images * num_classes * aux_h * aux_w;
+        if (cudaMemsetAsync(d_main_lowres, 0, nm * sizeof(float), st) != cudaSuccess ||
+            cudaMemsetAsync(d_aux_lowres, 0, na * sizeof(float), st) != cudaSuccess) {
+            cudaGetLastError();
+            return MSPL_ERR_CUDA;
+        }
+    }
+    LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
+    const double inv_n = 1.0 / norm_pixels;
+#define MSPL_CASE(KK) case KK: return launch_uw_ce_lowres<KK>(bwd, main_lowres, aux_lowres, target, class_weights, num_images, g, alpha, inv_n, grad_scale, out3, d_main_lowres, d_aux_lowres, ws, st)
     switch (num_classes) {
         MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
     }

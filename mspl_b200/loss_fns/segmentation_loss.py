@@ -69,6 +69,20 @@ class FusedUncertaintyWeightedLoss(nn.Module):
         return loss
 
 
+class FusedUpsampleUncertaintyWeightedLoss(FusedUncertaintyWeightedLoss):
+    """[NEW] FusedUncertaintyWeightedLoss on the tensors the network holds BEFORE its closing
+    ``F.interpolate(..., size=x_size, mode='bilinear', align_corners=True)`` calls (model/segmentation/espdnet_ue.py:301-302):
+    ``forward(pred_lowres, pred_aux_lowres, labels)`` equals the parent's forward on the two upsampled tensors, and the
+    gradients arrive at the low-resolution tensors directly -- the upsampled logits and their gradients are never written."""
+
+    def forward(self, pred_lowres, pred_aux_lowres, labels, norm_pixels=None):
+        cw = self.class_weights.to(device=pred_lowres.device, dtype=torch.float32).contiguous()
+        loss, parts = ops.uw_ce_loss_lowres(pred_lowres.contiguous(), pred_aux_lowres.contiguous(), labels.contiguous(), cw,
+                                            self.alpha, norm_pixels, return_parts=True)
+        self.last_parts = parts
+        return loss
+
+
 class NIDLoss(nn.Module):
     """loss_fns/segmentation_loss.py:54-118: normalised information distance between the grey-scale camera image and the
     soft-argmax label map, rescaled as ``(nid - 0.95) * 20`` -- the optional ``--use-nid`` training term

@@ -439,6 +439,59 @@ def uw_ce_loss(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, r
     return (loss, parts) if return_parts else loss
 
 
+def uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True):
+    """K4-lowres, explicit form: main_lr (N,K,hm,wm), aux_lr (N,K,ha,wa) are the tensors the network feeds to its closing
+    bilinear align_corners=True upsample (model/segmentation/espdnet_ue.py:301-302), target (N,H,W) int64 gives the output
+    size.  Returns (out3, d_main_lr, d_aux_lr) like uw_ce_fwd_bwd, the gradients being w.r.t. the PRE-upsample tensors."""
+    main_lr = _require_cuda(main_lr, "main_lr", torch.float32, 4)
+    aux_lr = _require_cuda(aux_lr, "aux_lr", torch.float32, 4)
+    target = _require_cuda(target, "target", torch.int64, 3)
+    cw = _require_cuda(class_weights, "class_weights", torch.float32, 1)
+    n, k, hm, wm = main_lr.shape
+    ha, wa = aux_lr.shape[2:]
+    h, w = target.shape[1:]
+    if aux_lr.shape[:2] != (n, k) or target.shape[0] != n or cw.numel() != k:
+        raise ValueError("shape mismatch: main %s aux %s target %s class_weights %s" %
+                         (tuple(main_lr.shape), tuple(aux_lr.shape), tuple(target.shape), tuple(cw.shape)))
+    dev = main_lr.device
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    d_main = torch.empty_like(main_lr) if backward else None
+    d_aux = torch.empty_like(aux_lr) if backward else None
+    ws = _workspace(dev)
+    norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
+    with torch.cuda.device(dev):
+        st = _lib.load().mspl_uw_ce_lowres_fwd_bwd(_ptr(main_lr), _ptr(aux_lr), _ptr(target), _ptr(cw), n, k, hm, wm, ha, wa, h, w,
+                                                   float(alpha), norm, float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux),
+                                                   _ptr(ws), ws.numel(), _stream(dev))
+    if st == -3:
+        raise NotImplementedError("uw_ce_lowres: geometry not supported by the fused-upsample loss kernel (more than %d classes, "
+                                  "a source larger than the output, or rows too wide for shared memory); upsample and use "
+                                  "uw_ce_loss" % MAX_CLASSES)
+    _lib.check(st, "mspl_uw_ce_lowres_fwd_bwd")
+    return out3, d_main, d_aux
+
+
+class _UwCeLossLowres(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, main_lr, aux_lr, target, class_weights, alpha, norm_pixels):
+        need = main_lr.requires_grad or aux_lr.requires_grad
+        out3, d_main, d_aux = uw_ce_lowres_fwd_bwd(main_lr.detach(), aux_lr.detach(), target, class_weights.detach(), alpha,
+                                                   norm_pixels, 1.0, backward=need)
+        ctx.grads = (d_main, d_aux)
+        ctx.mark_non_differentiable(out3)
+        return out3[0].clone(), out3
+
+    backward = _UwCeLoss.backward          # same hand-over of the gradients produced by the forward launch
+
+
+def uw_ce_loss_lowres(main_lr, aux_lr, target, class_weights, alpha=20.0, norm_pixels=None, return_parts=False):
+    """K4-lowres with autograd: the training loss of uest_seg_multi_os.py:1020-1023 evaluated on
+    ``F.interpolate(main_lr, target.shape[1:], mode='bilinear', align_corners=True)`` (and the same for aux_lr) without ever
+    materialising the upsampled logits or their gradients; forward, backward and both interpolation transposes in ONE launch."""
+    loss, parts = _UwCeLossLowres.apply(main_lr, aux_lr, target, class_weights, alpha, norm_pixels)
+    return (loss, parts) if return_parts else loss
+
+
 def kld_fwd(d1, d2):
     return softmax_kld(d1, d2, want_prob=False, want_kld=True)[1]
 

@@ -319,6 +319,17 @@ def fuse_sources_lowres(mains_lr, auxs_lr, luts, out_size, policy='half', seg_cl
     return fuse_sources([u[0] for u in ups], [u[1] for u in ups], luts, policy, seg_classes, ignore)
 
 
+def training_loss_lowres_and_grads(main_lr, aux_lr, labels, class_weights, alpha=20.0, dtype=torch.float32):
+    """K4-lowres definition: the network's closing upsample (upsample_heads) followed by the training loss, with autograd
+    through both -> (loss, d loss / d main_lr, d loss / d aux_lr)."""
+    m = main_lr.detach().to(dtype).clone().requires_grad_(True)
+    a = aux_lr.detach().to(dtype).clone().requires_grad_(True)
+    mu, au = upsample_heads(m, a, tuple(labels.shape[-2:]))
+    loss = training_loss(mu, au, labels, class_weights.to(dtype), alpha)
+    gm, ga = torch.autograd.grad(loss, (m, a))
+    return loss.detach(), gm, ga
+
+
 def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUSE_CLASSES, ignore=None):
     """Class-balanced (CBST/CRST-style) per-class confidence thresholds (SURVEY.md section 8 A4'').
 

@@ -461,6 +461,70 @@ def test_fused_loss_fp64_oracle_and_determinism(ops, dev):
     torch.testing.assert_close(torch.cat([dm_a, dm_b]), dm, rtol=1e-6, atol=0)
 
 
+LOWRES_GEOMETRIES = [
+    # (B, K, H, W, (hm, wm), (ha, wa))
+    (2, 5, 256, 480, (128, 240), (64, 120)),        # ESPDNetUE on the benchmark crop: x2 main head, x4 aux head, 8-row tiles
+    (3, 3, 37, 50, (19, 25), (10, 13)),             # odd sizes, non-integer scales, partial last tile
+    (2, 5, 24, 32, (24, 32), (12, 16)),             # main head already at full resolution
+    (1, 8, 20, 44, (7, 11), (3, 5)),                # K = 8, large scale factors
+    (2, 2, 9, 1, (5, 1), (3, 1)),                   # single column
+]
+
+
+@pytest.mark.parametrize("geom", LOWRES_GEOMETRIES)
+def test_fused_upsample_loss_matches_oracle(ops, dev, geom):
+    """K4-lowres == F.interpolate(bilinear, align_corners=True) + training loss + autograd through both (the oracle's
+    definition): loss 1e-5 relative, gradients w.r.t. the PRE-upsample tensors against the fp64 oracle; bitwise reproducible."""
+    b, k, h, w, (hm, wm), (ha, wa) = geom
+    gen = torch.Generator().manual_seed(h * 131 + w)
+    main_lr = 3.0 * torch.randn(b, k, hm, wm, generator=gen)
+    aux_lr = main_lr.new_empty(b, k, ha, wa).normal_(0, 3.0, generator=gen)
+    target = torch.randint(0, k, (b, h, w), generator=gen)
+    cw = torch.rand(k, generator=gen) * 3
+    cw[k - 1] = 0.0
+    l64, gm64, ga64 = O.training_loss_lowres_and_grads(main_lr, aux_lr, target, cw, dtype=torch.float64)
+    l32, _, _ = O.training_loss_lowres_and_grads(main_lr, aux_lr, target, cw)
+    out3, dm, da = ops.uw_ce_lowres_fwd_bwd(main_lr.to(dev), aux_lr.to(dev), target.to(dev), cw.to(dev))
+    assert abs(out3[0].item() - l64.item()) <= RTOL * abs(l64.item())
+    assert abs(out3[0].item() - l32.item()) <= RTOL * abs(l32.item())
+    assert abs(out3[0].item() - (20 * out3[1].item() + out3[2].item())) <= 1e-5 * abs(l64.item())
+    # a low-resolution gradient is a weighted sum of up to (2*scale)^2 per-pixel fp32 gradients of mixed sign: the absolute
+    # floor is 5e-5 of the largest gradient instead of the 1e-5 used for the per-pixel gradients of the full-resolution K4
+    scale = float(max(gm64.abs().max(), ga64.abs().max()))
+    torch.testing.assert_close(dm.cpu().double(), gm64, rtol=1e-4, atol=5e-5 * scale)
+    torch.testing.assert_close(da.cpu().double(), ga64, rtol=1e-4, atol=5e-5 * scale)
+    out3b, dmb, dab = ops.uw_ce_lowres_fwd_bwd(main_lr.to(dev), aux_lr.to(dev), target.to(dev), cw.to(dev))
+    assert torch.equal(out3, out3b) and torch.equal(dm, dmb) and torch.equal(da, dab)
+    out3f, none_m, none_a = ops.uw_ce_lowres_fwd_bwd(main_lr.to(dev), aux_lr.to(dev), target.to(dev), cw.to(dev), backward=False)
+    assert none_m is None and none_a is None and torch.equal(out3f, out3)
+    # the same numbers as upsampling on the device and running the full-resolution K4
+    mu, au = O.upsample_heads(main_lr.to(dev).requires_grad_(True), aux_lr.to(dev), (h, w))
+    full, _, _ = ops.uw_ce_fwd_bwd(mu.detach().contiguous(), au.contiguous(), target.to(dev), cw.to(dev), backward=False)
+    assert abs(full[0].item() - out3[0].item()) <= RTOL * abs(full[0].item())
+
+
+def test_fused_upsample_loss_autograd_and_module(ops, dev):
+    from mspl_b200.loss_fns.segmentation_loss import FusedUncertaintyWeightedLoss, FusedUpsampleUncertaintyWeightedLoss
+    b, k, h, w = 2, 5, 64, 96
+    gen = torch.Generator().manual_seed(91)
+    main_lr, aux_lr = 2.0 * torch.randn(b, k, h // 2, w // 2, generator=gen), 2.0 * torch.randn(b, k, h // 4, w // 4, generator=gen)
+    target = torch.randint(0, k, (b, h, w), generator=gen).to(dev)
+    ml, al = main_lr.to(dev).requires_grad_(True), aux_lr.to(dev).requires_grad_(True)
+    crit = FusedUpsampleUncertaintyWeightedLoss(k, class_weights=torch.ones(k, device=dev), ignore_idx=4, device=dev)
+    (crit(ml, al, target) * 0.5).backward()
+    # reference route on the device: F.interpolate (autograd) + the full-resolution fused loss
+    ml2, al2 = main_lr.to(dev).requires_grad_(True), aux_lr.to(dev).requires_grad_(True)
+    mu, au = O.upsample_heads(ml2, al2, (h, w))
+    crit_full = FusedUncertaintyWeightedLoss(k, class_weights=torch.ones(k, device=dev), ignore_idx=4, device=dev)
+    (crit_full(mu, au, target) * 0.5).backward()
+    scale = float(ml2.grad.abs().max())
+    torch.testing.assert_close(ml.grad, ml2.grad, rtol=1e-4, atol=5e-5 * scale)
+    torch.testing.assert_close(al.grad, al2.grad, rtol=1e-4, atol=5e-5 * scale)
+    torch.testing.assert_close(crit.last_parts, crit_full.last_parts, rtol=RTOL, atol=1e-7)
+    with pytest.raises(NotImplementedError):        # a source larger than the output is not an upsample
+        ops.uw_ce_loss_lowres(torch.zeros(1, 5, 80, 96, device=dev), al[:1].detach(), target[:1], torch.ones(5, device=dev))
+
+
 @pytest.mark.parametrize("tag", ["flat", "normal"])
 def test_reference_named_modules(dev, golden, tag):
     """PixelwiseKLD / UncertaintyWeightedSegmentationLoss used exactly as uest_seg_multi_os.py:1020-1023 uses them."""

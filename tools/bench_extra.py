@@ -117,6 +117,33 @@ def lowres_section(dev, iters):
     report("k1_fullres_only_all_%dimg" % n, n * h * w, 313, med3, best3)
 
 
+def loss_lowres_section(dev, iters, flush):
+    """SURVEY.md 8f-1, loss side: K4 taking ESPDNetUE's PRE-upsample heads (x2 main, x4 aux), against upsampling with
+    F.interpolate (autograd) and running the full-resolution fused K4."""
+    import torch.nn.functional as F
+    b, k, h, w = 64, 5, 256, 480
+    g = torch.Generator(device=dev).manual_seed(13)
+    main_lr = 3 * torch.randn((b, k, h // 2, w // 2), device=dev, generator=g)
+    aux_lr = 3 * torch.randn((b, k, h // 4, w // 4), device=dev, generator=g)
+    target = torch.randint(1, 5, (b, h, w), device=dev)
+    cw = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], device=dev)
+    lr_bytes = 2 * 4 * k * (1 / 4 + 1 / 16) + 8        # read + written low-res tensors, int64 target
+    med, best = timed(lambda: ops.uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, cw), iters, flush=flush)
+    report("loss_b64_lowres_fused_upsample_fwd_bwd", b * h * w, lr_bytes, med, best, launches_per_step=1,
+           note="pre-upsample heads in, gradients w.r.t. them out (%.1f B/pixel); compute-bound" % lr_bytes)
+    medf, bestf = timed(lambda: ops.uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, cw, backward=False), iters, flush=flush)
+    report("loss_b64_lowres_fused_upsample_fwd_only", b * h * w, lr_bytes / 2 + 4, medf, bestf, launches_per_step=1)
+
+    def unfused():
+        m, a = main_lr.detach().requires_grad_(True), aux_lr.detach().requires_grad_(True)
+        mu = F.interpolate(m, size=(h, w), mode="bilinear", align_corners=True)
+        au = F.interpolate(a, size=(h, w), mode="bilinear", align_corners=True)
+        ops.uw_ce_loss(mu, au, target, cw).backward()
+    med2, best2 = timed(unfused, iters, flush=flush)
+    report("loss_b64_torch_upsample_then_fused_k4_fwd_bwd", b * h * w, lr_bytes, med2, best2,
+           note="F.interpolate x2 + K4 + upsample_bilinear2d_backward x2 (PyTorch); speed-up of the fused kernel: %.2fx" % (med2 / med))
+
+
 def nid_section(dev, iters):
     """NIDLoss forward + backward at the training batch (64 x 480x256, 16 intensity bins, 5 label bins)."""
     from mspl_b200.loss_fns.segmentation_loss import NIDLoss
@@ -139,7 +166,7 @@ def nid_section(dev, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io", "lowres", "nid"))
+    ap.add_argument("--section", default="all", choices=("all", "loss", "policies", "stress", "io", "lowres", "nid", "loss_lowres"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     iters = 5 if args.quick else 20
@@ -185,9 +212,11 @@ def main():
         label_io_section(dev)
     if args.section in ("all", "lowres"):
         lowres_section(dev, iters)
+    if args.section in ("all", "loss_lowres"):
+        loss_lowres_section(dev, iters, flush)
     if args.section in ("all", "nid"):
         nid_section(dev, iters)
-    if args.section in ("loss", "io", "lowres", "nid"):
+    if args.section in ("loss", "io", "lowres", "nid", "loss_lowres"):
         return
     # ---- non-headline policies on the 13/20/5 configuration -----------------------------------------------------------
     n = 100 if args.quick else 400
