@@ -525,6 +525,41 @@ def test_fused_upsample_loss_autograd_and_module(ops, dev):
         ops.uw_ce_loss_lowres(torch.zeros(1, 5, 80, 96, device=dev), al[:1].detach(), target[:1], torch.ones(5, device=dev))
 
 
+def test_fused_upsample_loss_trains_a_network(dev):
+    """The training-step wiring: forward_lowres() hands the loss the heads a network holds before its closing upsample
+    (the interception ESPDNetUE needs, model/segmentation/espdnet_ue.py:301-302) and the parameter gradients equal those of
+    the ordinary route (network upsamples, autograd runs upsample_bilinear2d_backward, full-resolution fused loss)."""
+    import torch.nn.functional as F
+    from mspl_b200.lowres import forward_lowres
+    from mspl_b200.loss_fns.segmentation_loss import FusedUncertaintyWeightedLoss, FusedUpsampleUncertaintyWeightedLoss
+
+    class TwoHeads(torch.nn.Module):                   # the closing statements of ESPDNetwithUncertaintyEstimation.forward
+        def __init__(self):
+            super().__init__()
+            self.main = torch.nn.Conv2d(3, 5, 3, stride=2, padding=1)
+            self.aux = torch.nn.Conv2d(3, 5, 5, stride=4, padding=2)
+
+        def forward(self, x):
+            size = x.shape[-2:]
+            return (F.interpolate(self.main(x), size=size, mode='bilinear', align_corners=True),
+                    F.interpolate(self.aux(x), size=size, mode='bilinear', align_corners=True))
+
+    torch.manual_seed(4)
+    net = TwoHeads().to(dev)
+    x = torch.randn(2, 3, 48, 64, device=dev)
+    labels = torch.randint(0, 5, (2, 48, 64), device=dev)
+    cw = torch.ones(5, device=dev)
+    pred, pred_aux = net(x)
+    FusedUncertaintyWeightedLoss(5, cw.clone(), 4, dev)(pred, pred_aux, labels).backward()
+    want = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    heads = forward_lowres(net, x)
+    assert heads is not None and heads[0].shape[-2:] == (24, 32) and heads[1].shape[-2:] == (12, 16)
+    FusedUpsampleUncertaintyWeightedLoss(5, cw.clone(), 4, dev)(heads[0], heads[1], labels).backward()
+    for p, g in zip(net.parameters(), want):
+        torch.testing.assert_close(p.grad, g, rtol=1e-4, atol=1e-5 * float(g.abs().max()))
+
+
 @pytest.mark.parametrize("tag", ["flat", "normal"])
 def test_reference_named_modules(dev, golden, tag):
     """PixelwiseKLD / UncertaintyWeightedSegmentationLoss used exactly as uest_seg_multi_os.py:1020-1023 uses them."""
