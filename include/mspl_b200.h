@@ -247,6 +247,19 @@ MSPL_API int mspl_nid_bwd(const float* camera, const float* label, const float* 
                  int64_t pixels_per_image, int image_bins, int label_bins, float bw_camera, float bw_label, const void* state,
                  float* d_label, void* stream);
 
+/* ---- in-training visualisation maps (next-row component) ----------------------------------
+ * Replaces the device half of in_training_visualization_img (utilities/utils.py:76-133; call sites uest_seg_multi_os.py:1060-1066,
+ * 1211-1215): predictions = argmax_c(main + 0.5*aux) (first maximal index; aux may be NULL: argmax of main), kld =
+ * PixelwiseKLD(main, aux), kld_max_key (u32, zeroed by the caller) = order-preserving key of max(kld) over the batch;
+ * mspl_kld_heatmap then writes -kld / max(kld) + 1 (IEEE division, :92) without the reference's host round trip, and
+ * mspl_label_colors is LongTensorToRGBPIL (:188-237) for a batch: labels (n, pixels) int64 -> rgb (n, 3, pixels) u8 through a
+ * HOST table of num_colors (<= 256) RGB triples; labels outside the table give black. */
+MSPL_API int mspl_prediction_maps(const float* main_logits, const float* aux_logits, int64_t n, int c, int64_t pixels_per_image,
+                         int64_t* labels, float* kld, unsigned int* kld_max_key, void* stream);
+MSPL_API int mspl_kld_heatmap(const float* kld, int64_t count, const unsigned int* kld_max_key, float* heat, void* stream);
+MSPL_API int mspl_label_colors(const int64_t* labels, int64_t n, int64_t pixels_per_image, const uint8_t* colors_rgb,
+                      int num_colors, uint8_t* rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,9 @@ SIGNATURES = {
     "mspl_nid_state_bytes": (c_sz, []),
     "mspl_nid_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_sz, c_vp, c_vp]),
     "mspl_nid_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "mspl_prediction_maps": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mspl_kld_heatmap": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "mspl_label_colors": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
     "mspl_miou_from_logits": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_vp]),
     "mspl_miou_from_labels": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_vp]),
 }

@@ -10,6 +10,7 @@
 //   dL/dm_k  = dL/dz_k + g_D p1_k (log p1_k - log p2_k - D)
 //   dL/da_k  = dL/dz_k / 2 + g_D (p2_k - p1_k)
 #include <algorithm>
+#include <cstring>
 
 #include "pixel_math.cuh"
 #include "bilinear.cuh"
@@ -273,6 +274,73 @@ __global__ void __launch_bounds__(256) softmax_kld_kernel(const float* __restric
                 PixVec<P>::store(prob + n * C * hw + off + c * hw, o);
             }
         }
+    }
+}
+
+// ---- in-training visualisation maps (utilities/utils.py:76-133, next-row component SURVEY.md 8f-4) -------------------------
+// predictions = argmax_c(main + aux/2) (first maximal index, as torch.max), kld = PixelwiseKLD(main, aux), and the maximum of
+// kld over the whole batch as an order-preserving key (float_to_key) folded with atomicMax -- what the reference gets from
+// torch.max(kld).item() after three library passes and a host sync.
+template <int P>
+__global__ void __launch_bounds__(256) prediction_maps_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l,
+                                                              int64_t n_img, int C, int64_t hw, long long* __restrict__ labels,
+                                                              float* __restrict__ kld, unsigned int* __restrict__ kld_max_key) {
+    const int64_t gpi = hw / P, n_groups = n_img * gpi;
+    unsigned int best_key = 0;
+    for (int64_t g = blockIdx.x * 256ll + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t n = g / gpi, off = (g - n * gpi) * P;
+        const float* pm = main_l + n * C * hw + off;
+        const float* pa = aux_l ? aux_l + n * C * hw + off : nullptr;
+        float zmax[P];
+        int amax[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { zmax[p] = -INFINITY; amax[p] = 0; }
+        for (int c = 0; c < C; ++c) {
+            float x[P], y[P];
+            PixVec<P>::load(pm + c * hw, x);
+            if (pa) PixVec<P>::load(pa + c * hw, y);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float z = pa ? fmaf(0.5f, y[p], x[p]) : x[p];
+                if (z > zmax[p] || c == 0) { zmax[p] = z; amax[p] = c; }      // strict >: first maximal index
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) labels[n * hw + off + p] = amax[p];
+        if (kld && pa) {
+            KldStats<P> ks;
+            kld_stats<P>(pm, pa, C, hw, ks);
+            PixVec<P>::store(kld + n * hw + off, ks.D);
+#pragma unroll
+            for (int p = 0; p < P; ++p) best_key = max(best_key, float_to_key(ks.D[p]));
+        }
+    }
+    if (kld_max_key) {
+        best_key = __reduce_max_sync(0xffffffffu, best_key);
+        if ((threadIdx.x & 31) == 0 && best_key) atomicMax(kld_max_key, best_key);
+    }
+}
+
+// heat = -kld / max(kld) + 1 with IEEE fp32 division, exactly the reference's expression (utilities/utils.py:92, 103)
+__global__ void __launch_bounds__(256) kld_heatmap_kernel(const float* __restrict__ kld, int64_t count,
+                                                          const unsigned int* __restrict__ kld_max_key, float* __restrict__ heat) {
+    const float mx = key_to_float(*kld_max_key);
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256)
+        heat[i] = __fadd_rn(__fdiv_rn(-kld[i], mx), 1.0f);
+}
+
+struct ColorTable { unsigned char rgb[256][3]; int n; };
+
+// LongTensorToRGBPIL (utilities/utils.py:188-237) for a whole batch: labels (n, hw) int64 -> rgb (n, 3, hw) u8; labels outside
+// the table give black (the reference leaves those bytes uninitialised)
+__global__ void __launch_bounds__(256) label_colors_kernel(const long long* __restrict__ labels, int64_t n_img, int64_t hw,
+                                                           const __grid_constant__ ColorTable tab, uint8_t* __restrict__ rgb) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n_img * hw; i += (int64_t)gridDim.x * 256) {
+        const int64_t n = i / hw, px = i - n * hw;
+        const long long l = labels[i];
+        const bool ok = l >= 0 && l < tab.n;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) rgb[(n * 3 + ch) * hw + px] = ok ? tab.rgb[l][ch] : 0;
     }
 }
 
@@ -660,6 +728,51 @@ extern "C" int mspl_softmax_kld(const float* main_logits, const float* aux_logit
         case 8: { constexpr int CC = 8; STMT; } break; \
         default: break;                         \
     }
+
+extern "C" int mspl_prediction_maps(const float* main_logits, const float* aux_logits, int64_t n, int c, int64_t pixels_per_image,
+                                    int64_t* labels, float* kld, unsigned int* kld_max_key, void* stream) {
+    if (!main_logits || !labels || n < 0 || c < 1 || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
+    if ((kld || kld_max_key) && !aux_logits) return MSPL_ERR_BAD_ARG;
+    if (kld_max_key && !kld) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(main_logits, 4) || !aligned_to(aux_logits, 4) || !aligned_to(labels, 8) || !aligned_to(kld, 4) ||
+        !aligned_to(kld_max_key, 4))
+        return MSPL_ERR_ALIGN;
+    if (n == 0) return MSPL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = pick_vec(pixels_per_image, {main_logits, aux_logits, kld}) == 4 ? 4 : 1;
+    const int64_t grid = persistent_grid(n * (pixels_per_image / P), 256, 8, 1 << 20);
+    if (P == 4)
+        prediction_maps_kernel<4><<<(unsigned)grid, 256, 0, st>>>(main_logits, aux_logits, n, c, pixels_per_image,
+                                                                  reinterpret_cast<long long*>(labels), kld, kld_max_key);
+    else
+        prediction_maps_kernel<1><<<(unsigned)grid, 256, 0, st>>>(main_logits, aux_logits, n, c, pixels_per_image,
+                                                                  reinterpret_cast<long long*>(labels), kld, kld_max_key);
+    return launch_status();
+}
+
+extern "C" int mspl_kld_heatmap(const float* kld, int64_t count, const unsigned int* kld_max_key, float* heat, void* stream) {
+    if (!kld || !kld_max_key || !heat || count < 0) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(kld, 4) || !aligned_to(heat, 4) || !aligned_to(kld_max_key, 4)) return MSPL_ERR_ALIGN;
+    if (count == 0) return MSPL_OK;
+    kld_heatmap_kernel<<<(unsigned)persistent_grid(count, 256, 8, 1 << 20), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        kld, count, kld_max_key, heat);
+    return launch_status();
+}
+
+extern "C" int mspl_label_colors(const int64_t* labels, int64_t n, int64_t pixels_per_image, const uint8_t* colors_rgb, int num_colors,
+                                 uint8_t* rgb, void* stream) {
+    if (!labels || !colors_rgb || !rgb || n < 0 || pixels_per_image < 1 || num_colors < 0 || num_colors > 256) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(labels, 8)) return MSPL_ERR_ALIGN;
+    if (n == 0) return MSPL_OK;
+    ColorTable tab;
+    memset(&tab, 0, sizeof(tab));
+    tab.n = num_colors;
+    for (int i = 0; i < num_colors; ++i)
+        for (int ch = 0; ch < 3; ++ch) tab.rgb[i][ch] = colors_rgb[3 * i + ch];
+    label_colors_kernel<<<(unsigned)persistent_grid(n * pixels_per_image, 256, 8, 1 << 20), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(labels), n, pixels_per_image, tab, rgb);
+    return launch_status();
+}
 
 extern "C" int mspl_kld_fwd(const float* dist1, const float* dist2, int64_t n, int c, int64_t pixels_per_image, float* kld, void* stream) {
     if (!kld) return MSPL_ERR_BAD_ARG;

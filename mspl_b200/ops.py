@@ -650,3 +650,51 @@ def nid_loss(camera, label, image_bins=16, label_bins=4, bw_camera=0.005, bw_lab
     if image_bins > 32 or label_bins > 8:
         raise NotImplementedError("nid_loss supports up to 32 image bins and 8 label bins")
     return _NidLoss.apply(camera, label, image_bins, label_bins, bw_camera, bw_label)
+
+
+# ---- in-training visualisation maps -------------------------------------------------------------------------------------
+def prediction_maps(main, aux=None, want_heat=True):
+    """Device half of in_training_visualization_img (utilities/utils.py:76-133): returns (predictions int64 (N,H,W) =
+    first-argmax of ``main + 0.5*aux`` (of ``main`` when aux is None), heat f32 (N,1,H,W) = ``-kld / max(kld) + 1`` with
+    ``kld = PixelwiseKLD(main, aux)``, or None without aux / with want_heat=False).  Two launches, no host sync."""
+    main = _require_cuda(main.detach().float().contiguous(), "main", torch.float32, 4)
+    if aux is not None:
+        aux = _require_cuda(aux.detach().float().contiguous(), "aux", torch.float32, 4)
+        if aux.shape != main.shape:
+            raise ValueError("main/aux shapes differ")
+    n, c, h, w = main.shape
+    dev = main.device
+    labels = torch.empty((n, h, w), dtype=torch.int64, device=dev)
+    heat_wanted = want_heat and aux is not None
+    kld = torch.empty((n, h, w), dtype=torch.float32, device=dev) if heat_wanted else None
+    key = torch.zeros(1, dtype=torch.int32, device=dev) if heat_wanted else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        _lib.check(lib.mspl_prediction_maps(_ptr(main), _ptr(aux), n, c, h * w, _ptr(labels), _ptr(kld), _ptr(key), st),
+                   "mspl_prediction_maps")
+        heat = None
+        if heat_wanted:
+            heat = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+            _lib.check(lib.mspl_kld_heatmap(_ptr(kld), kld.numel(), _ptr(key), _ptr(heat), st), "mspl_kld_heatmap")
+    return labels, heat
+
+
+def label_colors(labels, colors):
+    """LongTensorToRGBPIL (utilities/utils.py:188-237) for a batch on the device: labels (N,H,W) integer CUDA tensor, colors a
+    sequence of (r, g, b) triples indexed by class id -> uint8 (N,3,H,W).  Labels outside the table give black."""
+    if not isinstance(labels, torch.Tensor) or not labels.is_cuda:
+        raise ValueError("labels must be a CUDA tensor (mspl_b200 has no CPU path)")
+    if labels.dim() != 3:
+        raise ValueError("labels must be (N,H,W)")
+    labels = labels.to(torch.int64).contiguous()
+    table = [int(v) for rgb in colors for v in rgb]
+    if len(table) % 3 or len(table) > 3 * 256 or any(v < 0 or v > 255 for v in table):
+        raise ValueError("colors must be at most 256 (r, g, b) triples of bytes")
+    n, h, w = labels.shape
+    rgb = torch.empty((n, 3, h, w), dtype=torch.uint8, device=labels.device)
+    buf = (ctypes.c_ubyte * max(1, len(table)))(*table)
+    with torch.cuda.device(labels.device):
+        st = _lib.load().mspl_label_colors(_ptr(labels), n, h * w, buf, len(table) // 3, _ptr(rgb), _stream(labels.device))
+    _lib.check(st, "mspl_label_colors")
+    return rgb

@@ -235,6 +235,49 @@ def golden_nid(ref):
         torch.Tensor.to = orig_to
 
 
+GREENHOUSE_ENCODING = (('end_of_plant', (0, 255, 0)), ('other_part_of_plant', (0, 255, 255)), ('artificial_objects', (255, 0, 0)),
+                       ('ground', (255, 255, 0)), ('background', (0, 0, 0)))
+
+
+class CapturingWriter:
+    """Stands in for the TensorBoard SummaryWriter the reference writes its grids to."""
+
+    def __init__(self):
+        self.images = {}
+        self.order = []
+
+    def add_image(self, tag, img, epoch):
+        self.images[tag] = np.asarray(img)
+        self.order.append(tag)
+
+
+def golden_visualization(ref):
+    """in_training_visualization_img (utilities/utils.py:76-133) run live with a capturing writer: tuple predictions (KLD heat
+    map + argmax of main + 0.5*aux) and plain-tensor predictions, greenhouse colour encoding."""
+    from collections import OrderedDict
+    gen = torch.Generator().manual_seed(3)
+    enc = OrderedDict(GREENHOUSE_ENCODING)
+    b, c, h, w = 3, 5, 20, 28
+    images = torch.rand(b, 3, h, w, generator=gen)
+    main = 3.0 * torch.randn(b, c, h, w, generator=gen)
+    aux = main + 1.5 * torch.randn(b, c, h, w, generator=gen)
+    labels = torch.randint(0, c, (b, h, w), generator=gen)
+    out = dict(images=images.numpy(), main=main.numpy(), aux=aux.numpy(), labels=labels.numpy())
+    wr = CapturingWriter()
+    ref.utils.in_training_visualization_img(None, images.clone(), labels=labels.clone(), predictions=(main.clone(), aux.clone()),
+                                            class_encoding=enc, writer=wr, epoch=0, data='train')
+    for tag, img in wr.images.items():
+        out["tuple_" + tag.replace('/', '_')] = img
+    out["tuple_order"] = np.array(wr.order)
+    wr = CapturingWriter()
+    ref.utils.in_training_visualization_img(None, images.clone(), labels=None, predictions=main.clone(), class_encoding=enc, writer=wr,
+                                            epoch=0, data='val')
+    for tag, img in wr.images.items():
+        out["tensor_" + tag.replace('/', '_')] = img
+    out["tensor_order"] = np.array(wr.order)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "visualization.npz"), **out)
+
+
 def main():
     ref = load_reference()
     if ref is None:
@@ -242,7 +285,7 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou, golden_nid):
+    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou, golden_nid, golden_visualization):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
     for f in sorted(os.listdir(GOLDEN_DIR)):

@@ -330,6 +330,28 @@ def training_loss_lowres_and_grads(main_lr, aux_lr, labels, class_weights, alpha
     return loss.detach(), gm, ga
 
 
+def visualization_maps(main, aux):
+    """The tuple branch of in_training_visualization_img, utilities/utils.py:88-97 (CPU tensors): returns
+    (predictions int64 (N,H,W), heat (N,1,H,W) = -kld / max(kld) + 1)."""
+    f_pred = main + 0.5 * aux
+    kld = pixelwise_kld(main, aux)
+    kld = (-kld / torch.max(kld).item() + 1)
+    kld = torch.reshape(kld, (kld.size(0), 1, kld.size(1), kld.size(2)))
+    _, predictions = torch.max(f_pred, dim=1)
+    return predictions, kld
+
+
+def label_to_rgb(labels, class_encoding):
+    """batch_transform(labels, LongTensorToRGBPIL(class_encoding)), utilities/utils.py:157-170, 188-237, with the bytes the
+    reference leaves uninitialised (labels outside the encoding) set to 0.  labels (N,H,W) int64 -> uint8 (N,3,H,W)."""
+    out = torch.zeros((labels.shape[0], 3) + tuple(labels.shape[1:]), dtype=torch.uint8)
+    for index, (_, color) in enumerate(class_encoding.items()):
+        mask = labels == index
+        for channel, value in enumerate(color):
+            out[:, channel].masked_fill_(mask, value)
+    return out
+
+
 def cb_thresholds(label, conf, portion=0.2, ds_rate=1, seg_classes=NUM_GREENHOUSE_CLASSES, ignore=None):
     """Class-balanced (CBST/CRST-style) per-class confidence thresholds (SURVEY.md section 8 A4'').
 

@@ -968,3 +968,47 @@ def test_nid_loss_full_size_vs_oracle(dev):
     got.backward()
     assert abs(got.item() - want.item()) <= 1e-4
     torch.testing.assert_close(ld.grad.cpu(), gw, rtol=1e-3, atol=1e-4 * float(gw.abs().max()))
+
+
+def test_in_training_visualization_matches_reference_golden(dev, golden):
+    """The TensorBoard hook (utilities/utils.py:76-133) with the maps computed on the device: same tags in the same order,
+    identical image / label grids, KLD heat map within 1e-5."""
+    from collections import OrderedDict
+    from oracle.make_golden import GREENHOUSE_ENCODING, CapturingWriter
+    from mspl_b200.utilities.utils import in_training_visualization_img, prediction_maps
+    g = golden("visualization.npz")
+    images, main, aux, labels = (_t(g[k]).to(dev) for k in ("images", "main", "aux", "labels"))
+    enc = OrderedDict(GREENHOUSE_ENCODING)
+    wr = CapturingWriter()
+    in_training_visualization_img(None, images, labels=labels, predictions=(main, aux), class_encoding=enc, writer=wr, epoch=0,
+                                  data='train')
+    assert wr.order == list(g["tuple_order"])
+    assert np.array_equal(wr.images["train/images"], g["tuple_train_images"])
+    assert np.array_equal(wr.images["train/train_labels"], g["tuple_train_train_labels"])
+    assert np.array_equal(wr.images["train/pred_labels"], g["tuple_train_pred_labels"])
+    np.testing.assert_allclose(wr.images["train/kld"], g["tuple_train_kld"], rtol=0, atol=1e-5)
+    wr = CapturingWriter()
+    in_training_visualization_img(None, images, labels=None, predictions=main, class_encoding=enc, writer=wr, epoch=0, data='val')
+    assert wr.order == list(g["tensor_order"])
+    assert np.array_equal(wr.images["val/pred_labels"], g["tensor_val_pred_labels"])
+    # OrderedDict predictions (torchvision-style heads) and a model call
+    pred_od, heat_od = prediction_maps(OrderedDict([('out', main), ('aux', aux)]))
+    pred_t, heat_t = prediction_maps((main, aux))
+    assert torch.equal(pred_od, pred_t) and torch.equal(heat_od, heat_t)
+    ref_pred, ref_heat = O.visualization_maps(main.cpu(), aux.cpu())
+    assert torch.equal(pred_t.cpu(), ref_pred)
+    torch.testing.assert_close(heat_t.cpu(), ref_heat, rtol=0, atol=1e-5)
+
+    class Net(torch.nn.Module):
+        def forward(self, x):
+            return main, aux
+    wr = CapturingWriter()
+    in_training_visualization_img(Net(), images, labels=labels, class_encoding=enc, writer=wr, epoch=1, data='train')
+    assert np.array_equal(wr.images["train/pred_labels"], g["tuple_train_pred_labels"])
+    # exact ties -> first maximal index; labels outside the colour table -> black
+    tied = torch.zeros(1, 5, 4, 8, device=dev)
+    p, _ = prediction_maps(tied)
+    assert int(p.abs().sum()) == 0
+    from mspl_b200 import ops
+    rgb = ops.label_colors(torch.tensor([[[0, 4, 7, -1]]], device=dev), [c for _, c in GREENHOUSE_ENCODING])
+    assert rgb[0, :, 0, 0].tolist() == [0, 255, 0] and rgb[0, :, 0, 2].tolist() == [0, 0, 0] and rgb[0, :, 0, 3].tolist() == [0, 0, 0]
