@@ -177,3 +177,32 @@ def test_generate_with_fused_upsample(tmp_path):
         b = np.array(Image.open(lb.strip().split(',')[1]))
         assert not ((a != want[i]) & ~marg[i]).any()
         assert not ((b != want[i]) & ~marg[i]).any()
+
+
+@pytest.mark.parametrize("batch_images", [1, 2, 8])
+def test_evaluate_pseudo_labels_matches_reference_loop(batch_images):
+    """eval_label.main's loop (:156-211): per-image get_output -> argmax -> table -> merge_outputs('all') -> MIOU.get_iou,
+    restated with the oracle, against the batched GPU evaluation (one fusion + one counting launch per batch)."""
+    from mspl_b200.eval_label import evaluate_pseudo_labels
+    models = [TinySource(c, 5 + i, as_dict=(i == 1)) for i, (_, c) in enumerate(SOURCES)]
+    names = [n for n, _ in SOURCES]
+    g = torch.Generator().manual_seed(8)
+    targets = torch.randint(0, 5, (N, 1, H, W), generator=g)
+    targets[targets == 0] = 255                                  # unlabelled pixels of the greenhouse validation set
+
+    def loader():
+        for i, b in enumerate(_loader()):
+            yield b[0], targets[i], b[2]
+
+    labels, _, marg = _oracle_run(models, names, 'all')
+    inter_sum, union_sum = np.zeros(5, np.float32), np.zeros(5, np.float32)
+    for i in range(N):                                            # AverageMeter.sum of the per-image float32 arrays (:195-197)
+        inter, union = O.miou_get_iou(torch.from_numpy(labels[i].astype(np.int64)), targets[i, 0], num_classes=5)
+        inter_sum, union_sum = inter_sum + inter, union_sum + union
+    want = inter_sum / (union_sum + 1e-10) * 100
+    iou, miou, counts = evaluate_pseudo_labels([m.to('cuda:0') for m in models], names, loader(), 'cuda:0', batch_images=batch_images,
+                                               return_counts=True)
+    assert int(marg.sum()) == 0, "fixture has near-tie pixels; pick another seed"
+    np.testing.assert_allclose(iou, want, rtol=1e-5, atol=1e-6)
+    assert abs(miou - want[[1, 2, 3]].mean()) <= 1e-5 * max(1.0, abs(miou))
+    assert counts.dtype == torch.int64 and counts.shape == (3, 5)
