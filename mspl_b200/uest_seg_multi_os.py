@@ -17,7 +17,11 @@ network.  Differences from the reference, all deliberate:
   * optional class-balanced confidence thresholds ([NEW], ``args.cb_thresholds``; the reference keeps only the
     CBST/CRST flags ``--init-tgt-port`` / ``--ds-rate`` at :216-219);
   * optional fused upsample ([NEW], ``args.fuse_upsample``): the sources' closing bilinear ``F.interpolate`` calls are
-    intercepted (mspl_b200/lowres.py) and performed inside the fusion kernel.
+    intercepted (mspl_b200/lowres.py) and performed inside the fusion kernel;
+  * multi-GPU ([NEW]): when ``torch.distributed`` is initialised (one process per GPU, torchrun) the generators shard the
+    target images over the ranks round-robin by loader batch; only the integer histograms (class counts, confidence bins)
+    are all-reduced, every rank returns the same class weights, and rank 0 writes ``tgt_train.lst`` in the loader's order.
+    ``args.shard_target_images = False`` switches this off for callers that already hand each rank its own loader.
 """
 import os
 import os.path as osp
@@ -150,8 +154,31 @@ def _image_and_names(batch, use_depth):
     return image, ([name] if isinstance(name, str) else list(name))
 
 
+def _dist_info(args):
+    """(world_size, rank) of the label-generation job: one process per GPU when torch.distributed is initialised (and
+    ``args.shard_target_images`` is not switched off), else a single process."""
+    import torch.distributed as dist
+    if getattr(args, 'shard_target_images', True) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _all_reduce_sum(t):
+    """In-place SUM over the ranks of a small integer tensor (histograms, counters).  NCCL reduces the device tensor on the
+    compute stream; any other backend (gloo in the tests) goes through the host."""
+    import torch.distributed as dist
+    if dist.get_backend() == 'nccl':
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    else:
+        c = t.cpu()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        t.copy_(c)
+    return t
+
+
 def _generate(model_list, luts, device, save_path, round_idx, args, logger, testloader, batch_images, policy):
     dev = _cuda_device(device)
+    world, rank = _dist_info(args)
     num_classes = args.classes
     use_depth = getattr(args, 'use_depth', False)
     if policy not in ('half', 'all', 'prob') and not (isinstance(policy, int) and not isinstance(policy, bool)):
@@ -173,6 +200,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
         logger.info('###### Start evaluating target domain train set in round {}! ######'.format(round_idx))
     start_eval = time.time()
     image_path_list, label_path_list, depth_path_list, names = [], [], [], []
+    entry_order = []        # global position (loader batch index, index inside the batch) of every entry of the lists above
     class_hist = torch.zeros(num_classes, dtype=torch.int64, device=dev)
     conf_hist = torch.zeros((num_classes, ops.RADIX_BINS), dtype=torch.int64, device=dev) if use_cb else None
     count_ties = bool(getattr(args, 'count_near_ties', False))     # needs the softmax: off keeps the labels-only kernel
@@ -181,9 +209,10 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
 
     writer = LabelWriter(dev, workers=int(getattr(args, 'label_writer_threads', 8)))
 
-    def save_maps(label_u8, batch_names):
+    def save_maps(label_u8, batch_names, batch_order):
         # PNG encode + file write happen on the writer's threads while the GPU works on the next batch
         out_paths = []
+        entry_order.extend(batch_order)
         for path_name in batch_names:
             image_name = path_name.split('/')[-1].rsplit('.', 1)[0]
             out_paths.append('%s/%s.png' % (save_pred_path, image_name))
@@ -195,7 +224,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
 
     fuse_upsample = bool(getattr(args, 'fuse_upsample', False))
 
-    def flush(images, batch_names):
+    def flush(images, batch_names, batch_order):
         x = torch.cat(images).to(dev, non_blocking=True)
         kw = dict(policy=policy, num_classes=num_classes, ignore_label=IGNORE_LABEL, ds_rate=ds_rate, want_conf=use_cb,
                   want_unc=False, want_conf_hist=use_cb, class_hist=None if use_cb else class_hist, conf_hist=conf_hist,
@@ -218,33 +247,56 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
                 auxs.append(pred_aux.float().contiguous())
             r = ops.fuse_sources(mains, auxs, luts, **kw)
         if use_cb:      # labels wait on the device until the dataset-wide thresholds are known
-            kept_labels.append(r.label), kept_confs.append(r.conf), names.append(batch_names)
+            kept_labels.append(r.label), kept_confs.append(r.conf), names.append((batch_names, batch_order))
         else:
-            save_maps(r.label, batch_names)
+            save_maps(r.label, batch_names, batch_order)
 
     with torch.no_grad():
-        pending, pending_names = [], []
-        for batch in testloader:
+        pending, pending_names, pending_order = [], [], []
+        for batch_idx, batch in enumerate(testloader):
+            if batch_idx % world != rank:       # target images shard over the ranks, round-robin by loader batch
+                continue
             image, batch_names = _image_and_names(batch, use_depth)
             pending.append(image), pending_names.extend(batch_names)
+            pending_order.extend((batch_idx, j) for j in range(len(batch_names)))
             if len(pending_names) >= batch_images:
-                flush(pending, pending_names)
-                pending, pending_names = [], []
+                flush(pending, pending_names, pending_order)
+                pending, pending_names, pending_order = [], [], []
         if pending:
-            flush(pending, pending_names)
-        if use_cb and kept_labels:
+            flush(pending, pending_names, pending_order)
+        if use_cb and (kept_labels or world > 1):
             # conf_hist already holds the linear confidence histogram of every batch; one more pass over the kept maps
-            # settles every pixel outside its class's bracket and the few inside it are resolved from a candidate list
-            label_all, conf_all = torch.cat(kept_labels), torch.cat(kept_confs)
+            # settles every pixel outside its class's bracket and the few inside it are resolved from a candidate list.
+            # With several ranks only the (K, 2048) histograms travel; a rank without images still takes part in them.
+            if kept_labels:
+                label_all, conf_all = torch.cat(kept_labels), torch.cat(kept_confs)
+            else:
+                label_all = torch.empty((0, 1, 1), dtype=torch.uint8, device=dev)
+                conf_all = torch.empty((0, 1, 1), dtype=torch.float32, device=dev)
             _, _, final, _, _ = ops.select_and_apply(label_all, conf_all, portion, ds_rate, num_classes, IGNORE_LABEL,
-                                                     conf_hist=conf_hist, want_final=True, final_hist=class_hist)
+                                                     conf_hist=conf_hist, all_reduce=_all_reduce_sum if world > 1 else None,
+                                                     want_final=True, final_hist=class_hist)
             pos = 0
-            for batch_names in names:
-                save_maps(final[pos:pos + len(batch_names)], batch_names)
+            for batch_names, batch_order in names:
+                save_maps(final[pos:pos + len(batch_names)], batch_names, batch_order)
                 pos += len(batch_names)
+        if world > 1:       # the dataset-wide class histogram (-> class weights) and the near-tie count
+            _all_reduce_sum(class_hist)
+            if count_ties:
+                _all_reduce_sum(marginal)
 
     writer.close()       # every label map is on disk before the list that points at it is written
-    update_image_list(tgt_train_lst, image_path_list, label_path_list, depth_path_list)
+    if world > 1:
+        # every rank hands over its share of the list; rank 0 writes it in the loader's order and all ranks wait for the file
+        import torch.distributed as dist
+        shares = [None] * world
+        dist.all_gather_object(shares, (entry_order, image_path_list, label_path_list, depth_path_list))
+        if rank == 0:
+            rows = sorted((o, i, sh[1][i], sh[2][i], (sh[3][i] if sh[3] else None)) for sh in shares for i, o in enumerate(sh[0]))
+            update_image_list(tgt_train_lst, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows] if use_depth else [])
+        dist.barrier()
+    else:
+        update_image_list(tgt_train_lst, image_path_list, label_path_list, depth_path_list)
     class_weights = _class_weights_from_histogram(class_hist.cpu().numpy(), getattr(args, 'class_weighting', 'normal'), dev)
     if logger is not None:
         ties = ' ({} near-tie pixels)'.format(int(marginal.item())) if count_ties else ''

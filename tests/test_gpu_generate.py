@@ -206,3 +206,48 @@ def test_evaluate_pseudo_labels_matches_reference_loop(batch_images):
     np.testing.assert_allclose(iou, want, rtol=1e-5, atol=1e-6)
     assert abs(miou - want[[1, 2, 3]].mean()) <= 1e-5 * max(1.0, abs(miou))
     assert counts.dtype == torch.int64 and counts.shape == (3, 5)
+
+
+def _dist_worker(rank, world, port, save_path, use_cb, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mspl_b200 import uest_seg_multi_os as U
+        models = [TinySource(c, 5 + i, as_dict=(i == 1)) for i, (_, c) in enumerate(SOURCES)]
+        names = [n for n, _ in SOURCES]
+        lst, cw = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', save_path, 0, N, None, None,
+                                                      _args(merge_label_policy='half', cb_thresholds=use_cb, init_tgt_port=0.3),
+                                                      None, None, None, testloader=_loader(), batch_images=2)
+        out[rank] = (lst, cw.cpu())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_cb", [False, True])
+def test_generators_shard_over_ranks(tmp_path, use_cb):
+    """Two processes (gloo rendezvous, both on cuda:0) share the target images round-robin: label maps, tgt_train.lst and class
+    weights equal the single-process run; only integer histograms cross ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    from mspl_b200 import uest_seg_multi_os as U
+    models = [TinySource(c, 5 + i, as_dict=(i == 1)) for i, (_, c) in enumerate(SOURCES)]
+    names = [n for n, _ in SOURCES]
+    single_dir, multi_dir = str(tmp_path / "single"), str(tmp_path / "multi")
+    lst1, cw1 = U.generate_pseudo_label_multi_model(models, names, 'cuda:0', single_dir, 0, N, None, None,
+                                                    _args(merge_label_policy='half', cb_thresholds=use_cb, init_tgt_port=0.3),
+                                                    None, None, None, testloader=_loader(), batch_images=2)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_dist_worker, args=(2, port, multi_dir, use_cb, out), nprocs=2, join=True)
+    rows1 = [ln.strip().split(',') for ln in open(lst1)]
+    rows2 = [ln.strip().split(',') for ln in open(out[0][0])]
+    assert out[0][0] == out[1][0] == os.path.join(multi_dir, 'tgt_train.lst')
+    assert [r[0] for r in rows1] == [r[0] for r in rows2] and len(rows2) == N
+    for (_, p1), (_, p2) in zip(rows1, rows2):
+        assert os.path.basename(p1) == os.path.basename(p2)
+        assert np.array_equal(np.array(Image.open(p1)), np.array(Image.open(p2)))
+    for r in (0, 1):
+        assert torch.equal(out[r][1], cw1.cpu())
