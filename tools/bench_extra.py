@@ -174,7 +174,7 @@ def main():
     h, w, k = 256, 480, 5
 
     # ---- config 4: loss ------------------------------------------------------------------------------------------
-    for b in ((64, 8) if args.section in ("all", "loss") else ()):
+    for b in ((64, 8, 256) if args.section in ("all", "loss") else ()):
         main_l, aux_l = logits(b, k, h, w, dev, 11)
         target = torch.randint(1, 5, (b, h, w), device=dev)
         cw = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], device=dev)
