@@ -72,3 +72,26 @@ def test_ops_refuse_cpu_tensors():
         ops.pixelwise_kld(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
     assert ops.vote_threshold(3, None) == 2 and ops.vote_threshold(3, 'all') == 3 and ops.vote_threshold(3, 1) == 1
     assert ops.vote_threshold(3, 7) == 2 and ops.vote_threshold(3, '3') == 2 and ops.vote_threshold(2, 'half') == 2
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C program links against the library and calls its host-only
+    entry points (what a cgo / JNI / ctypes-free binding would do)."""
+    from mspl_b200 import _lib
+    src = tmp_path / "abi_smoke.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "mspl_b200.h"\n'
+                   'int main(void) {\n'
+                   '    if (mspl_abi_version() != MSPL_ABI_VERSION) return 1;\n'
+                   '    if (strcmp(mspl_strerror(MSPL_OK), "ok") != 0) return 2;\n'
+                   '    if (mspl_radix_state_bytes(MSPL_MAX_CLASSES) == 0 || mspl_uw_ce_workspace_bytes() == 0) return 3;\n'
+                   '    /* argument validation happens before any CUDA call: usable without a device */\n'
+                   '    if (mspl_fuse_sources(0, NULL, NULL, NULL, NULL, 0, 0, 5, 0, 2, 4, 1, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL)\n'
+                   '        != MSPL_ERR_BAD_ARG) return 4;\n'
+                   '    printf("%s\\n", mspl_fuse_variant());\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir,
+                           "-lmspl_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert "CH=" in out
