@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(256, 4) bracket_classify_kernel(const uint8_t*
             if (g < n_groups) load_label_conf<VEC>(label, conf, g * VEC, l[u], c[u]);
             else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) l[u][v] = 255;        // class "never kept, never a candidate"
+                for (int v = 0; v < VEC; ++v) { l[u][v] = 255; c[u][v] = 0.f; }     // class "never kept, never a candidate"
             }
         }
         uint32_t cmask = 0;             // bit u*VEC+v: pixel (u, v) lies inside its class's bracket
