@@ -224,9 +224,20 @@ def claim_stdout():
     sys.stdout = sys.stderr
 
 
+def _strict(x):
+    """Strict JSON has no NaN/Infinity tokens: non-finite floats become null."""
+    if isinstance(x, float):
+        return x if x == x and abs(x) != float("inf") else None
+    if isinstance(x, dict):
+        return {k: _strict(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_strict(v) for v in x]
+    return x
+
+
 def emit(line):
     out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
-    out.write(json.dumps(line) + "\n")
+    out.write(json.dumps(_strict(line), allow_nan=False) + "\n")
     out.flush()
 
 
@@ -370,6 +381,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
             "results": {"near_tie_pixels": int(job.marginal.item()) if job.marginal is not None else None,
                         "class_hist": job.class_hist.tolist(), "final_hist": job.final_hist.tolist(),
+                        # the never-selected ignore class has threshold +inf: emit() writes it as null (strict JSON has no Infinity)
                         "thresholds": [round(x, 6) for x in job.thresh.tolist()] if job.thresh is not None else None, "kept": kept},
         }
         emit(line)

@@ -32,7 +32,7 @@ extern "C" {
 #define MSPL_API
 #endif
 
-#define MSPL_ABI_VERSION 2
+#define MSPL_ABI_VERSION 3
 #define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
 #define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
 #define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14) */
@@ -189,6 +189,15 @@ MSPL_API int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logit
                        int64_t pixels_per_image, float alpha, double norm_pixels, float grad_scale,
                        float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* The same with the target given as uint8 class indices -- the format the label maps are generated, stored and
+ * written to PNG in (uest_seg_multi_os.py:929-931), 1 byte per pixel instead of the 8 that torch's gather needs
+ * (loss_fns/segmentation_loss.py:160-166): 81 instead of 88 algorithmic bytes per pixel.  Values >= K (e.g. 255)
+ * contribute like a zero-weight class. */
+MSPL_API int mspl_uw_ce_fwd_bwd_u8(const float* main_logits, const float* aux_logits, const uint8_t* target,
+                          const float* class_weights, int64_t num_images, int num_classes,
+                          int64_t pixels_per_image, float alpha, double norm_pixels, float grad_scale,
+                          float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
+                          void* stream);
 /* K4-lowres (next-row component): the same loss on the tensors ESPDNetUE hands to its closing
  * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) calls (model/segmentation/espdnet_ue.py:301-302):
  * main_lowres (num_images, K, main_h, main_w), aux_lowres (num_images, K, aux_h, aux_w), target (num_images, out_h, out_w).
@@ -200,6 +209,11 @@ MSPL_API int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* au
                               int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels,
                               float grad_scale, float* out3, float* d_main_lowres, float* d_aux_lowres,
                               void* workspace, size_t workspace_bytes, void* stream);
+MSPL_API int mspl_uw_ce_lowres_fwd_bwd_u8(const float* main_lowres, const float* aux_lowres, const uint8_t* target,
+                                 const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
+                                 int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels,
+                                 float grad_scale, float* out3, float* d_main_lowres, float* d_aux_lowres,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 /* In-place x *= *scale unless *scale == 1 (device scalar); lets autograd apply an upstream gradient
  * without a host sync. */
 MSPL_API int mspl_scale_inplace(float* x, int64_t count, const float* scale, void* stream);

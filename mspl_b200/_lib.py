@@ -36,6 +36,10 @@ SIGNATURES = {
     "mspl_uw_ce_workspace_bytes": (c_sz, []),
     "mspl_uw_ce_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_f64, c_f32, c_vp, c_vp,
                                    c_vp, c_vp, c_sz, c_vp]),
+    "mspl_uw_ce_fwd_bwd_u8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_f64, c_f32, c_vp, c_vp,
+                                      c_vp, c_vp, c_sz, c_vp]),
+    "mspl_uw_ce_lowres_fwd_bwd_u8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
+                                             c_f64, c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mspl_uw_ce_lowres_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f64,
                                           c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mspl_scale_inplace": (c_int, [c_vp, c_i64, c_vp, c_vp]),

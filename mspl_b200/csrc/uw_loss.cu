@@ -123,9 +123,46 @@ MSPL_DEVINL void uw_ce_pixel(const float (&m)[K], const float (&a)[K], long long
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------------
-template <int P, int K, bool BWD>
-__global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l,
-                                                                   const int64_t* __restrict__ target, const float* __restrict__ cw,
+// Targets of P consecutive pixels as class indices: int64 (what torch's gather wants, the reference's format) or uint8 (the
+// format the label maps are generated and stored in: 1 B/pixel instead of 8).
+template <int P> MSPL_DEVINL void load_targets(const int64_t* p, long long (&t)[P]) {
+    if (P == 4) {
+        const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(p));
+        const longlong2 t1 = __ldcs(reinterpret_cast<const longlong2*>(p) + 1);
+        t[0] = t0.x; t[1] = t0.y; t[P > 2 ? 2 : 0] = t1.x; t[P > 3 ? 3 : 0] = t1.y;
+    } else if (P == 2) {
+        const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(p));
+        t[0] = t0.x; t[P > 1 ? 1 : 0] = t0.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) t[i] = __ldcs(p + i);
+    }
+}
+template <int P> MSPL_DEVINL void load_targets(const uint8_t* p, long long (&t)[P]) {
+    if (P == 4) {
+        const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(p));
+        t[0] = v.x; t[1] = v.y; t[P > 2 ? 2 : 0] = v.z; t[P > 3 ? 3 : 0] = v.w;
+    } else if (P == 2) {
+        const uchar2 v = __ldcs(reinterpret_cast<const uchar2*>(p));
+        t[0] = v.x; t[P > 1 ? 1 : 0] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) t[i] = __ldcs(p + i);
+    }
+}
+
+// Three resident CTAs per SM: without the bound ptxas spends 126 registers on the P=2 backward (2 CTAs/SM); capped at 85 it
+// needs 80, spills nothing, and the third CTA's loads in flight are worth +6.5 % (profiles/r01_loss_variants.txt).  K = 7, 8
+// would spill under that cap and keep two CTAs.
+#ifndef MSPL_UWCE_MINB
+#define MSPL_UWCE_MINB 3
+#endif
+#ifndef MSPL_UWCE_BWD_P
+#define MSPL_UWCE_BWD_P 2
+#endif
+template <int P, int K, bool BWD, typename TT>
+__global__ void __launch_bounds__(kLossThreads, (K <= 6 ? MSPL_UWCE_MINB : 2)) uw_ce_fused_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l,
+                                                                   const TT* __restrict__ target, const float* __restrict__ cw,
                                                                    int64_t n_img, int64_t hw, float alpha, double inv_n, float gscale,
                                                                    float* __restrict__ out3, float* __restrict__ d_main,
                                                                    float* __restrict__ d_aux, LossWorkspace* ws) {
@@ -144,17 +181,7 @@ __global__ void __launch_bounds__(kLossThreads) uw_ce_fused_kernel(const float* 
         for (int k = 0; k < K; ++k) PixVec<P>::load(main_l + base + k * hw, m[k]);
 #pragma unroll
         for (int k = 0; k < K; ++k) PixVec<P>::load(aux_l + base + k * hw, a[k]);
-        if (P == 4) {
-            const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off));
-            const longlong2 t1 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off) + 1);
-            t[0] = t0.x; t[1] = t0.y; t[P > 2 ? 2 : 0] = t1.x; t[P > 3 ? 3 : 0] = t1.y;
-        } else if (P == 2) {
-            const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2*>(target + n * hw + off));
-            t[0] = t0.x; t[P > 1 ? 1 : 0] = t0.y;
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; ++p) t[p] = __ldcs(target + n * hw + off + p);
-        }
+        load_targets<P>(target + n * hw + off, t);
         float gm[K][P], ga[K][P];
         float ce_sum = 0.f, d_sum = 0.f;
 #pragma unroll
@@ -568,18 +595,18 @@ static int64_t resident_grid(Kern kern, int64_t n_groups) {
     return blocks < 1 ? 1 : (blocks < cap ? blocks : cap);
 }
 
-template <int K>
-static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, int64_t hw,
+template <int K, typename TT>
+static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const TT* t, const float* cw, int64_t n, int64_t hw,
                         float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
-    const int pv = P == 4 ? (bwd ? 2 : 4) : 1;
+    const int pv = P == 4 ? (bwd ? MSPL_UWCE_BWD_P : 4) : 1;
     const int64_t n_groups = n * (hw / pv);
 #define MSPL_UWCE(PP, BB)                                                                                                  \
     {                                                                                                                      \
-        auto kern = uw_ce_fused_kernel<PP, K, BB>;                                                                         \
+        auto kern = uw_ce_fused_kernel<PP, K, BB, TT>;                                                                        \
         kern<<<(unsigned)resident_grid(kern, n_groups), kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws); \
     }
-    if (pv == 4) MSPL_UWCE(4, false)
-    else if (pv == 2) MSPL_UWCE(2, true)
+    if (pv == 4 && !bwd) MSPL_UWCE(4, false)
+    else if (pv == MSPL_UWCE_BWD_P && bwd) MSPL_UWCE(MSPL_UWCE_BWD_P, true)
     else if (bwd) MSPL_UWCE(1, true)
     else MSPL_UWCE(1, false)
 #undef MSPL_UWCE
@@ -592,22 +619,26 @@ using namespace mspl;
 
 extern "C" size_t mspl_uw_ce_workspace_bytes(void) { return sizeof(LossWorkspace); }
 
-extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logits, const int64_t* target, const float* class_weights,
-                                  int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
-                                  float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+template <typename TT>
+static int uw_ce_entry(const float* main_logits, const float* aux_logits, const TT* target, const float* class_weights,
+                       int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
+                       float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
+                       void* stream) {
     if (!main_logits || !aux_logits || !target || !class_weights || !out3 || !workspace) return MSPL_ERR_BAD_ARG;
     if ((d_main == nullptr) != (d_aux == nullptr)) return MSPL_ERR_BAD_ARG;
     if (num_images < 1 || pixels_per_image < 1 || num_classes < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
     if (workspace_bytes < sizeof(LossWorkspace)) return MSPL_ERR_WORKSPACE;
     if (num_classes > MSPL_MAX_CLASSES) return MSPL_ERR_UNSUPPORTED;
-    if (!aligned_to(main_logits, 4) || !aligned_to(aux_logits, 4) || !aligned_to(target, 8) || !aligned_to(workspace, 8)) return MSPL_ERR_ALIGN;
+    if (!aligned_to(main_logits, 4) || !aligned_to(aux_logits, 4) || !aligned_to(target, sizeof(TT)) || !aligned_to(workspace, 8))
+        return MSPL_ERR_ALIGN;
     const bool bwd = d_main != nullptr;
-    int P = pick_vec(pixels_per_image, {main_logits, aux_logits, d_main, d_aux}) == 4 && aligned_to(target, 16) ? 4 : 1;
+    // widest group of pixels per thread: rows of logits 16-byte aligned, and the group's targets loadable as one vector
+    // (two 16-byte loads of int64, one 4-byte load of uint8; the backward takes half a group)
+    int P = pick_vec(pixels_per_image, {main_logits, aux_logits, d_main, d_aux}) == 4 && aligned_to(target, sizeof(TT) == 8 ? 16 : 4) ? 4 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
     const double inv_n = 1.0 / norm_pixels;
-#define MSPL_CASE(KK) case KK: return launch_uw_ce<KK>(P, bwd, main_logits, aux_logits, target, class_weights, num_images, pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws, st)
+#define MSPL_CASE(KK) case KK: return launch_uw_ce<KK, TT>(P, bwd, main_logits, aux_logits, target, class_weights, num_images, pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws, st)
     switch (num_classes) {
         MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
     }
@@ -615,8 +646,24 @@ extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_log
     return MSPL_ERR_UNSUPPORTED;
 }
 
-template <int K>
-static int launch_uw_ce_lowres(bool bwd, const float* m, const float* a, const int64_t* t, const float* cw, int64_t n, LowresGeom g,
+extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_logits, const int64_t* target, const float* class_weights,
+                                  int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
+                                  float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    return uw_ce_entry<int64_t>(main_logits, aux_logits, target, class_weights, num_images, num_classes, pixels_per_image, alpha,
+                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mspl_uw_ce_fwd_bwd_u8(const float* main_logits, const float* aux_logits, const uint8_t* target, const float* class_weights,
+                                     int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
+                                     float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    return uw_ce_entry<uint8_t>(main_logits, aux_logits, target, class_weights, num_images, num_classes, pixels_per_image, alpha,
+                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, stream);
+}
+
+template <int K, typename TT>
+static int launch_uw_ce_lowres(bool bwd, const float* m, const float* a, const TT* t, const float* cw, int64_t n, LowresGeom g,
                                float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
     int dev = 0, sms = kNumSMs, max_smem = 227 * 1024;
     if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -648,14 +695,14 @@ static int launch_uw_ce_lowres(bool bwd, const float* m, const float* a, const i
         kern<<<(unsigned)grid, kLowresThreads, smem, st>>>(m, a, t, cw, n, g, alpha, inv_n, gs, out3, dm, da, ws);
         return launch_status();
     };
-    return bwd ? launch(uw_ce_lowres_kernel<K, true>) : launch(uw_ce_lowres_kernel<K, false>);
+    return bwd ? launch(uw_ce_lowres_kernel<K, true, TT>) : launch(uw_ce_lowres_kernel<K, false, TT>);
 }
 
-extern "C" int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* aux_lowres, const int64_t* target,
-                                         const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
-                                         int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels, float grad_scale,
-                                         float* out3, float* d_main_lowres, float* d_aux_lowres, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+template <typename TT>
+static int uw_ce_lowres_entry(const float* main_lowres, const float* aux_lowres, const TT* target, const float* class_weights,
+                              int64_t num_images, int num_classes, int main_h, int main_w, int aux_h, int aux_w, int out_h, int out_w,
+                              float alpha, double norm_pixels, float grad_scale, float* out3, float* d_main_lowres,
+                              float* d_aux_lowres, void* workspace, size_t workspace_bytes, void* stream) {
     if (!main_lowres || !aux_lowres || !target || !class_weights || !out3 || !workspace) return MSPL_ERR_BAD_ARG;
     if ((d_main_lowres == nullptr) != (d_aux_lowres == nullptr)) return MSPL_ERR_BAD_ARG;
     if (num_images < 1 || num_classes < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
@@ -664,7 +711,7 @@ extern "C" int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* 
     if (num_classes > MSPL_MAX_CLASSES) return MSPL_ERR_UNSUPPORTED;
     if (main_h > out_h || main_w > out_w || aux_h > out_h || aux_w > out_w) return MSPL_ERR_UNSUPPORTED;   // upsampling only
     if ((int64_t)out_h * out_w >= (1ll << 24)) return MSPL_ERR_UNSUPPORTED;
-    if (!aligned_to(main_lowres, 4) || !aligned_to(aux_lowres, 4) || !aligned_to(target, 8) || !aligned_to(workspace, 8) ||
+    if (!aligned_to(main_lowres, 4) || !aligned_to(aux_lowres, 4) || !aligned_to(target, sizeof(TT)) || !aligned_to(workspace, 8) ||
         !aligned_to(d_main_lowres, 4) || !aligned_to(d_aux_lowres, 4))
         return MSPL_ERR_ALIGN;
     const bool bwd = d_main_lowres != nullptr;
@@ -685,13 +732,34 @@ extern "C" int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* 
     }
     LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
     const double inv_n = 1.0 / norm_pixels;
-#define MSPL_CASE(KK) case KK: return launch_uw_ce_lowres<KK>(bwd, main_lowres, aux_lowres, target, class_weights, num_images, g, alpha, inv_n, grad_scale, out3, d_main_lowres, d_aux_lowres, ws, st)
+#define MSPL_CASE(KK) case KK: return launch_uw_ce_lowres<KK, TT>(bwd, main_lowres, aux_lowres, target, class_weights, num_images, g, alpha, inv_n, grad_scale, out3, d_main_lowres, d_aux_lowres, ws, st)
     switch (num_classes) {
         MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
     }
 #undef MSPL_CASE
     return MSPL_ERR_UNSUPPORTED;
 }
+
+#define MSPL_LOWRES_ARGS                                                                                                          \
+    main_lowres, aux_lowres, target, class_weights, num_images, num_classes, main_h, main_w, aux_h, aux_w, out_h, out_w, alpha,      \
+        norm_pixels, grad_scale, out3, d_main_lowres, d_aux_lowres, workspace, workspace_bytes, stream
+
+extern "C" int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* aux_lowres, const int64_t* target,
+                                         const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
+                                         int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels, float grad_scale,
+                                         float* out3, float* d_main_lowres, float* d_aux_lowres, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    return uw_ce_lowres_entry<int64_t>(MSPL_LOWRES_ARGS);
+}
+
+extern "C" int mspl_uw_ce_lowres_fwd_bwd_u8(const float* main_lowres, const float* aux_lowres, const uint8_t* target,
+                                            const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,
+                                            int aux_h, int aux_w, int out_h, int out_w, float alpha, double norm_pixels,
+                                            float grad_scale, float* out3, float* d_main_lowres, float* d_aux_lowres, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    return uw_ce_lowres_entry<uint8_t>(MSPL_LOWRES_ARGS);
+}
+#undef MSPL_LOWRES_ARGS
 
 extern "C" int mspl_scale_inplace(float* x, int64_t count, const float* scale, void* stream) {
     if (!x || !scale || count < 0) return MSPL_ERR_BAD_ARG;

@@ -92,9 +92,9 @@ MSPL_DEVINL void lowres_gather(const float* __restrict__ g, int g_stride, float*
     __syncthreads();
 }
 
-template <int K, bool BWD>
+template <int K, bool BWD, typename TT>
 __global__ void __launch_bounds__(kLowresThreads, 1) uw_ce_lowres_kernel(const float* __restrict__ main_lr, const float* __restrict__ aux_lr,
-                                                                         const int64_t* __restrict__ target, const float* __restrict__ cw,
+                                                                         const TT* __restrict__ target, const float* __restrict__ cw,
                                                                          int64_t n_img, const LowresGeom gm, float alpha, double inv_n,
                                                                          float gscale, float* __restrict__ out3, float* __restrict__ d_main,
                                                                          float* __restrict__ d_aux, LossWorkspace* ws) {
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kLowresThreads, 1) uw_ce_lowres_kernel(const f
         }
         __syncthreads();
         // ---- per output pixel: interpolate both heads, K4 closed forms ----
-        const int64_t* tg = target + ((size_t)n * gm.H + y0) * W;
+        const TT* tg = target + ((size_t)n * gm.H + y0) * W;
         for (int p = threadIdx.x; p < rows * W; p += kLowresThreads) {
             int yl, x;
             split_index(p, W, gm.inv_w, yl, x);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kLowresThreads, 1) uw_ce_lowres_kernel(const f
                 m[k] = bilinear(src_m + k * gm.nrm * wm, bm);
                 a[k] = bilinear(src_a + k * gm.nra * wa, ba);
             }
-            uw_ce_pixel<K, BWD>(m, a, __ldcs(tg + p), s_w, alpha, gscale, inv_nf, l, D, gmain, gaux);
+            uw_ce_pixel<K, BWD>(m, a, (long long)__ldcs(tg + p), s_w, alpha, gscale, inv_nf, l, D, gmain, gaux);
             acc_ce += (double)l;
             acc_d += (double)D;
             if (BWD) {

@@ -374,12 +374,20 @@ def _workspace(dev):
     return ws
 
 
+def _class_index_target(target):
+    """Targets of the fused losses: int64 (the reference's format, what torch.gather needs) or uint8 (the format the label
+    maps are generated, stored and saved in -- 1 byte per pixel of HBM traffic instead of 8).  Returns (tensor, is_u8)."""
+    if isinstance(target, torch.Tensor) and target.dtype == torch.uint8:
+        return _require_cuda(target, "target", torch.uint8, 3), True
+    return _require_cuda(target, "target", torch.int64, 3), False
+
+
 def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True):
     """K4, explicit form: returns (out3, d_main, d_aux) with out3 = [loss, mean w*ce*exp(-kld), mean kld] on device and
-    the gradients of loss*grad_scale (None, None when backward=False)."""
+    the gradients of loss*grad_scale (None, None when backward=False).  target: (N,H,W) class indices, int64 or uint8."""
     main = _require_cuda(main, "main", torch.float32, 4)
     aux = _require_cuda(aux, "aux", torch.float32, 4)
-    target = _require_cuda(target, "target", torch.int64, 3)
+    target, u8 = _class_index_target(target)
     cw = _require_cuda(class_weights, "class_weights", torch.float32, 1)
     n, k, h, w = main.shape
     if aux.shape != main.shape or target.shape != (n, h, w) or cw.numel() != k:
@@ -394,11 +402,12 @@ def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None
     d_aux = torch.empty_like(aux) if backward else None
     ws = _workspace(dev)
     norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
+    lib = _lib.load()
+    entry = lib.mspl_uw_ce_fwd_bwd_u8 if u8 else lib.mspl_uw_ce_fwd_bwd
     with torch.cuda.device(dev):
-        st = _lib.load().mspl_uw_ce_fwd_bwd(_ptr(main), _ptr(aux), _ptr(target), _ptr(cw), n, k, h * w, float(alpha), norm,
-                                            float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux), _ptr(ws), ws.numel(),
-                                            _stream(dev))
-    _lib.check(st, "mspl_uw_ce_fwd_bwd")
+        st = entry(_ptr(main), _ptr(aux), _ptr(target), _ptr(cw), n, k, h * w, float(alpha), norm, float(grad_scale), _ptr(out3),
+                   _ptr(d_main), _ptr(d_aux), _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(st, "mspl_uw_ce_fwd_bwd_u8" if u8 else "mspl_uw_ce_fwd_bwd")
     return out3, d_main, d_aux
 
 
@@ -441,11 +450,11 @@ def uw_ce_loss(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, r
 
 def uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True):
     """K4-lowres, explicit form: main_lr (N,K,hm,wm), aux_lr (N,K,ha,wa) are the tensors the network feeds to its closing
-    bilinear align_corners=True upsample (model/segmentation/espdnet_ue.py:301-302), target (N,H,W) int64 gives the output
-    size.  Returns (out3, d_main_lr, d_aux_lr) like uw_ce_fwd_bwd, the gradients being w.r.t. the PRE-upsample tensors."""
+    bilinear align_corners=True upsample (model/segmentation/espdnet_ue.py:301-302), target (N,H,W) int64 or uint8 gives the
+    output size.  Returns (out3, d_main_lr, d_aux_lr) like uw_ce_fwd_bwd, the gradients being w.r.t. the PRE-upsample tensors."""
     main_lr = _require_cuda(main_lr, "main_lr", torch.float32, 4)
     aux_lr = _require_cuda(aux_lr, "aux_lr", torch.float32, 4)
-    target = _require_cuda(target, "target", torch.int64, 3)
+    target, u8 = _class_index_target(target)
     cw = _require_cuda(class_weights, "class_weights", torch.float32, 1)
     n, k, hm, wm = main_lr.shape
     ha, wa = aux_lr.shape[2:]
@@ -459,15 +468,16 @@ def uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, class_weights, alpha=20.0, nor
     d_aux = torch.empty_like(aux_lr) if backward else None
     ws = _workspace(dev)
     norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
+    lib = _lib.load()
+    entry = lib.mspl_uw_ce_lowres_fwd_bwd_u8 if u8 else lib.mspl_uw_ce_lowres_fwd_bwd
     with torch.cuda.device(dev):
-        st = _lib.load().mspl_uw_ce_lowres_fwd_bwd(_ptr(main_lr), _ptr(aux_lr), _ptr(target), _ptr(cw), n, k, hm, wm, ha, wa, h, w,
-                                                   float(alpha), norm, float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux),
-                                                   _ptr(ws), ws.numel(), _stream(dev))
+        st = entry(_ptr(main_lr), _ptr(aux_lr), _ptr(target), _ptr(cw), n, k, hm, wm, ha, wa, h, w, float(alpha), norm,
+                   float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux), _ptr(ws), ws.numel(), _stream(dev))
     if st == -3:
         raise NotImplementedError("uw_ce_lowres: geometry not supported by the fused-upsample loss kernel (more than %d classes, "
                                   "a source larger than the output, or rows too wide for shared memory); upsample and use "
                                   "uw_ce_loss" % MAX_CLASSES)
-    _lib.check(st, "mspl_uw_ce_lowres_fwd_bwd")
+    _lib.check(st, "mspl_uw_ce_lowres_fwd_bwd_u8" if u8 else "mspl_uw_ce_lowres_fwd_bwd")
     return out3, d_main, d_aux
 
 

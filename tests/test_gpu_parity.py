@@ -461,6 +461,48 @@ def test_fused_loss_fp64_oracle_and_determinism(ops, dev):
     torch.testing.assert_close(torch.cat([dm_a, dm_b]), dm, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("shape", [(4, 5, 36, 44), (2, 5, 31, 7), (3, 8, 16, 18), (1, 1, 8, 8)])
+def test_fused_loss_uint8_targets(ops, dev, shape):
+    """uint8 class indices (the format the label maps are generated and stored in) give the same bits as int64 targets,
+    for the full-resolution and the fused-upsample kernels, aligned (vector) and unaligned (scalar) target loads alike;
+    255 -- outside [0,K) for either dtype -- contributes like a zero-weight class."""
+    b, k, h, w = shape
+    main, aux = O.synthetic_logits(b, k, h, w, seed=91)
+    target = torch.randint(0, k, (b, h, w), generator=torch.Generator().manual_seed(5))
+    target[0, 0, :3] = 255
+    cw = torch.rand(k, generator=torch.Generator().manual_seed(6)) + 0.5
+    m, a, t64, c = main.to(dev), aux.to(dev), target.to(dev), cw.to(dev)
+    t8 = t64.to(torch.uint8)
+    want = ops.uw_ce_fwd_bwd(m, a, t64, c)
+    got = ops.uw_ce_fwd_bwd(m, a, t8, c)
+    for x, y in zip(want, got):
+        assert torch.equal(x, y)
+    # against the oracle: pixels labelled 255 carry weight 0, i.e. behave like a class whose weight is zero
+    t_or = target.clone()
+    cw_or = torch.cat([cw, torch.zeros(1)])
+    t_or[target == 255] = k
+    pad = torch.full((b, 1, h, w), -1e4)            # an extra class no pixel can prefer: softmax over K unchanged
+    l64, gm64, _ = O.training_loss_and_grads(torch.cat([main, pad], 1), torch.cat([aux, pad], 1), t_or, cw_or, dtype=torch.float64)
+    assert abs(got[0][0].item() - l64.item()) <= RTOL * abs(l64.item())
+    torch.testing.assert_close(got[1].cpu().double(), gm64[:, :k], rtol=2e-5, atol=2e-6 * float(gm64.abs().max()))
+    # an offset view: targets no longer 4-byte aligned -> the scalar-load instantiation
+    flat = torch.zeros(t8.numel() + 1, dtype=torch.uint8, device=dev)
+    flat[1:] = t8.reshape(-1)
+    got_off = ops.uw_ce_fwd_bwd(m, a, flat[1:].view(b, h, w), c)
+    torch.testing.assert_close(got_off[0], want[0], rtol=1e-6, atol=0)
+    torch.testing.assert_close(got_off[1], want[1], rtol=1e-6, atol=1e-12)
+    # autograd route and the fused-upsample kernel
+    md, ad = m.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    ops.uw_ce_loss(md, ad, t8, c).backward()
+    assert torch.equal(md.grad, want[1]) and torch.equal(ad.grad, want[2])
+    if h >= 4 and w >= 4:
+        ml, al = m[:, :, ::2, ::2].contiguous(), a[:, :, ::4, ::4].contiguous()
+        for x, y in zip(ops.uw_ce_lowres_fwd_bwd(ml, al, t64, c), ops.uw_ce_lowres_fwd_bwd(ml, al, t8, c)):
+            assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        ops.uw_ce_fwd_bwd(m, a, t64.to(torch.int32), c)
+
+
 LOWRES_GEOMETRIES = [
     # (B, K, H, W, (hm, wm), (ha, wa))
     (2, 5, 256, 480, (128, 240), (64, 120)),        # ESPDNetUE on the benchmark crop: x2 main head, x4 aux head, 8-row tiles

@@ -182,6 +182,12 @@ def main():
         report("loss_b%d_fused_fwd_bwd" % b, b * h * w, 88, med, best, launches_per_step=1)
         med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw, backward=False), iters, flush=flush)
         report("loss_b%d_fused_fwd_only" % b, b * h * w, 48, med, best, launches_per_step=1)
+        target8 = target.to(torch.uint8)
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target8, cw), iters, flush=flush)
+        report("loss_b%d_fused_fwd_bwd_u8_targets" % b, b * h * w, 81, med, best, launches_per_step=1,
+               note="labels read as the uint8 maps the generator wrote (1 B/pixel instead of int64's 8)")
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target8, cw, backward=False), iters, flush=flush)
+        report("loss_b%d_fused_fwd_only_u8_targets" % b, b * h * w, 41, med, best, launches_per_step=1)
         if b == 64 and args.section == "all":
             crit = UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=4, device=dev)
             kld_layer = PixelwiseKLD()
@@ -206,7 +212,7 @@ def main():
             med, best = timed(torch_eager, max(3, iters // 4), flush=flush)
             report("loss_b64_torch_eager_cuda_for_context", b * h * w, 88, med, best,
                    note="the reference's op sequence run by PyTorch eager on this GPU (not a CPU baseline)")
-        del main_l, aux_l, target
+        del main_l, aux_l, target, target8
 
     if args.section in ("all", "io"):
         label_io_section(dev)
