@@ -198,6 +198,16 @@ MSPL_API int mspl_uw_ce_fwd_bwd_u8(const float* main_logits, const float* aux_lo
                           int64_t pixels_per_image, float alpha, double norm_pixels, float grad_scale,
                           float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
                           void* stream);
+/* One training step's worth of the path in one launch: the loss above plus the counts MIOU.get_iou(pred, labels) makes of the
+ * very same tensors straight after it (uest_seg_multi_os.py:1032, utilities/metrics/segmentation_miou.py:13-44):
+ * pred = first-max argmax of main_logits, both sides cast to uint8 and shifted by one, pixels with shifted target 0 dropped.
+ *   target      int64 (target_is_u8 == 0) or uint8 class indices
+ *   iou_counts  3*K u64, += : [K intersection | K prediction | K mask] pixel counts (the metric's num_classes = K);
+ *               NULL = loss only.  area_union = prediction + mask - intersection (+1e-6 on the host, :41). */
+MSPL_API int mspl_uw_ce_step(const float* main_logits, const float* aux_logits, const void* target, int target_is_u8,
+                    const float* class_weights, int64_t num_images, int num_classes, int64_t pixels_per_image,
+                    float alpha, double norm_pixels, float grad_scale, float* out3, float* d_main, float* d_aux,
+                    unsigned long long* iou_counts, void* workspace, size_t workspace_bytes, void* stream);
 /* K4-lowres (next-row component): the same loss on the tensors ESPDNetUE hands to its closing
  * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) calls (model/segmentation/espdnet_ue.py:301-302):
  * main_lowres (num_images, K, main_h, main_w), aux_lowres (num_images, K, aux_h, aux_w), target (num_images, out_h, out_w).

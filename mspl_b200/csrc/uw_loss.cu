@@ -154,20 +154,75 @@ template <int P> MSPL_DEVINL void load_targets(const uint8_t* p, long long (&t)[
 // Three resident CTAs per SM: without the bound ptxas spends 126 registers on the P=2 backward (2 CTAs/SM); capped at 85 it
 // needs 80, spills nothing, and the third CTA's loads in flight are worth +6.5 % (profiles/r01_loss_variants.txt).  K = 7, 8
 // would spill under that cap and keep two CTAs.
+// ---- MIOU.get_iou counts folded into K4 (the training loop calls it on the very tensors the loss reads,
+// uest_seg_multi_os.py:1032: `inter, union = miou_class.get_iou(pred, labels)`) -------------------------------------------
+// Semantics of utilities/metrics/segmentation_miou.py:13-44 as in miou.cu: pred = first-max argmax of the MAIN logits, both
+// sides cast to uint8 and shifted by one, pixels with shifted target 0 dropped, classes outside [1, K] not counted.
+// Per-thread counts live in shared memory, one word per class and thread ([K][threads]: conflict-free), three 10-bit fields
+// [inter | pred | mask] per word, folded into the CTA's totals before a field can overflow: no atomics, no warp votes and
+// no registers in the pixel loop (the P=2 backward has none to spare under its 80-register occupancy bound).
+constexpr int kIouFieldBits = 10;
+constexpr int kIouFlushPixels = (1 << kIouFieldBits) - 8;
+
+template <int K>
+MSPL_DEVINL void iou_tally(const float (&m)[K], long long t, uint32_t* my_cnt) {      // my_cnt = s_cnt + threadIdx.x
+    int am = 0;
+    float best = m[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        am = (m[k] > best) ? k : am;          // strict >: first maximal index, as torch.max(output, 1)
+        best = fmaxf(best, m[k]);
+    }
+    const uint32_t ts = ((uint32_t)t + 1u) & 0xffu;            // ByteTensor cast, += 1 "so that 255 is 0"
+    if (ts == 0) return;                                       // pred * (target > 0): nothing to count for this pixel
+    const uint32_t ps = (uint32_t)am + 1u;                     // always in [1, K]
+    my_cnt[(ps - 1) * kLossThreads] += 1u << kIouFieldBits;
+    if (ts <= (uint32_t)K) my_cnt[(ts - 1) * kLossThreads] += 1u + (ps == ts ? (1u << (2 * kIouFieldBits)) : 0u);
+}
+
+// Unpack this thread's fields, add them to the CTA's totals s_iou[3][K] (stored [inter | pred | mask]) and clear.
+// WARP: every lane of the warp is here (the flush after the pixel loop), so reduce over the warp first; otherwise (the rare
+// mid-loop flush, once per ~1,000 pixels of a thread) each thread adds its own fields and no convergence is assumed.
+template <int K, bool WARP>
+MSPL_DEVINL void iou_flush(uint32_t* my_cnt, uint32_t* s_iou) {
+    constexpr uint32_t kMask = (1u << kIouFieldBits) - 1u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t word = my_cnt[k * kLossThreads];
+        my_cnt[k * kLossThreads] = 0;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            uint32_t v = (word >> (f * kIouFieldBits)) & kMask;       // f: 0 mask, 1 pred, 2 inter
+            if (WARP) v = __reduce_add_sync(0xffffffffu, v);
+            if ((!WARP || (threadIdx.x & 31) == 0) && v) atomicAdd(&s_iou[(2 - f) * K + k], v);
+        }
+    }
+}
+
 #ifndef MSPL_UWCE_MINB
 #define MSPL_UWCE_MINB 3
 #endif
 #ifndef MSPL_UWCE_BWD_P
 #define MSPL_UWCE_BWD_P 2
 #endif
-template <int P, int K, bool BWD, typename TT>
+template <int P, int K, bool BWD, typename TT, bool IOU>
 __global__ void __launch_bounds__(kLossThreads, (K <= 6 ? MSPL_UWCE_MINB : 2)) uw_ce_fused_kernel(const float* __restrict__ main_l, const float* __restrict__ aux_l,
                                                                    const TT* __restrict__ target, const float* __restrict__ cw,
                                                                    int64_t n_img, int64_t hw, float alpha, double inv_n, float gscale,
                                                                    float* __restrict__ out3, float* __restrict__ d_main,
-                                                                   float* __restrict__ d_aux, LossWorkspace* ws) {
+                                                                   float* __restrict__ d_aux, LossWorkspace* ws,
+                                                                   unsigned long long* __restrict__ iou_counts) {
     __shared__ float s_w[K];
+    __shared__ uint32_t s_iou[3 * K];
+    __shared__ uint32_t s_cnt[IOU ? K * kLossThreads : 1];
+    uint32_t* const my_cnt = s_cnt + (IOU ? threadIdx.x : 0);
     if (threadIdx.x < K) s_w[threadIdx.x] = cw[threadIdx.x];
+    if (IOU) {
+        if (threadIdx.x < 3 * K) s_iou[threadIdx.x] = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) my_cnt[k * kLossThreads] = 0;
+    }
+    int iou_pixels = 0;
     __syncthreads();
     const int64_t gpi = hw / P, n_groups = n_img * gpi;
     const float inv_nf = (float)inv_n;
@@ -190,6 +245,7 @@ __global__ void __launch_bounds__(kLossThreads, (K <= 6 ? MSPL_UWCE_MINB : 2)) u
 #pragma unroll
             for (int k = 0; k < K; ++k) { mp[k] = m[k][p]; ap[k] = a[k][p]; }
             uw_ce_pixel<K, BWD>(mp, ap, t[p], s_w, alpha, gscale, inv_nf, l, D, gmp, gap);
+            if (IOU) iou_tally<K>(mp, t[p], my_cnt);
             ce_sum += l;
             d_sum += D;
             if (BWD) {
@@ -205,6 +261,18 @@ __global__ void __launch_bounds__(kLossThreads, (K <= 6 ? MSPL_UWCE_MINB : 2)) u
 #pragma unroll
             for (int k = 0; k < K; ++k) PixVec<P>::store(d_aux + base + k * hw, ga[k]);
         }
+        if (IOU) {
+            iou_pixels += P;
+            if (iou_pixels >= kIouFlushPixels) {      // a field holds < 2^10 pixels
+                iou_flush<K, false>(my_cnt, s_iou);
+                iou_pixels = 0;
+            }
+        }
+    }
+    if (IOU) {
+        iou_flush<K, true>(my_cnt, s_iou);
+        __syncthreads();
+        if (threadIdx.x < 3 * K && s_iou[threadIdx.x]) atomicAdd(iou_counts + threadIdx.x, (unsigned long long)s_iou[threadIdx.x]);
     }
     finish_loss<3>(acc_ce, acc_d, ws, inv_n, alpha, out3);
 }
@@ -595,15 +663,16 @@ static int64_t resident_grid(Kern kern, int64_t n_groups) {
     return blocks < 1 ? 1 : (blocks < cap ? blocks : cap);
 }
 
-template <int K, typename TT>
+template <int K, typename TT, bool IOU>
 static int launch_uw_ce(int P, bool bwd, const float* m, const float* a, const TT* t, const float* cw, int64_t n, int64_t hw,
-                        float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws, cudaStream_t st) {
+                        float alpha, double inv_n, float gs, float* out3, float* dm, float* da, LossWorkspace* ws,
+                        unsigned long long* iou, cudaStream_t st) {
     const int pv = P == 4 ? (bwd ? MSPL_UWCE_BWD_P : 4) : 1;
     const int64_t n_groups = n * (hw / pv);
 #define MSPL_UWCE(PP, BB)                                                                                                  \
     {                                                                                                                      \
-        auto kern = uw_ce_fused_kernel<PP, K, BB, TT>;                                                                        \
-        kern<<<(unsigned)resident_grid(kern, n_groups), kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws); \
+        auto kern = uw_ce_fused_kernel<PP, K, BB, TT, IOU>;                                                                        \
+        kern<<<(unsigned)resident_grid(kern, n_groups), kLossThreads, 0, st>>>(m, a, t, cw, n, hw, alpha, inv_n, gs, out3, dm, da, ws, iou); \
     }
     if (pv == 4 && !bwd) MSPL_UWCE(4, false)
     else if (pv == MSPL_UWCE_BWD_P && bwd) MSPL_UWCE(MSPL_UWCE_BWD_P, true)
@@ -623,8 +692,9 @@ template <typename TT>
 static int uw_ce_entry(const float* main_logits, const float* aux_logits, const TT* target, const float* class_weights,
                        int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha, double norm_pixels,
                        float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
-                       void* stream) {
+                       unsigned long long* iou_counts, void* stream) {
     if (!main_logits || !aux_logits || !target || !class_weights || !out3 || !workspace) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(iou_counts, 8)) return MSPL_ERR_ALIGN;
     if ((d_main == nullptr) != (d_aux == nullptr)) return MSPL_ERR_BAD_ARG;
     if (num_images < 1 || pixels_per_image < 1 || num_classes < 1 || !(norm_pixels > 0)) return MSPL_ERR_BAD_ARG;
     if (workspace_bytes < sizeof(LossWorkspace)) return MSPL_ERR_WORKSPACE;
@@ -638,7 +708,14 @@ static int uw_ce_entry(const float* main_logits, const float* aux_logits, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossWorkspace* ws = static_cast<LossWorkspace*>(workspace);
     const double inv_n = 1.0 / norm_pixels;
-#define MSPL_CASE(KK) case KK: return launch_uw_ce<KK, TT>(P, bwd, main_logits, aux_logits, target, class_weights, num_images, pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws, st)
+#define MSPL_CASE(KK)                                                                                                            \
+    case KK:                                                                                                                     \
+        return iou_counts ? launch_uw_ce<KK, TT, true>(P, bwd, main_logits, aux_logits, target, class_weights, num_images,        \
+                                                       pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws,       \
+                                                       iou_counts, st)                                                            \
+                          : launch_uw_ce<KK, TT, false>(P, bwd, main_logits, aux_logits, target, class_weights, num_images,       \
+                                                        pixels_per_image, alpha, inv_n, grad_scale, out3, d_main, d_aux, ws,      \
+                                                        nullptr, st)
     switch (num_classes) {
         MSPL_CASE(1); MSPL_CASE(2); MSPL_CASE(3); MSPL_CASE(4); MSPL_CASE(5); MSPL_CASE(6); MSPL_CASE(7); MSPL_CASE(8);
     }
@@ -651,7 +728,7 @@ extern "C" int mspl_uw_ce_fwd_bwd(const float* main_logits, const float* aux_log
                                   float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace, size_t workspace_bytes,
                                   void* stream) {
     return uw_ce_entry<int64_t>(main_logits, aux_logits, target, class_weights, num_images, num_classes, pixels_per_image, alpha,
-                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, stream);
+                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int mspl_uw_ce_fwd_bwd_u8(const float* main_logits, const float* aux_logits, const uint8_t* target, const float* class_weights,
@@ -659,7 +736,20 @@ extern "C" int mspl_uw_ce_fwd_bwd_u8(const float* main_logits, const float* aux_
                                      float grad_scale, float* out3, float* d_main, float* d_aux, void* workspace,
                                      size_t workspace_bytes, void* stream) {
     return uw_ce_entry<uint8_t>(main_logits, aux_logits, target, class_weights, num_images, num_classes, pixels_per_image, alpha,
-                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, stream);
+                                norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int mspl_uw_ce_step(const float* main_logits, const float* aux_logits, const void* target, int target_is_u8,
+                               const float* class_weights, int64_t num_images, int num_classes, int64_t pixels_per_image, float alpha,
+                               double norm_pixels, float grad_scale, float* out3, float* d_main, float* d_aux,
+                               unsigned long long* iou_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    if (target_is_u8)
+        return uw_ce_entry<uint8_t>(main_logits, aux_logits, static_cast<const uint8_t*>(target), class_weights, num_images,
+                                    num_classes, pixels_per_image, alpha, norm_pixels, grad_scale, out3, d_main, d_aux, workspace,
+                                    workspace_bytes, iou_counts, stream);
+    return uw_ce_entry<int64_t>(main_logits, aux_logits, static_cast<const int64_t*>(target), class_weights, num_images, num_classes,
+                                pixels_per_image, alpha, norm_pixels, grad_scale, out3, d_main, d_aux, workspace, workspace_bytes,
+                                iou_counts, stream);
 }
 
 template <int K, typename TT>

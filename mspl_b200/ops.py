@@ -382,9 +382,11 @@ def _class_index_target(target):
     return _require_cuda(target, "target", torch.int64, 3), False
 
 
-def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True):
+def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, grad_scale=1.0, backward=True, iou_counts=None):
     """K4, explicit form: returns (out3, d_main, d_aux) with out3 = [loss, mean w*ce*exp(-kld), mean kld] on device and
-    the gradients of loss*grad_scale (None, None when backward=False).  target: (N,H,W) class indices, int64 or uint8."""
+    the gradients of loss*grad_scale (None, None when backward=False).  target: (N,H,W) class indices, int64 or uint8.
+    iou_counts: optional (3, K) int64 CUDA tensor that the same launch ADDS the MIOU.get_iou(main, target) pixel counts to
+    ([intersection | prediction | mask] per class, utilities/metrics/segmentation_miou.py:13-44 with num_classes = K)."""
     main = _require_cuda(main, "main", torch.float32, 4)
     aux = _require_cuda(aux, "aux", torch.float32, 4)
     target, u8 = _class_index_target(target)
@@ -402,21 +404,24 @@ def uw_ce_fwd_bwd(main, aux, target, class_weights, alpha=20.0, norm_pixels=None
     d_aux = torch.empty_like(aux) if backward else None
     ws = _workspace(dev)
     norm = float(norm_pixels) if norm_pixels is not None else float(n * h * w)
-    lib = _lib.load()
-    entry = lib.mspl_uw_ce_fwd_bwd_u8 if u8 else lib.mspl_uw_ce_fwd_bwd
+    if iou_counts is not None:
+        iou_counts = _require_cuda(iou_counts, "iou_counts", torch.int64, 2)
+        if iou_counts.shape != (3, k) or iou_counts.device != dev:
+            raise ValueError("iou_counts must be a (3, %d) int64 tensor on %s" % (k, dev))
     with torch.cuda.device(dev):
-        st = entry(_ptr(main), _ptr(aux), _ptr(target), _ptr(cw), n, k, h * w, float(alpha), norm, float(grad_scale), _ptr(out3),
-                   _ptr(d_main), _ptr(d_aux), _ptr(ws), ws.numel(), _stream(dev))
-    _lib.check(st, "mspl_uw_ce_fwd_bwd_u8" if u8 else "mspl_uw_ce_fwd_bwd")
+        st = _lib.load().mspl_uw_ce_step(_ptr(main), _ptr(aux), _ptr(target), int(u8), _ptr(cw), n, k, h * w, float(alpha), norm,
+                                         float(grad_scale), _ptr(out3), _ptr(d_main), _ptr(d_aux), _ptr(iou_counts), _ptr(ws),
+                                         ws.numel(), _stream(dev))
+    _lib.check(st, "mspl_uw_ce_step")
     return out3, d_main, d_aux
 
 
 class _UwCeLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, main, aux, target, class_weights, alpha, norm_pixels):
+    def forward(ctx, main, aux, target, class_weights, alpha, norm_pixels, iou_counts=None):
         need = main.requires_grad or aux.requires_grad
         out3, d_main, d_aux = uw_ce_fwd_bwd(main.detach(), aux.detach(), target, class_weights.detach(), alpha, norm_pixels,
-                                            1.0, backward=need)
+                                            1.0, backward=need, iou_counts=iou_counts)
         ctx.grads = (d_main, d_aux)
         ctx.mark_non_differentiable(out3)
         return out3[0].clone(), out3
@@ -429,7 +434,7 @@ class _UwCeLoss(torch.autograd.Function):
         d_main, d_aux = ctx.grads
         ctx.grads = None
         if d_main is None:
-            return None, None, None, None, None, None
+            return (None,) * 7
         # upstream gradient applied on device, skipped inside the kernel when it is exactly 1 (loss.backward())
         g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         lib = _lib.load()
@@ -437,14 +442,15 @@ class _UwCeLoss(torch.autograd.Function):
             st = _stream(d_main.device)
             _lib.check(lib.mspl_scale_inplace(_ptr(d_main), d_main.numel(), _ptr(g), st), "mspl_scale_inplace")
             _lib.check(lib.mspl_scale_inplace(_ptr(d_aux), d_aux.numel(), _ptr(g), st), "mspl_scale_inplace")
-        return d_main, d_aux, None, None, None, None
+        return d_main, d_aux, None, None, None, None, None
 
 
-def uw_ce_loss(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, return_parts=False):
+def uw_ce_loss(main, aux, target, class_weights, alpha=20.0, norm_pixels=None, return_parts=False, iou_counts=None):
     """K4 with autograd: the value of ``criterion(main + 0.5*aux, target, kld) * alpha + kld.mean()`` with
     ``kld = PixelwiseKLD()(main, aux)`` (uest_seg_multi_os.py:1020-1023), forward and backward in ONE kernel launch.
-    norm_pixels overrides the divisor of the means (global pixel count under data parallelism)."""
-    loss, parts = _UwCeLoss.apply(main, aux, target, class_weights, alpha, norm_pixels)
+    norm_pixels overrides the divisor of the means (global pixel count under data parallelism); iou_counts: see
+    uw_ce_fwd_bwd (the training loop's ``miou_class.get_iou(pred, labels)`` of :1032 counted by the same launch)."""
+    loss, parts = _UwCeLoss.apply(main, aux, target, class_weights, alpha, norm_pixels, iou_counts)
     return (loss, parts) if return_parts else loss
 
 
@@ -483,7 +489,7 @@ def uw_ce_lowres_fwd_bwd(main_lr, aux_lr, target, class_weights, alpha=20.0, nor
 
 class _UwCeLossLowres(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, main_lr, aux_lr, target, class_weights, alpha, norm_pixels):
+    def forward(ctx, main_lr, aux_lr, target, class_weights, alpha, norm_pixels, _reserved=None):   # 7 inputs like _UwCeLoss
         need = main_lr.requires_grad or aux_lr.requires_grad
         out3, d_main, d_aux = uw_ce_lowres_fwd_bwd(main_lr.detach(), aux_lr.detach(), target, class_weights.detach(), alpha,
                                                    norm_pixels, 1.0, backward=need)
@@ -498,7 +504,7 @@ def uw_ce_loss_lowres(main_lr, aux_lr, target, class_weights, alpha=20.0, norm_p
     """K4-lowres with autograd: the training loss of uest_seg_multi_os.py:1020-1023 evaluated on
     ``F.interpolate(main_lr, target.shape[1:], mode='bilinear', align_corners=True)`` (and the same for aux_lr) without ever
     materialising the upsampled logits or their gradients; forward, backward and both interpolation transposes in ONE launch."""
-    loss, parts = _UwCeLossLowres.apply(main_lr, aux_lr, target, class_weights, alpha, norm_pixels)
+    loss, parts = _UwCeLossLowres.apply(main_lr, aux_lr, target, class_weights, alpha, norm_pixels, None)
     return (loss, parts) if return_parts else loss
 
 

@@ -503,6 +503,59 @@ def test_fused_loss_uint8_targets(ops, dev, shape):
         ops.uw_ce_fwd_bwd(m, a, t64.to(torch.int32), c)
 
 
+@pytest.mark.parametrize("shape,dtype", [((4, 5, 36, 44), torch.int64), ((4, 5, 36, 44), torch.uint8), ((2, 5, 31, 7), torch.int64),
+                                         ((3, 8, 16, 18), torch.uint8), ((1, 2, 8, 8), torch.int64), ((6, 5, 256, 480), torch.uint8)])
+def test_fused_loss_with_iou_counts(ops, dev, shape, dtype):
+    """One launch = the loss AND the counts of the training loop's next statement, miou_class.get_iou(pred, labels)
+    (uest_seg_multi_os.py:1032): counts bit-equal to the oracle's restatement of MIOU.get_iou and to the stand-alone metric
+    kernel (itself pinned to the live reference), loss and gradients bit-equal to the launch without the counts."""
+    b, k, h, w = shape
+    main, aux = O.synthetic_logits(b, k, h, w, seed=17)
+    main[0, :, 0, :2] = 1.25                                    # argmax ties -> first index
+    target = torch.randint(0, k, (b, h, w), generator=torch.Generator().manual_seed(8))
+    target[0, 0, 2:5] = 255                                     # wraps to 0 after the +1 shift: dropped
+    if k < 8:
+        target[0, 1, :3] = k                                    # a class id outside histc's range: not counted as mask
+    cw = torch.rand(k, generator=torch.Generator().manual_seed(9)) + 0.5
+    m, a, t, c = main.to(dev), aux.to(dev), target.to(dev).to(dtype), cw.to(dev)
+    counts = torch.zeros((3, k), dtype=torch.int64, device=dev)
+    got = ops.uw_ce_fwd_bwd(m, a, t, c, iou_counts=counts)
+    plain = ops.uw_ce_fwd_bwd(m, a, t, c)
+    for x, y in zip(got, plain):
+        assert torch.equal(x, y)
+    inter, union = O.miou_get_iou(main, target, num_classes=k)
+    alone = ops.miou_counts(m, target.to(dev), k)
+    assert torch.equal(counts, alone)
+    np.testing.assert_array_equal(counts[0].cpu().numpy().astype(np.float32), inter)
+    np.testing.assert_array_equal((counts[1] + counts[2] - counts[0]).cpu().numpy().astype(np.float32) + np.float32(1e-6), union)
+    # accumulation (+=) and forward-only launches
+    ops.uw_ce_fwd_bwd(m, a, t, c, backward=False, iou_counts=counts)
+    assert torch.equal(counts, 2 * alone)
+    with pytest.raises(ValueError):
+        ops.uw_ce_fwd_bwd(m, a, t, c, iou_counts=torch.zeros((3, k + 1), dtype=torch.int64, device=dev))
+
+
+def test_fused_loss_module_tracks_epoch_iou(dev):
+    """FusedUncertaintyWeightedLoss(track_iou=True) over several batches == the reference loop's meters
+    (inter_meter.sum / (union_meter.sum + 1e-10), uest_seg_multi_os.py:1032-1049) fed by the oracle's MIOU.get_iou."""
+    from mspl_b200.loss_fns.segmentation_loss import FusedUncertaintyWeightedLoss
+    k, h, w = 5, 40, 48
+    crit = FusedUncertaintyWeightedLoss(k, torch.ones(k, device=dev), 4, device=dev, track_iou=True)
+    inter_sum, union_sum = np.zeros(k, np.float32), np.zeros(k, np.float32)
+    for step in range(3):
+        main, aux = O.synthetic_logits(2, k, h, w, seed=30 + step)
+        target = torch.randint(0, k, (2, h, w), generator=torch.Generator().manual_seed(step))
+        md = main.to(dev).requires_grad_(True)
+        crit(md, aux.to(dev), target.to(dev)).backward()
+        assert md.grad is not None
+        i, u = O.miou_get_iou(main, target, num_classes=k)
+        inter_sum += i
+        union_sum += u
+    np.testing.assert_allclose(crit.iou(), inter_sum / (union_sum + 1e-10), rtol=1e-6)
+    crit.reset_iou()
+    assert crit.iou_counts is None
+
+
 LOWRES_GEOMETRIES = [
     # (B, K, H, W, (hm, wm), (ha, wa))
     (2, 5, 256, 480, (128, 240), (64, 120)),        # ESPDNetUE on the benchmark crop: x2 main head, x4 aux head, 8-row tiles

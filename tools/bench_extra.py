@@ -188,6 +188,20 @@ def main():
                note="labels read as the uint8 maps the generator wrote (1 B/pixel instead of int64's 8)")
         med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target8, cw, backward=False), iters, flush=flush)
         report("loss_b%d_fused_fwd_only_u8_targets" % b, b * h * w, 41, med, best, launches_per_step=1)
+        # the training loop's pair of statements (uest_seg_multi_os.py:1020-1032): loss, then miou_class.get_iou(pred, labels)
+        counts = torch.zeros((3, k), dtype=torch.int64, device=dev)
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw, iou_counts=counts), iters, flush=flush)
+        report("loss_b%d_fused_fwd_bwd_with_iou_counts" % b, b * h * w, 88, med, best, launches_per_step=1,
+               note="loss forward+backward and the MIOU.get_iou counts of the same tensors in one launch")
+        med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target8, cw, iou_counts=counts), iters, flush=flush)
+        report("loss_b%d_fused_fwd_bwd_with_iou_counts_u8_targets" % b, b * h * w, 81, med, best, launches_per_step=1)
+
+        def two_launches():
+            ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw)
+            ops.miou_counts(main_l, target, k, counts=counts)
+        med, best = timed(two_launches, iters, flush=flush)
+        report("loss_b%d_fused_fwd_bwd_then_miou_kernel" % b, b * h * w, 88 + 4 * k + 8, med, best, launches_per_step=2,
+               note="the same work as two launches: K4, then the stand-alone metric kernel re-reading the main logits and labels")
         if b == 64 and args.section == "all":
             crit = UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=4, device=dev)
             kld_layer = PixelwiseKLD()
