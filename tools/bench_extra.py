@@ -196,6 +196,10 @@ def main():
         med, best = timed(lambda: ops.uw_ce_fwd_bwd(main_l, aux_l, target8, cw, iou_counts=counts), iters, flush=flush)
         report("loss_b%d_fused_fwd_bwd_with_iou_counts_u8_targets" % b, b * h * w, 81, med, best, launches_per_step=1)
 
+        med, best = timed(lambda: ops.miou_counts(main_l, target, k, counts=counts), iters, flush=flush)
+        report("miou_counts_from_logits_b%d" % b, b * h * w, 4 * k + 8, med, best, launches_per_step=1,
+               note="stand-alone MIOU.get_iou counting kernel (argmax of the logits + int64 labels)")
+
         def two_launches():
             ops.uw_ce_fwd_bwd(main_l, aux_l, target, cw)
             ops.miou_counts(main_l, target, k, counts=counts)
