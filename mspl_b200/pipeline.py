@@ -163,4 +163,5 @@ class LabelGenerator:
         if out_host is None:
             out_host = torch.empty((n, h, w), dtype=torch.uint8, pin_memory=True)
         out_host.copy_(final, non_blocking=True)
+        compute.synchronize()          # a host-buffer API: the maps are in `out_host` when the call returns
         return out_host, LabelJob(label, final, None, conf, None, thresh, kept, class_hist, final_hist, marginal)
