@@ -212,7 +212,8 @@ MSPL_API int mspl_uw_ce_step(const float* main_logits, const float* aux_logits, 
  * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) calls (model/segmentation/espdnet_ue.py:301-302):
  * main_lowres (num_images, K, main_h, main_w), aux_lowres (num_images, K, aux_h, aux_w), target (num_images, out_h, out_w).
  * The interpolation (ATen's upsample_bilinear2d arithmetic) and its transpose run inside the kernel; d_main_lowres /
- * d_aux_lowres receive the gradients w.r.t. the PRE-upsample tensors (both NULL = forward only).  Upsampling only
+ * d_aux_lowres receive the gradients w.r.t. the PRE-upsample tensors (both NULL = forward only); they are reproducible bit
+ * for bit for row scale factors up to x4 at widths up to 480, to rounding beyond (fp32 adds of three tile shares).  Upsampling only
  * (source sizes <= output size); MSPL_ERR_UNSUPPORTED when one output row of gradients does not fit in shared memory. */
 MSPL_API int mspl_uw_ce_lowres_fwd_bwd(const float* main_lowres, const float* aux_lowres, const int64_t* target,
                               const float* class_weights, int64_t num_images, int num_classes, int main_h, int main_w,

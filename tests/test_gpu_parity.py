@@ -591,8 +591,15 @@ def test_fused_upsample_loss_matches_oracle(ops, dev, geom):
     torch.testing.assert_close(da.cpu().double(), ga64, rtol=1e-4, atol=5e-5 * scale)
     out3b, dmb, dab = ops.uw_ce_lowres_fwd_bwd(main_lr.to(dev), aux_lr.to(dev), target.to(dev), cw.to(dev))
     assert torch.equal(out3, out3b)
-    if w <= 480:        # 8-row tiles: every low-resolution element gets at most two shares -> order-independent sums
+    if w <= 480 and max((h - 1) / max(hm - 1, 1), (h - 1) / max(ha - 1, 1)) <= 4.1:
+        # 8-row tiles and row scale factors up to x4 (ESPDNetUE's heads): every low-resolution element gets at most two
+        # shares, and two adds onto a zeroed element commute -> bit-reproducible
         assert torch.equal(dm, dmb) and torch.equal(da, dab)
+    else:
+        # larger factors: a low-resolution row's footprint (2 x scale output rows) can straddle three tiles, and the order of
+        # their fp32 adds is not fixed (as in ATen's upsample backward): equal to rounding, not bit for bit
+        torch.testing.assert_close(dm, dmb, rtol=1e-5, atol=1e-7 * scale)
+        torch.testing.assert_close(da, dab, rtol=1e-5, atol=1e-7 * scale)
     else:
         torch.testing.assert_close(da, dab, rtol=1e-5, atol=1e-6 * scale)
     out3f, none_m, none_a = ops.uw_ce_lowres_fwd_bwd(main_lr.to(dev), aux_lr.to(dev), target.to(dev), cw.to(dev), backward=False)
