@@ -99,7 +99,9 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
  * 8*sum(C_s) to ~1.25*sum(C_s) bytes per output pixel for the x2 / x4 heads of ESPDNetUE.
  * Needs every row length (main/aux width) to be a multiple of 4 and out_h*out_w % 4 == 0; returns MSPL_ERR_UNSUPPORTED when
  * the tile's source rows do not fit in shared memory (very wide images): upsample and call mspl_fuse_sources instead.
- * Contract: |logit| differences between the heads beyond 64 units lose confidence precision (no slow path here). */
+ * Contract: pixels whose head maxima sit more than 16 logit units above the fused maximum (heads that disagree that strongly)
+ * or whose fused logits exceed +-48 keep the shared-exponential confidence -- up to ~3e-5 relative error at 64 units / |z| = 256,
+ * clamped to [0,1] -- no slow path here. */
 MSPL_API int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,
                              const int* num_classes, const uint8_t* const* lut, const int* main_hw, const int* aux_hw,
                              int64_t num_images, int out_h, int out_w, int num_target_classes, int policy, int vote_t,

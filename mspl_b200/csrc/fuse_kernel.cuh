@@ -92,14 +92,14 @@ struct PixelFusion {
             if (GK) {
 #pragma unroll
                 for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
-                    Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
+                    Fk[k][p] += fminf(exp_neg(zk[k][p] - r.rz) * r.inv_sz, 1.0f);
             } else {
                 csum[p] += r.pmax;
             }
         }
     }
 
-    // K1-lowres has no full-resolution logits to recompute from: a degenerate pixel (heads more than 64 logit units apart)
+    // K1-lowres has no full-resolution logits to recompute from: a degenerate pixel (head maxima more than 16 logit units above the fused maximum)
     // falls back to the exact-but-underflow-prone shared-exponential value, clamped to a valid probability.
     MSPL_DEVINL void add_source_lowres(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P]) {
 #pragma unroll
@@ -117,7 +117,7 @@ struct PixelFusion {
             last_lab[p] = lab;
             if (GK) {
 #pragma unroll
-                for (int k = 1; k < K; ++k) Fk[k][p] += exp_neg(zk[k][p] - r.rz) * r.inv_sz;
+                for (int k = 1; k < K; ++k) Fk[k][p] += fminf(exp_neg(zk[k][p] - r.rz) * r.inv_sz, 1.0f);
             } else {
                 csum[p] += r.pmax;
             }

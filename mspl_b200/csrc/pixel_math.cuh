@@ -147,8 +147,25 @@ struct SourceResult {
     float rz;       // Rz = Mm + Ma/2, the reference point of Sz
     float inv_sz;   // 1 / Sz:  softmax(z)_c = e^{z_c - Rz} * inv_sz
     float pmax;     // probability of the argmax class = e^{Mz - Rz} * inv_sz
-    bool degenerate;  // the two heads disagree by > 64 logit units: Sz may underflow, caller must take the slow path
+    bool degenerate;  // the two heads' maxima sit more than kMaxSharedExpGap logit units above Mz: caller takes the slow path
 };
+
+// Largest Rz - Mz for which the shared exponentials are trusted.  e^{z-Rz} is formed as a product of two MUFU.EX2 results
+// whose arguments grow with the gap; an argument of magnitude 2^e carries an absolute rounding error of 2^(e-24), i.e. a
+// relative error of ~0.7 * 2^(e-24) in the exponential.  Up to a gap of 16 (arguments < 32) the confidence stays within
+// ~3e-6 of the exact softmax; at 64 -- where Sz would start to underflow -- it would be 3e-5 (seen by the seeded sweep in
+// tests/test_gpu_fuzz.py on logits of standard deviation 40).  Network logits are O(10): the slow path is never taken on
+// the benchmark's inputs, it exists so that pathological inputs still meet the 1e-5 tolerance.
+constexpr float kMaxSharedExpGap = 16.f;
+// Largest |Mz| for the same.  The reference takes the softmax of z AFTER rounding it to fp32 (`pred + 0.5*pred_aux`), the
+// shared exponentials work on the unrounded sum (m-Mm) + (a-Ma)/2 and on a separately rounded Rz: the two differ by up to
+// ~1.5 ulp(z) in the exponent: at most 7.6e-6 relative up to |Mz| = 48 (|Rz| <= 64), but 3e-5 at |z| = 256.  Beyond 48 the
+// slow path recomputes the reference's own expression e^{z_c - Mz} from the rounded z.  (A limit of 32 put ~3 pixels in 10^5
+// of the benchmark's N(0, 6.4^2) fused logits on the slow path and cost K1 1.6 %; 48 is 7.5 sigma away.)
+#ifndef MSPL_MAX_EXP_LOGIT
+#define MSPL_MAX_EXP_LOGIT 48.f
+#endif
+constexpr float kMaxSharedExpLogit = MSPL_MAX_EXP_LOGIT;
 
 template <int P>
 MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
@@ -157,8 +174,8 @@ MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
     r.kld = fmaf(st.T[p], inv_sm, log_fast(st.Sa[p] * inv_sm));
     r.rz = fmaf(0.5f, st.Ma[p], st.Mm[p]);
     r.inv_sz = rcp_fast(st.Sz[p]);
-    r.pmax = exp_neg(st.Mz[p] - r.rz) * r.inv_sz;
-    r.degenerate = !(r.rz - st.Mz[p] <= 64.f);      // Sz >= e^-64 otherwise: no underflow, full precision
+    r.pmax = fminf(exp_neg(st.Mz[p] - r.rz) * r.inv_sz, 1.0f);     // numerator and its term of Sz round separately: clamp
+    r.degenerate = !(r.rz - st.Mz[p] <= kMaxSharedExpGap) || !(fabsf(st.Mz[p]) <= kMaxSharedExpLogit);     // also catches NaN
     return r;
 }
 
