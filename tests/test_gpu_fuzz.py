@@ -85,3 +85,86 @@ def test_random_configuration_matches_oracle(case):
         lo = ops.fuse_sources([m.to(dev) for m in mains], [a.to(dev) for a in auxs], luts, policy=policy, num_classes=K,
                               ignore_label=ignore, want_conf=False, want_unc=False, want_conf_hist=False)
         assert torch.equal(lo.label, r.label) and torch.equal(lo.class_hist, r.class_hist)
+
+
+def _loss_cases(count, seed):
+    rng = random.Random(seed)
+    cases = []
+    for i in range(count):
+        k = rng.choice([1, 2, 3, 5, 5, 5, 7, 8])
+        shape = rng.choice([(2, 16, 24), (1, 9, 7), (3, 1, 40), (2, 31, 5), (1, 48, 80), (4, 8, 480), (1, 2, 2)])
+        sigma = rng.choice([0.05, 1.0, 3.0, 3.0, 12.0, 40.0])
+        independent = rng.random() < 0.3        # aux head unrelated to the main head: large KLD, tiny exp(-KLD)
+        zero_w = rng.random() < 0.5
+        bad_targets = rng.random() < 0.4
+        u8 = rng.random() < 0.5
+        cases.append((i, k, shape, sigma, independent, zero_w, bad_targets, u8))
+    return cases
+
+
+@pytest.mark.parametrize("case", _loss_cases(40, seed=77), ids=lambda c: "loss%02d" % c[0])
+def test_random_loss_configuration_matches_oracle(case):
+    """K4 (fused forward+backward, int64 / uint8 targets, with and without the folded MIOU counts), the reference-named
+    modules (PixelwiseKLD, UncertaintyWeightedSegmentationLoss) and K0 (get_output's maps) against the fp64 / fp32 oracle."""
+    from mspl_b200 import ops
+    from mspl_b200.loss_fns.segmentation_loss import PixelwiseKLD, UncertaintyWeightedSegmentationLoss
+    i, k, (b, h, w), sigma, independent, zero_w, bad_targets, u8 = case
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5000 + i)
+    main, aux = O.synthetic_logits(b, k, h, w, seed=7000 + i, sigma=sigma)
+    if independent:
+        aux = sigma * torch.randn(b, k, h, w, generator=gen)
+    target = torch.randint(0, k, (b, h, w), generator=gen)
+    cw = torch.rand(k, generator=gen) * 3 + 0.1
+    if zero_w:
+        cw[rng_index(gen, k)] = 0.0
+    m, a, c = main.to(dev), aux.to(dev), cw.to(dev)
+
+    # ---- K4 ----
+    t_or, cw_or, m_or, a_or = target, cw, main, aux
+    if bad_targets:                    # labels outside [0,K) (255 = the PNG ignore value) behave like a zero-weight class
+        target = target.clone()
+        target.view(-1)[:: 7] = 255
+        pad = torch.full((b, 1, h, w), -1e4)
+        t_or = target.clone()
+        t_or[target == 255] = k
+        cw_or = torch.cat([cw, torch.zeros(1)])
+        m_or, a_or = torch.cat([main, pad], 1), torch.cat([aux, pad], 1)
+    l64, gm64, ga64 = O.training_loss_and_grads(m_or, a_or, t_or, cw_or, dtype=torch.float64)
+    gm64, ga64 = gm64[:, :k], ga64[:, :k]
+    t_dev = target.to(dev).to(torch.uint8 if u8 else torch.int64)
+    counts = torch.zeros((3, k), dtype=torch.int64, device=dev) if k >= 2 else None
+    out3, dm, da = ops.uw_ce_fwd_bwd(m, a, t_dev, c, iou_counts=counts)
+    assert abs(out3[0].item() - l64.item()) <= RTOL * abs(l64.item()) + 1e-9
+    # per-pixel gradients: relative to the largest gradient of the tensor (they are 1/N-scaled sums of O(1) terms)
+    scale = float(max(gm64.abs().max(), ga64.abs().max()))
+    torch.testing.assert_close(dm.cpu().double(), gm64, rtol=1e-4, atol=1e-5 * scale)
+    torch.testing.assert_close(da.cpu().double(), ga64, rtol=1e-4, atol=1e-5 * scale)
+    if counts is not None:
+        inter, union = O.miou_get_iou(main, target, num_classes=k)
+        np.testing.assert_array_equal(counts[0].cpu().numpy().astype(np.float32), inter)
+        np.testing.assert_array_equal((counts[1] + counts[2] - counts[0]).cpu().numpy().astype(np.float32) + np.float32(1e-6), union)
+        assert torch.equal(counts, ops.miou_counts(m, target.to(dev), k))
+
+    # ---- the reference-named modules, values and autograd gradients (in-range targets only: torch.gather needs them) ----
+    if not bad_targets:
+        p, q = m.clone().requires_grad_(True), a.clone().requires_grad_(True)
+        kld = PixelwiseKLD()(p, q)
+        crit = UncertaintyWeightedSegmentationLoss(k, class_weights=c.clone(), ignore_idx=None, device=dev)
+        loss = crit(p + 0.5 * q, target.to(dev), kld) * 20 + kld.mean()
+        loss.backward()
+        kld_ref = O.pixelwise_kld(main.double(), aux.double())
+        torch.testing.assert_close(kld.detach().cpu().double(), kld_ref, rtol=RTOL, atol=KLD_ATOL * max(1.0, sigma))
+        assert abs(loss.item() - l64.item()) <= 2e-5 * abs(l64.item()) + 1e-9
+        torch.testing.assert_close(p.grad.cpu().double(), gm64, rtol=1e-4, atol=2e-5 * scale)
+        torch.testing.assert_close(q.grad.cpu().double(), ga64, rtol=1e-4, atol=2e-5 * scale)
+
+    # ---- K0: get_output's softmax + KLD maps ----
+    prob, kmap = ops.softmax_kld(m, a)
+    want_p = torch.softmax(main + 0.5 * aux, dim=1)
+    torch.testing.assert_close(prob.cpu(), want_p, rtol=RTOL, atol=1e-7)
+    torch.testing.assert_close(kmap.cpu(), O.pixelwise_kld(main, aux), rtol=RTOL, atol=KLD_ATOL * max(1.0, sigma))
+
+
+def rng_index(gen, k):
+    return int(torch.randint(0, k, (1,), generator=gen))
