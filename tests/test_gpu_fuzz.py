@@ -168,3 +168,74 @@ def test_random_loss_configuration_matches_oracle(case):
 
 def rng_index(gen, k):
     return int(torch.randint(0, k, (1,), generator=gen))
+
+
+def _lowres_cases(count, seed):
+    rng = random.Random(seed)
+    cases = []
+    for i in range(count):
+        H = rng.choice([8, 12, 20, 33, 48, 64, 70])
+        W = rng.choice([16, 48, 96, 240, 480, 496])
+        # head sizes between 1/8 of the output and the output itself (upsampling only), independent per axis; the fused
+        # kernels bulk-copy whole source rows, so row lengths are multiples of 4 floats (their documented contract)
+        hm, wm = rng.randint(max(1, H // 8), H), 4 * rng.randint(max(1, W // 32), W // 4)
+        ha, wa = rng.randint(max(1, H // 8), H), 4 * rng.randint(max(1, W // 32), W // 4)
+        espdnet = rng.random() < 0.4
+        if espdnet:                                 # the ESPDNetUE geometry: x2 and x4
+            hm, wm, ha, wa = (H + 1) // 2, W // 2, (H + 3) // 4, W // 4
+        S = rng.choice([1, 2, 3])
+        cls = [rng.choice([2, 5, 13, 20]) for _ in range(S)]
+        K = rng.choice([3, 5, 5, 8])
+        luts = [[rng.randrange(1, K) for _ in range(c)] for c in cls]
+        policy = rng.choice(["half", "all", "prob"])
+        n = rng.choice([1, 2, 3])
+        cases.append((i, n, H, W, (hm, wm), (ha, wa), S, cls, K, luts, policy, espdnet))
+    return cases
+
+
+@pytest.mark.parametrize("case", _lowres_cases(32, seed=4242), ids=lambda c: "lowres%02d" % c[0])
+def test_random_lowres_geometry_matches_oracle(case):
+    """The fused-upsample kernels (K1-lowres, K4-lowres) over random output sizes, head sizes (integer and non-integer scale
+    factors, heads already at full size, partial tiles) and source sets, against upsample-then-fuse / upsample-then-loss with
+    autograd on the CPU (their parity definitions and tolerances, tests/test_gpu_parity.py)."""
+    from mspl_b200 import ops
+    i, n, H, W, (hm, wm), (ha, wa), S, cls, K, luts, policy, espdnet = case
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(9000 + i)
+    mains = [(3 * torch.randn(n, c, hm, wm, generator=gen) + 3 * torch.randn(n, c, 1, 1, generator=gen)).contiguous() for c in cls]
+    auxs = [(3 * torch.randn(n, c, ha, wa, generator=gen)).contiguous() for c in cls]
+    ignore = K - 1
+    saved = O.NEAR_TIE_MARGIN, O.IGNORE_LABEL
+    O.NEAR_TIE_MARGIN, O.IGNORE_LABEL = 1e-5, ignore
+    try:
+        ref = O.fuse_sources_lowres(mains, auxs, luts, (H, W), policy, K, ignore)
+    finally:
+        O.NEAR_TIE_MARGIN, O.IGNORE_LABEL = saved
+    try:
+        r = ops.fuse_sources_lowres([m.to(dev) for m in mains], [a.to(dev) for a in auxs], luts, (H, W), policy=policy,
+                                    num_classes=K, ignore_label=ignore)
+    except NotImplementedError:
+        r = None                      # source rows too wide for the shared-memory ring (documented): callers upsample instead
+        assert not espdnet, "the ESPDNetUE geometry must be served by the fused kernel"
+    if r is not None:
+        diff = r.label.cpu() != ref["label"]
+        assert not bool((diff & ~ref["marginal"]).any()), "%d mismatches outside near-ties" % int((diff & ~ref["marginal"]).sum())
+        ok = ~diff
+        torch.testing.assert_close(r.conf.cpu()[ok], ref["conf"][ok], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(r.unc.cpu(), ref["unc"], rtol=1e-4, atol=1e-5)
+        assert torch.equal(r.class_hist, torch.bincount(r.label.reshape(-1).long(), minlength=K))
+
+    # ---- K4-lowres on the first source's heads (K <= 8 classes) ----
+    k = min(cls[0], 8)
+    ml, al = mains[0][:, :k].contiguous(), auxs[0][:, :k].contiguous()
+    target = torch.randint(0, k, (n, H, W), generator=gen)
+    cw = torch.rand(k, generator=gen) * 2 + 0.1
+    l64, gm64, ga64 = O.training_loss_lowres_and_grads(ml, al, target, cw, dtype=torch.float64)
+    try:
+        out3, dm, da = ops.uw_ce_lowres_fwd_bwd(ml.to(dev), al.to(dev), target.to(dev).to(torch.uint8 if i % 2 else torch.int64), cw.to(dev))
+    except NotImplementedError:
+        return
+    assert abs(out3[0].item() - l64.item()) <= RTOL * abs(l64.item())
+    scale = float(max(gm64.abs().max(), ga64.abs().max()))
+    torch.testing.assert_close(dm.cpu().double(), gm64, rtol=1e-4, atol=5e-5 * scale)
+    torch.testing.assert_close(da.cpu().double(), ga64, rtol=1e-4, atol=5e-5 * scale)
