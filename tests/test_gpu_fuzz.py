@@ -239,3 +239,65 @@ def test_random_lowres_geometry_matches_oracle(case):
     scale = float(max(gm64.abs().max(), ga64.abs().max()))
     torch.testing.assert_close(dm.cpu().double(), gm64, rtol=1e-4, atol=5e-5 * scale)
     torch.testing.assert_close(da.cpu().double(), ga64, rtol=1e-4, atol=5e-5 * scale)
+
+
+@pytest.mark.parametrize("num_classes,c,shape", [(2, 2, (2, 8, 12)), (5, 5, (3, 31, 7)), (21, 21, (2, 16, 20)), (32, 40, (1, 24, 36)),
+                                                 (33, 33, (2, 16, 20)), (40, 48, (1, 24, 36)), (200, 64, (1, 16, 16)),
+                                                 (5, 5, (40, 64, 96))])
+def test_miou_counts_any_class_count(num_classes, c, shape):
+    """MIOU.get_iou counting for class counts on both sides of the per-thread-counter / warp-aggregated split (32), more
+    logit channels than metric classes (predictions outside histc's range are not counted), 255 and other out-of-range labels,
+    logits / uint8 / int64 predictions, and enough pixels per thread to force mid-loop counter flushes."""
+    from mspl_b200 import ops
+    dev = torch.device("cuda:0")
+    b, h, w = shape
+    gen = torch.Generator().manual_seed(num_classes * 1000 + c)
+    logits = torch.randn(b, c, h, w, generator=gen)
+    logits[0, :, 0, :3] = 0.5                                   # ties -> first index
+    target = torch.randint(0, max(c, num_classes) + 3, (b, h, w), generator=gen)
+    target[0, 0, 3:6] = 255
+    inter, union = O.miou_get_iou(logits, target, num_classes=num_classes)
+    got = ops.miou_counts(logits.to(dev), target.to(dev), num_classes)
+    np.testing.assert_array_equal(got[0].cpu().numpy().astype(np.float32), inter)
+    np.testing.assert_array_equal((got[1] + got[2] - got[0]).cpu().numpy().astype(np.float32) + np.float32(1e-6), union)
+    pred = logits.argmax(1)
+    for p in (pred.to(dev), pred.to(torch.uint8).to(dev)):
+        assert torch.equal(ops.miou_counts(p, target.to(dev), num_classes), got)
+    # accumulation into a caller-provided tensor
+    acc = got.clone()
+    ops.miou_counts(logits.to(dev), target.to(dev), num_classes, counts=acc)
+    assert torch.equal(acc, 2 * got)
+
+
+def test_packed_counters_flush_at_scale():
+    """The per-thread packed counters hold < 1,024 pixels per field and are folded into the CTA totals before that: run both
+    counting kernels on enough pixels (> 1,016 per thread of a full persistent grid) that every thread flushes mid-loop, and
+    compare with counts formed by torch ops on the device (MIOU.get_iou's definition, utilities/metrics/segmentation_miou.py:30-40)."""
+    from mspl_b200 import ops
+    dev = torch.device("cuda:0")
+    k = 5
+    gen = torch.Generator(device=dev).manual_seed(12)
+
+    def expected(pred, target):
+        ts = (target + 1) & 255
+        ps = (pred.long() + 1) * (ts > 0)
+        inter = ps * (ps == ts)
+        return torch.stack([torch.bincount(x.reshape(-1), minlength=k + 3)[1:k + 1] for x in (inter, ps, ts)])
+
+    # stand-alone kernel, label input: 1 pixel per thread and iteration, 148 x 6 CTAs x 256 threads
+    npx = 148 * 6 * 256 * 1100
+    pred = torch.randint(0, k, (npx,), device=dev, generator=gen, dtype=torch.uint8)
+    target = torch.randint(0, k + 2, (npx,), device=dev, generator=gen)
+    target[::97] = 255
+    assert torch.equal(ops.miou_counts(pred, target, k), expected(pred, target))
+    del pred, target
+
+    # K4 forward with the counts folded in: 4 pixels per thread and iteration, 148 x 3 CTAs x 256 threads
+    h, w = 10000, 13000
+    main = torch.randn((1, k, h, w), device=dev, generator=gen)
+    aux = main + 0.5
+    target = torch.randint(0, k + 1, (1, h, w), device=dev, generator=gen).to(torch.uint8)
+    counts = torch.zeros((3, k), dtype=torch.int64, device=dev)
+    out3, _, _ = ops.uw_ce_fwd_bwd(main, aux, target, torch.ones(k, device=dev), backward=False, iou_counts=counts)
+    assert torch.equal(counts, expected(main.argmax(1), target.long()))
+    assert torch.isfinite(out3).all()
