@@ -301,3 +301,62 @@ def test_packed_counters_flush_at_scale():
     out3, _, _ = ops.uw_ce_fwd_bwd(main, aux, target, torch.ones(k, device=dev), backward=False, iou_counts=counts)
     assert torch.equal(counts, expected(main.argmax(1), target.long()))
     assert torch.isfinite(out3).all()
+
+
+def _threshold_cases(count, seed):
+    rng = random.Random(seed)
+    cases = []
+    for i in range(count):
+        K = rng.choice([2, 5, 5, 8])
+        ignore = rng.choice([K - 1, K - 1, 0, None])
+        shape = rng.choice([(1, 7, 9), (2, 32, 48), (3, 50, 70), (1, 256, 480), (5, 64, 100), (1, 1, 4)])
+        dist = rng.choice(["uniform", "few_values", "all_equal", "bin_edges", "near_one", "tiny", "mixed"])
+        portion = rng.choice([0.0, 1e-4, 0.05, 0.2, 0.5, 0.999, 1.0])
+        ds_rate = rng.choice([1, 1, 2, 3, 7])
+        cases.append((i, K, ignore, shape, dist, portion, ds_rate))
+    return cases
+
+
+@pytest.mark.parametrize("case", _threshold_cases(36, seed=99), ids=lambda c: "thr%02d" % c[0])
+def test_random_threshold_inputs_match_sort_definition(case):
+    """Class-balanced thresholds + selection on adversarial confidence distributions -- heavy duplicates (every pixel inside
+    the bracket bin), all-equal values, values exactly on histogram bin edges, values within an ulp of 1, denormal-sized
+    values -- exactly equal to the sort-based definition, for the bracketed protocol and the generic radix one."""
+    from mspl_b200 import ops
+    i, K, ignore, (n, h, w), dist, portion, ds_rate = case
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(300 + i)
+    label = torch.randint(0, K, (n, h, w), generator=gen).to(torch.uint8)
+    u = torch.rand(n, h, w, generator=gen)
+    if dist == "few_values":
+        conf = torch.tensor([0.25, 0.5, 0.5000001, 0.75, 0.9])[torch.randint(0, 5, (n, h, w), generator=gen)]
+    elif dist == "all_equal":
+        conf = torch.full((n, h, w), 0.3333333)
+    elif dist == "bin_edges":
+        conf = torch.randint(0, 2049, (n, h, w), generator=gen).float() / 2048
+    elif dist == "near_one":
+        conf = 1.0 - torch.randint(0, 4, (n, h, w), generator=gen).float() * 5.9604645e-08
+    elif dist == "tiny":
+        conf = u * 1e-38
+    elif dist == "mixed":
+        conf = torch.where(u < 0.3, torch.zeros(()), torch.where(u < 0.6, torch.ones(()), u))
+    else:
+        conf = u
+    conf = conf.float().contiguous()
+    if ignore is not None:                       # as the fusion kernel writes it: the ignore class carries conf 0
+        conf = torch.where(label == ignore, torch.zeros(()), conf)
+    th_ref, kept_ref = O.cb_thresholds(label, conf, portion, ds_rate, K, ignore=ignore)
+    lab_d, conf_d = label.to(dev), conf.to(dev)
+    th, kept, final, mask, fh = ops.select_and_apply(lab_d, conf_d, portion, ds_rate, K, ignore, want_final=ignore is not None,
+                                                     want_mask=ignore is not None)
+    assert torch.equal(th.cpu(), th_ref), (th.cpu(), th_ref)
+    assert torch.equal(kept.cpu(), kept_ref)
+    if ignore is not None:
+        f_ref, m_ref = O.apply_thresholds(label, conf, th_ref, ignore)
+        assert torch.equal(final.cpu(), f_ref) and torch.equal(mask.cpu(), m_ref)
+        assert torch.equal(fh.cpu(), torch.bincount(f_ref.reshape(-1).long(), minlength=K))
+        f2, m2, fh2 = ops.apply_thresholds(lab_d, conf_d, th, ignore_label=ignore)        # the stand-alone K3 kernel
+        assert torch.equal(f2, final) and torch.equal(m2, mask) and torch.equal(fh2, fh)
+    th2, kept2 = ops.cb_thresholds_radix(lab_d, conf_d, portion, ds_rate, K)
+    sel = torch.arange(K) != (ignore if ignore is not None else -1)
+    assert torch.equal(th2.cpu()[sel], th_ref[sel]) and torch.equal(kept2.cpu(), kept_ref)
