@@ -83,3 +83,38 @@ def test_label_generator_without_thresholds_is_the_reference_loop(dev):
         assert job.class_hist.cpu().tolist() == [int(x) for x in class_array]
         torch.testing.assert_close(class_weights_from_histogram(job.class_hist),
                                    O.class_weights_from_histogram(class_array, 'normal'))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_follow_their_tensors_to_a_non_current_device():
+    """Tensors on cuda:1 while cuda:0 is the current device (and a non-default stream is current on cuda:1): every launch must
+    go to the tensors' device and stream -- results equal those computed on cuda:0."""
+    from mspl_b200 import ops
+    from mspl_b200.pipeline import LabelGenerator
+    d0, d1 = torch.device("cuda:0"), torch.device("cuda:1")
+    torch.cuda.set_device(d0)
+    mains, auxs, luts = _inputs(3, 32, 48, seed=600)
+    want = LabelGenerator(luts, policy="half").run([m.to(d0) for m in mains], [a.to(d0) for a in auxs])
+    side = torch.cuda.Stream(d1)
+    with torch.cuda.stream(side):
+        assert torch.cuda.current_device() == 1
+    assert torch.cuda.current_device() == 0
+    m1, a1 = [m.to(d1) for m in mains], [a.to(d1) for a in auxs]
+    torch.cuda.synchronize(d1)
+    with torch.cuda.stream(side):           # current stream on cuda:1 is `side`; leave the block -> current device is cuda:0 again
+        pass
+    got = LabelGenerator(luts, policy="half").run(m1, a1)
+    assert got.final.device == d1
+    assert torch.equal(got.final.cpu(), want.final.cpu()) and torch.equal(got.thresh.cpu(), want.thresh.cpu())
+    assert torch.equal(got.class_hist.cpu(), want.class_hist.cpu())
+    k = 5
+    main, aux = O.synthetic_logits(2, k, 24, 36, seed=601)
+    target = torch.randint(0, k, (2, 24, 36), generator=torch.Generator().manual_seed(3))
+    cw = torch.ones(k)
+    o0 = ops.uw_ce_fwd_bwd(main.to(d0), aux.to(d0), target.to(d0), cw.to(d0))
+    c1 = torch.zeros((3, k), dtype=torch.int64, device=d1)
+    o1 = ops.uw_ce_fwd_bwd(main.to(d1), aux.to(d1), target.to(d1), cw.to(d1), iou_counts=c1)
+    for x, y in zip(o0, o1):
+        assert y.device == d1 and torch.equal(x.cpu(), y.cpu())
+    assert torch.equal(c1.cpu(), ops.miou_counts(main.to(d0), target.to(d0), k).cpu())
+    assert torch.cuda.current_device() == 0
