@@ -360,3 +360,52 @@ def test_random_threshold_inputs_match_sort_definition(case):
     th2, kept2 = ops.cb_thresholds_radix(lab_d, conf_d, portion, ds_rate, K)
     sel = torch.arange(K) != (ignore if ignore is not None else -1)
     assert torch.equal(th2.cpu()[sel], th_ref[sel]) and torch.equal(kept2.cpu(), kept_ref)
+
+
+def test_threshold_stage_beyond_2_31_pixels():
+    """A 20,000-image target set thresholded on ONE GPU is 2,457,600,000 pixels -- more than 2^31 (BASELINE configs[2] kept
+    as label + conf, 5 B/pixel): pixel counts and offsets are 64-bit, candidate indices unsigned 32-bit.  Checked by counting:
+    thresh[k] is the j-th largest conf of class k iff #(conf >= t) >= j > #(conf > t); every kept pixel reaches its class
+    threshold, every dropped one does not, histograms are exact -- including the pixels whose index exceeds 2^31."""
+    from mspl_b200 import ops
+    dev = torch.device("cuda:0")
+    if torch.cuda.get_device_properties(dev).total_memory < 80 * 2 ** 30:
+        pytest.skip("needs ~45 GB of device memory")
+    n, h, w, K, ignore, portion = 20000, 256, 480, 5, 4, 0.2
+    npix = n * h * w
+    assert 2 ** 31 < npix < 2 ** 32
+    gen = torch.Generator(device=dev).manual_seed(31)
+    label = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    conf = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+    step = 2000
+    for lo in range(0, n, step):                       # filled in slices: no dataset-sized temporaries
+        label[lo:lo + step] = torch.randint(0, K, (step, h, w), device=dev, generator=gen, dtype=torch.uint8)
+        conf[lo:lo + step].uniform_(0.0, 1.0, generator=gen)
+        conf[lo:lo + step] *= (label[lo:lo + step] != ignore)          # as the fusion kernel writes it
+    thresh, kept, final, mask, final_hist = ops.select_and_apply(label, conf, portion, 1, K, ignore, want_mask=True)
+    th = thresh.cpu()
+    ge, gt, cnt, fh = (torch.zeros(K, dtype=torch.int64, device=dev) for _ in range(4))
+    ok = torch.ones((), dtype=torch.bool, device=dev)
+    for lo in range(0, n, step):
+        lab, cf, fin, msk = label[lo:lo + step].long(), conf[lo:lo + step], final[lo:lo + step].long(), mask[lo:lo + step]
+        t = thresh[lab]
+        cnt += torch.bincount(lab.reshape(-1), minlength=K)
+        fh += torch.bincount(fin.reshape(-1), minlength=K)
+        ge += torch.bincount(lab[cf >= t], minlength=K)
+        gt += torch.bincount(lab[cf > t], minlength=K)
+        keep = (lab != ignore) & (cf >= t)
+        ok &= ((fin == torch.where(keep, lab, torch.full_like(lab, ignore))).all()) & ((msk == (fin == ignore)).all())
+    assert bool(ok), "a final label / mask differs from label-if-conf>=thresh-else-ignore"
+    assert torch.equal(kept, cnt) and torch.equal(final_hist, fh)
+    for k in range(K):
+        if k == ignore:
+            assert th[k] == float("inf")
+            continue
+        j = int(int(cnt[k]) * portion)
+        assert int(ge[k]) >= j > int(gt[k]), (k, j, int(ge[k]), int(gt[k]))
+        assert int(fh[k]) == int(ge[k])
+    # the tail of the array (pixel indices above 2^31) against the CPU definition
+    tail = slice(n - 4, n)
+    assert (n - 4) * h * w > 2 ** 31
+    f_ref, m_ref = O.apply_thresholds(label[tail].cpu(), conf[tail].cpu(), th, ignore)
+    assert torch.equal(final[tail].cpu(), f_ref) and torch.equal(mask[tail].cpu(), m_ref)
