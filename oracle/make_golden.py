@@ -278,6 +278,43 @@ def golden_visualization(ref):
     np.savez_compressed(os.path.join(GOLDEN_DIR, "visualization.npz"), **out)
 
 
+def golden_train_step(ref):
+    """The per-iteration statements of train() that sit on the path, run by the LIVE reference for three batches
+    (uest_seg_multi_os.py:1020-1049): kld = kld_layer(pred, pred_aux); loss = criterion(pred + 0.5*pred_aux, labels, kld) * 20
+    + kld.mean(); inter, union = miou_class.get_iou(pred, labels); the two AverageMeters; iou = inter_meter.sum /
+    (union_meter.sum + 1e-10); miou = iou[[1, 2, 3]].mean() * 100.  Fixture of FusedUncertaintyWeightedLoss(track_iou=True)."""
+    from loss_fns.segmentation_loss import PixelwiseKLD, UncertaintyWeightedSegmentationLoss
+    from utilities.metrics.segmentation_miou import MIOU
+    from utilities.utils import AverageMeter
+    gen = torch.Generator().manual_seed(17)
+    k, b, h, w = 5, 2, 24, 40
+    cw = torch.tensor([1.0, 2.0, 0.5, 1.5, 3.0])
+    crit = UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=4, device='cpu')
+    kld_layer, miou_class = PixelwiseKLD(), MIOU(num_classes=k)
+    inter_meter, union_meter = AverageMeter(), AverageMeter()
+    out = {"class_weights": cw.numpy()}
+    for i in range(3):
+        pred, pred_aux = _logits(b, k, h, w, gen)
+        labels = torch.randint(0, k, (b, h, w), generator=gen)
+        if i == 1:
+            labels[0, 0, :4] = 255                                        # one batch with pixels the metric drops
+        loss_labels = labels.clone()
+        loss_labels[loss_labels == 255] = 4                               # the loss needs in-range targets (torch.gather)
+        p, q = pred.clone().requires_grad_(True), pred_aux.clone().requires_grad_(True)
+        kld = kld_layer(p, q)
+        loss = crit(p + 0.5 * q, loss_labels, kld) * 20 + kld.mean()
+        loss.backward()
+        inter, union = miou_class.get_iou(pred, labels)
+        inter_meter.update(inter)
+        union_meter.update(union)
+        out.update({"main_%d" % i: pred.numpy(), "aux_%d" % i: pred_aux.numpy(), "labels_%d" % i: labels.numpy(),
+                    "loss_labels_%d" % i: loss_labels.numpy(), "loss_%d" % i: np.float32(loss.item()),
+                    "grad_main_%d" % i: p.grad.numpy(), "grad_aux_%d" % i: q.grad.numpy(), "inter_%d" % i: inter, "union_%d" % i: union})
+    iou = inter_meter.sum / (union_meter.sum + 1e-10)
+    out["iou"], out["miou"] = iou, np.float32(iou[[1, 2, 3]].mean() * 100)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "train_step.npz"), **out)
+
+
 def main():
     ref = load_reference()
     if ref is None:
@@ -285,7 +322,7 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
     only = sys.argv[1:]
-    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou, golden_nid, golden_visualization):
+    for fn in (golden_multi_source, golden_adversarial, golden_loss, golden_config1, golden_miou, golden_nid, golden_visualization, golden_train_step):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
     for f in sorted(os.listdir(GOLDEN_DIR)):

@@ -556,6 +556,30 @@ def test_fused_loss_module_tracks_epoch_iou(dev):
     assert crit.iou_counts is None
 
 
+def test_fused_training_step_matches_live_reference_golden(dev, golden):
+    """FusedUncertaintyWeightedLoss(track_iou=True) against what the LIVE reference's training-loop statements produced for
+    three batches (tests/golden/train_step.npz: loss, gradients, and the epoch IoU from its two AverageMeters,
+    uest_seg_multi_os.py:1020-1049).  The labels are fed as they are -- uint8, with the 255s the metric drops: a 255 weighs
+    nothing in the fused loss, exactly like the ignore class the reference had to remap it to for torch.gather."""
+    from mspl_b200.loss_fns.segmentation_loss import FusedUncertaintyWeightedLoss
+    g = golden("train_step.npz")
+    for as_u8 in (False, True):
+        crit = FusedUncertaintyWeightedLoss(5, _t(g["class_weights"]).clone().to(dev), ignore_idx=4, device=dev, track_iou=True)
+        for i in range(3):
+            md, ad = _t(g["main_%d" % i]).to(dev).requires_grad_(True), _t(g["aux_%d" % i]).to(dev).requires_grad_(True)
+            labels = _t(g["labels_%d" % i]).to(dev)
+            loss = crit(md, ad, labels.to(torch.uint8) if as_u8 else labels)
+            loss.backward()
+            want = float(g["loss_%d" % i])
+            assert abs(loss.item() - want) <= RTOL * abs(want)
+            scale = float(np.abs(g["grad_main_%d" % i]).max())
+            torch.testing.assert_close(md.grad.cpu(), _t(g["grad_main_%d" % i]), rtol=1e-4, atol=1e-5 * scale)
+            torch.testing.assert_close(ad.grad.cpu(), _t(g["grad_aux_%d" % i]), rtol=1e-4, atol=1e-5 * scale)
+        np.testing.assert_allclose(crit.iou(), g["iou"], rtol=1e-6, atol=0)
+        assert abs(float(crit.iou()[[1, 2, 3]].mean() * 100) - float(g["miou"])) < 1e-3
+        assert crit.iou_batches == 3 and int(crit.iou_counts[2].sum()) == 3 * 2 * 24 * 40 - 4
+
+
 LOWRES_GEOMETRIES = [
     # (B, K, H, W, (hm, wm), (ha, wa))
     (2, 5, 256, 480, (128, 240), (64, 120)),        # ESPDNetUE on the benchmark crop: x2 main head, x4 aux head, 8-row tiles

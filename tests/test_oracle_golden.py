@@ -189,3 +189,24 @@ def test_visualization_maps_match_reference_golden(golden):
     assert np.array_equal(torchvision.utils.make_grid(O.label_to_rgb(labels, enc)).numpy(), g["tuple_train_train_labels"])
     _, pred_main = torch.max(main, dim=1)
     assert np.array_equal(torchvision.utils.make_grid(O.label_to_rgb(pred_main, enc)).numpy(), g["tensor_val_pred_labels"])
+
+
+def test_train_step_golden(golden):
+    """The oracle's restatements reproduce what the LIVE reference's training-loop statements gave for three batches
+    (uest_seg_multi_os.py:1020-1049): loss, gradients, MIOU areas, and the epoch IoU formed from the two meters."""
+    g = golden("train_step.npz")
+    cw = O.make_class_weights(5, _t(g["class_weights"]).clone(), ignore_idx=4)
+    inter_sum, union_sum = np.zeros(5, np.float32), np.zeros(5, np.float32)
+    for i in range(3):
+        main, aux = _t(g["main_%d" % i]), _t(g["aux_%d" % i])
+        loss, gm, ga = O.training_loss_and_grads(main, aux, _t(g["loss_labels_%d" % i]), cw)
+        assert abs(loss.item() - float(g["loss_%d" % i])) <= 1e-6 * abs(float(g["loss_%d" % i]))
+        _same(gm, _t(g["grad_main_%d" % i]), rtol=1e-5, atol=1e-9)
+        _same(ga, _t(g["grad_aux_%d" % i]), rtol=1e-5, atol=1e-9)
+        inter, union = O.miou_get_iou(main, _t(g["labels_%d" % i]), num_classes=5)
+        assert np.array_equal(inter, g["inter_%d" % i]) and np.array_equal(union, g["union_%d" % i])
+        inter_sum += inter
+        union_sum += union
+    iou = inter_sum / (union_sum + 1e-10)
+    assert np.array_equal(iou, g["iou"])
+    assert abs(float(iou[[1, 2, 3]].mean() * 100) - float(g["miou"])) < 1e-4
