@@ -134,3 +134,68 @@ def test_nid_loss_matches_reference(ref):
     gg, = torch.autograd.grad(got, b)
     _close(got.detach(), want.detach(), rtol=1e-6, atol=1e-6)
     _close(gg, gw, rtol=1e-5, atol=1e-6)
+
+
+def _sweep_cases(count, seed):
+    import random
+    rng = random.Random(seed)
+    out = []
+    for i in range(count):
+        srcs = rng.sample(SOURCES, rng.choice([1, 2, 3]))
+        out.append((i, srcs, rng.choice([(1, 7, 9), (2, 16, 24), (1, 1, 40), (3, 12, 5)]), rng.choice([0.05, 1.0, 3.0, 12.0, 40.0]),
+                    rng.random() < 0.3, rng.choice([None, "half", "all", 1, 2, 3])))
+    return out
+
+
+@pytest.mark.parametrize("case", _sweep_cases(24, seed=606), ids=lambda c: "ref%02d" % c[0])
+def test_oracle_sweep_against_live_reference(ref, case):
+    """Seeded sweep of the oracle against the LIVE reference: source subsets and orders, shapes, logit scales from 0.05 to 40,
+    quantised logits (exact ties -> first-index rules of np.argmax / merge_outputs), every vote policy; then the loss and the
+    training loop's metric statements on the same tensors."""
+    i, srcs, (n, h, w), sigma, ties, policy = case
+    gen = torch.Generator().manual_seed(7000 + i)
+    mains, auxs = [], []
+    for _, c in srcs:
+        m = sigma * torch.randn(n, c, h, w, generator=gen)
+        a = m + 0.5 * sigma * torch.randn(n, c, h, w, generator=gen)
+        if ties:
+            m, a = torch.round(m), torch.round(2 * a) / 2
+        mains.append(m), auxs.append(a)
+    luts = [O.LUTS[s] for s, _ in srcs]
+    got, got_ca = O.multi_source_labels(mains, auxs, luts, policy)
+    want_ca = np.zeros(5)
+    for j in range(n):
+        per = []
+        for (name, _), m, a in zip(srcs, mains, auxs):
+            out, kld = ref.uest.get_output(FixedLogitsModel(m[j:j + 1], a[j:j + 1]), torch.zeros(1), device='cpu')
+            o2, k2 = O.get_output_from_logits(m[j:j + 1], a[j:j + 1])
+            _close(o2, out, atol=0)
+            _close(k2, kld, rtol=1e-6, atol=4e-7 * max(1.0, sigma))
+            amax = np.asarray(np.argmax(out.transpose(1, 2, 0), axis=2), dtype=np.uint8)
+            per.append(getattr(ref.greenhouse, "id_%s_to_greenhouse" % name)[amax])
+        want = ref.uest.merge_outputs(np.array(per), seg_classes=5, thresh=policy)
+        assert np.array_equal(got[j], want)
+        for k in range(5):                                      # class_array as the loop accumulates it (:919-921)
+            want_ca[k] += (want == k).sum()
+    assert np.array_equal(got_ca, want_ca)
+
+    # loss + metric on the first source's first five classes
+    k = min(5, mains[0].shape[1])
+    main, aux = mains[0][:, :k].contiguous(), auxs[0][:, :k].contiguous()
+    target = torch.randint(0, k, (n, h, w), generator=gen)
+    cw = torch.rand(k, generator=gen) * 3
+    crit = ref.seg_loss.UncertaintyWeightedSegmentationLoss(k, class_weights=cw.clone(), ignore_idx=k - 1, device='cpu')
+    m, a = main.clone().requires_grad_(True), aux.clone().requires_grad_(True)
+    kld = ref.seg_loss.PixelwiseKLD()(m, a)
+    loss = crit(m + 0.5 * a, target, kld) * 20 + kld.mean()
+    gm, ga = torch.autograd.grad(loss, (m, a))
+    l_o, gm_o, ga_o = O.training_loss_and_grads(main, aux, target, O.make_class_weights(k, cw.clone(), k - 1))
+    _close(l_o, loss.detach(), rtol=1e-6, atol=1e-12)
+    _close(gm_o, gm, rtol=1e-6, atol=1e-10), _close(ga_o, ga, rtol=1e-6, atol=1e-10)
+    from utilities.metrics.segmentation_miou import MIOU
+    tgt = target.clone()
+    tgt[0, 0, :2] = 255
+    inter, union = MIOU(num_classes=k).get_iou(main, tgt) if k > 1 else (None, None)
+    if k > 1:
+        i_o, u_o = O.miou_get_iou(main, tgt, num_classes=k)
+        assert np.array_equal(i_o, inter) and np.array_equal(u_o, union)
