@@ -32,7 +32,7 @@ extern "C" {
 #define MSPL_API
 #endif
 
-#define MSPL_ABI_VERSION 3
+#define MSPL_ABI_VERSION 4
 #define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
 #define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
 #define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14) */
@@ -81,9 +81,10 @@ MSPL_API int mspl_softmax_kld(const float* main_logits, const float* aux_logits,
  *   class_hist      K u64, += number of pixels per label (the reference's class_array)
  *   conf_hist       K*MSPL_RADIX_BINS u64 or NULL, += linear histogram of conf per label (bin = min(2047, floor(conf*2048)),
  *                   the input of mspl_bracket_select), restricted to pixels with (pixel_index_in_image % ds_rate) == 0
- *   marginal_count  u64 or NULL, += pixels where some source's top-2 softmax margin is < 1e-6 (and, for
- *                   MSPL_POLICY_PROB, the top-2 margin of F): the only pixels whose label may legitimately
- *                   differ from the reference's argmax-of-softmax */
+ *   marginal_count  u64 or NULL, += pixels where, for some source, the softmax margin between the best class of its
+ *                   winning target and the best class of any OTHER target is < 1e-6 (and, for MSPL_POLICY_PROB, the
+ *                   top-2 margin of F): the only pixels whose label may legitimately differ from the reference's
+ *                   argmax-of-softmax (a near-tie between two source classes of the same target cannot change it) */
 MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
                       const int* num_classes, const uint8_t* const* lut, int64_t num_images,
                       int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,
@@ -99,9 +100,9 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
  * 8*sum(C_s) to ~1.25*sum(C_s) bytes per output pixel for the x2 / x4 heads of ESPDNetUE.
  * Needs every row length (main/aux width) to be a multiple of 4 and out_h*out_w % 4 == 0; returns MSPL_ERR_UNSUPPORTED when
  * the tile's source rows do not fit in shared memory (very wide images): upsample and call mspl_fuse_sources instead.
- * Contract: pixels whose head maxima sit more than 16 logit units above the fused maximum (heads that disagree that strongly)
- * or whose fused logits exceed +-48 keep the shared-exponential confidence -- up to ~3e-5 relative error at 64 units / |z| = 256,
- * clamped to [0,1] -- no slow path here. */
+ * Pixels whose head maxima sit more than 16 logit units above the fused maximum (heads that disagree that strongly) or whose
+ * fused logits exceed +-48 take a per-pixel slow path that re-interpolates the pixel's logits from global memory and evaluates
+ * the softmax directly, like mspl_fuse_sources: the 1e-5 confidence tolerance holds for any input. */
 MSPL_API int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,
                              const int* num_classes, const uint8_t* const* lut, const int* main_hw, const int* aux_hw,
                              int64_t num_images, int out_h, int out_w, int num_target_classes, int policy, int vote_t,
@@ -138,8 +139,14 @@ MSPL_API int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t nu
  *     (u32, capacity num_pixels; *cand_count u64 zeroed by the caller) and provisionally ignored.  Writes final_label /
  *     ignore_mask (either may be NULL) and += final_hist (K u64, NULLable).  num_pixels < 2^32.
  *   for pass = 0, 1, 2: mspl_cand_hist_pass (radix histogram of the candidates only); [all-reduce hist];
- *     mspl_cand_select (zeroes hist; after pass 2 thresh is final).
+ *     mspl_cand_select (zeroes hist; after pass 2 thresh is final).  final_hist (K u64, NULLable): after pass 2, the number
+ *     of candidates that reach the threshold moves from final_hist[ignore_label] to final_hist[k] -- read off the (all-reduced)
+ *     histograms, so the patch is the global one and identical on every rank; pass final_hist = NULL to mspl_cand_apply then.
+ *     A class with floor(n_k*portion) == 0 (threshold 1.0) takes part in the passes only to count its conf >= 1.0 candidates.
  *   mspl_cand_apply: candidates with conf >= thresh[label] get their label back (final_label, ignore_mask, final_hist).
+ *   mspl_cand_resolve: the three candidate passes, their selects and mspl_cand_apply in ONE launch, for callers with no
+ *     all-reduce to run in between (a single rank): one 8-CTA thread-block cluster per class, per-CTA candidate cache in
+ *     shared memory, histograms combined over distributed shared memory.  final_hist gets this call's own patch.
  *
  * (2) Generic radix -- 3 full passes over the order-preserving fp32 key (11+11+10 bits), 16 B/pixel with
  *   mspl_apply_thresholds: zero `hist` and `state`; for pass = 0, 1, 2: mspl_radix_hist_pass; [all-reduce hist];
@@ -158,7 +165,11 @@ MSPL_API int mspl_cand_hist_pass(const uint8_t* label, const float* conf, const 
                         const unsigned long long* cand_count, int64_t pixels_per_image, int num_target_classes,
                         int pass, const void* state, unsigned long long* hist, int ds_rate, void* stream);
 MSPL_API int mspl_cand_select(unsigned long long* hist, int num_target_classes, int pass, void* state, float* thresh,
-                     void* stream);
+                     unsigned long long* final_hist, int ignore_label, void* stream);
+MSPL_API int mspl_cand_resolve(const uint8_t* label, const float* conf, const uint32_t* cand_index,
+                      const unsigned long long* cand_count, int64_t pixels_per_image, int num_target_classes,
+                      int ignore_label, int ds_rate, void* state, float* thresh, uint8_t* final_label,
+                      uint8_t* ignore_mask, unsigned long long* final_hist, void* stream);
 MSPL_API int mspl_cand_apply(const uint8_t* label, const float* conf, const float* thresh, const uint32_t* cand_index,
                     const unsigned long long* cand_count, int num_target_classes, int ignore_label,
                     uint8_t* final_label, uint8_t* ignore_mask, unsigned long long* final_hist, void* stream);

@@ -28,7 +28,8 @@ SIGNATURES = {
     "mspl_bracket_select": (c_int, [c_vp, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_bracket_classify": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_cand_hist_pass": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
-    "mspl_cand_select": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "mspl_cand_select": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "mspl_cand_resolve": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_cand_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "mspl_radix_hist_pass": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "mspl_radix_select": (c_int, [c_vp, c_int, c_int, c_f64, c_vp, c_vp, c_vp, c_vp]),

@@ -1,16 +1,16 @@
 // K1 -- fused multi-source pseudo-label generation.
 //
 // One pass over HBM: every (main, aux) logit of every source is read exactly once; per pixel the kernel produces the
-// voted / fused label (u8), its confidence, the mean main-vs-aux KLD, and accumulates the class histogram plus radix
-// pass 0 of the per-class confidence histogram in shared memory.  Replaces uest_seg_multi_os.py:897-921 (+ :669-718)
+// voted / fused label (u8), its confidence, the mean main-vs-aux KLD, and accumulates the class histogram plus the linear
+// per-class confidence histogram in shared memory.  Replaces uest_seg_multi_os.py:897-921 (+ :669-718)
 // -- see include/mspl_b200.h.
 //
-// Two load mechanisms share all the per-pixel math below:
-//   fuse_sources_direct_kernel : every thread streams its own pixels with 128-bit ld.global.nc (any shape/alignment
-//                                when P=1; needs hw % 4 == 0 and 16-byte bases when P=4)
+// Two load mechanisms share all the per-pixel math (pixel_math.cuh):
+//   fuse_sources_direct_kernel : every thread streams its own pixel with ld.global.nc (any shape / alignment)
 //   fuse_sources_tma_kernel    : a producer warp stages [classes-chunk x tile-of-pixels] boxes into a shared-memory
 //                                ring with bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
 //                                consumer warps compute from shared memory; bytes in flight no longer cost registers
+// Both visit a source's classes grouped by target class (ClassOrder), see pixel_math.cuh.
 #pragma once
 #include "pixel_math.cuh"
 #include "bilinear.cuh"
@@ -34,6 +34,7 @@ struct FuseParams {
     float* kld[MSPL_MAX_SOURCES];
     int C[MSPL_MAX_SOURCES];
     uint8_t lut[MSPL_MAX_SOURCES][MSPL_MAX_SRC_CLASSES];
+    ClassOrder order[MSPL_MAX_SOURCES];
     int S, K, policy, vote_t, ignore, ds_rate;
     int64_t n_img, hw;
     uint8_t* label;
@@ -45,16 +46,19 @@ struct FuseParams {
     LowresGeom lr;
 };
 
-// Shared-memory bookkeeping common to both kernels: [K*2048 u32 conf histogram][8 u32 class counts][S*256 B tables]
-inline size_t fuse_tally_smem_bytes(int K) {
-    // [K*2048 hist][16 u32: class counts + spare][tables] (+16: padded-class table reads)
-    return sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 16) + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;
+// Shared-memory bookkeeping common to all kernels:
+//   [K*2048 u32 conf histogram][16 u32: class counts + spare][S*256 B label tables][S*256 B class visiting order][16 B slack]
+//   [KT * nthreads * P floats: committed group maxima, one column per thread]
+inline size_t fuse_tally_smem_bytes(int K, int KT, int nthreads, int P) {
+    size_t b = sizeof(uint32_t) * ((size_t)K * MSPL_RADIX_BINS + 16) + 2 * MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;
+    b = (b + 15) & ~(size_t)15;
+    return b + sizeof(float) * (size_t)KT * nthreads * P;
 }
 
 // ---- per-pixel accumulation across sources --------------------------------------------------------------------------
 // GK: per-target-class probabilities needed (policy 'prob', or a vote threshold below S); otherwise every source voted
 // for the winning label and G_s[label] is simply that source's max probability.
-template <int P, int K, bool GK, bool TOP2>
+template <int P, int K, bool GK>
 struct PixelFusion {
     float usum[P], csum[P], Fk[GK ? K : 1][P];
     uint32_t votes[P];
@@ -72,52 +76,53 @@ struct PixelFusion {
         }
     }
 
-    // fold one finished source in; d receives its KLD map values.  gm/ga: this thread's first pixel, class 0, of the
-    // source's two heads in global memory (only touched on the degenerate slow path).
-    MSPL_DEVINL void add_source(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P],
-                                const float* __restrict__ gm, const float* __restrict__ ga, int C, int64_t hw) {
+    // Fold one finished source in; d receives its KLD map values.  group: this thread's column of committed group maxima
+    // (g_k = max z over the source classes mapped to target k), present: targets the source's table maps to at all.
+    // slow: the kernel's out-of-line recomputations, slow.pmax(p, Mz) for a degenerate pixel and slow.label(p) for an exact
+    // tie between two targets (only those touch global memory again).
+    template <typename Slow>
+    MSPL_DEVINL void add_source(const SourceStats<P>& st, const Px<P>* group, int gstride, uint32_t present, float (&d)[P], Slow slow) {
+        SourceScalars sc[P];
+        unpack_stats<P>(st, sc);
+        float g[K][P];
+        const Px<P>* next = group;          // committed in ascending target order: one entry per target that is present
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if ((present >> k) & 1u) {
+                next->get(g[k]);
+                next += gstride;
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p) g[k][p] = -INFINITY;
+            }
+        }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            SourceResult r = finish_source<P>(st, p);
-            if (r.degenerate) {
-                r.rz = st.Mz[p];
-                r.inv_sz = r.pmax = recompute_pmax(gm + p, ga + p, C, hw, st.Mz[p]);
+            // the source's proposal: the target whose group holds the largest z; the runner-up target gives the near-tie
+            // report and detects exact ties between targets
+            float best = g[0][p], second = -INFINITY;
+            int lab = 0;
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                second = fmaxf(second, fminf(best, g[k][p]));
+                lab = (g[k][p] > best) ? k : lab;
+                best = fmaxf(best, g[k][p]);
             }
+            SourceResult r = finish_source(sc[p], best);
+            if (r.degenerate) {
+                r.rz = best;
+                r.inv_sz = r.pmax = slow.pmax(p, best);
+            }
+            if (second == best) lab = slow.label(p);     // first maximal class in ORIGINAL order decides (np.argmax, :904)
             d[p] = r.kld;
             usum[p] += r.kld;
-            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
-            const int lab = s_lut_s[st.amax[p]];
+            marg[p] |= (1.0f - exp_neg(second - best)) * r.pmax < kNearTieMargin;
             votes[p] += 1u << (4 * lab);
             last_lab[p] = lab;
             if (GK) {
 #pragma unroll
                 for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
-                    Fk[k][p] += fminf(exp_neg(zk[k][p] - r.rz) * r.inv_sz, 1.0f);
-            } else {
-                csum[p] += r.pmax;
-            }
-        }
-    }
-
-    // K1-lowres has no full-resolution logits to recompute from: a degenerate pixel (head maxima more than 16 logit units above the fused maximum)
-    // falls back to the exact-but-underflow-prone shared-exponential value, clamped to a valid probability.
-    MSPL_DEVINL void add_source_lowres(const SourceStats<P>& st, const float (&zk)[K][P], const uint8_t* s_lut_s, float (&d)[P]) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            SourceResult r = finish_source<P>(st, p);
-            if (r.degenerate) {
-                r.pmax = fminf(fmaxf(r.pmax, 0.f), 1.f);
-                if (!(r.pmax == r.pmax)) r.pmax = 1.f;
-            }
-            d[p] = r.kld;
-            usum[p] += r.kld;
-            if (TOP2) marg[p] |= (1.0f - exp_neg(st.z2[p] - st.Mz[p])) * r.pmax < kNearTieMargin;
-            const int lab = s_lut_s[st.amax[p]];
-            votes[p] += 1u << (4 * lab);
-            last_lab[p] = lab;
-            if (GK) {
-#pragma unroll
-                for (int k = 1; k < K; ++k) Fk[k][p] += fminf(exp_neg(zk[k][p] - r.rz) * r.inv_sz, 1.0f);
+                    Fk[k][p] += fminf(exp_neg(g[k][p] - r.rz) * r.inv_sz, 1.0f);
             } else {
                 csum[p] += r.pmax;
             }
@@ -143,7 +148,7 @@ struct PixelFusion {
                 }
                 label[p] = bk;
                 conf[p] = best;
-                if (TOP2) marg[p] |= (best - second) < kNearTieMargin;
+                marg[p] |= (best - second) < kNearTieMargin;
             } else {
                 int bk = 0;
                 uint32_t bc = votes[p] & 15u;
@@ -164,9 +169,11 @@ struct PixelFusion {
                 // which transfer_output_to_greenhouse never fills (G[0] = 0, uest_seg_multi_os.py:1340)
                 float f = (label[p] == 0) ? 0.f : csum[p];
                 if (GK) {
-                    f = 0.f;
+                    // F[label] by masking (a select chain over k gets turned into an indexed load of Fk from LOCAL memory)
+                    uint32_t bits = 0;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) f = (label[p] == k) ? Fk[GK ? k : 0][p] : f;
+                    for (int k = 0; k < K; ++k) bits |= __float_as_uint(Fk[GK ? k : 0][p]) & (0u - (uint32_t)(label[p] == k));
+                    f = __uint_as_float(bits);
                 }
                 conf[p] = (label[p] == ignore) ? 0.f : f * inv_s;
             }
@@ -228,71 +235,102 @@ struct Tally {
     }
 };
 
-MSPL_DEVINL void tally_smem_init(const FuseParams& prm, unsigned char* smem, uint32_t*& s_hist, uint32_t*& s_cls, uint8_t*& s_lut,
-                                 int nthreads) {
+// Carves the bookkeeping region (layout: fuse_tally_smem_bytes) and initialises it; the caller syncs.
+struct TallySmem {
+    uint32_t* hist;
+    uint32_t* cls;
+    uint8_t* lut;       // [S][256] label tables (slow paths, labels-only kernel)
+    uint8_t* row;       // [S][256] class visiting order
+    float* group;       // [KT][nthreads][P]
+};
+MSPL_DEVINL TallySmem tally_smem_init(const FuseParams& prm, unsigned char* smem, int nthreads) {
+    TallySmem t;
     const int nbins = prm.K * MSPL_RADIX_BINS;
-    s_hist = reinterpret_cast<uint32_t*>(smem);
-    s_cls = s_hist + nbins;
-    s_lut = reinterpret_cast<uint8_t*>(s_cls + 16);
-    for (int i = threadIdx.x; i < nbins; i += nthreads) s_hist[i] = 0;
-    if (threadIdx.x < 16) s_cls[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += nthreads)
-        s_lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
+    t.hist = reinterpret_cast<uint32_t*>(smem);
+    t.cls = t.hist + nbins;
+    t.lut = reinterpret_cast<uint8_t*>(t.cls + 16);
+    t.row = t.lut + MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES;
+    size_t off = sizeof(uint32_t) * ((size_t)nbins + 16) + 2 * MSPL_MAX_SOURCES * MSPL_MAX_SRC_CLASSES + 16;
+    off = (off + 15) & ~(size_t)15;
+    t.group = reinterpret_cast<float*>(smem + off);
+    for (int i = threadIdx.x; i < nbins; i += nthreads) t.hist[i] = 0;
+    if (threadIdx.x < 16) t.cls[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += nthreads) {
+        t.lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
+        t.row[i] = prm.order[i / MSPL_MAX_SRC_CLASSES].row[i % MSPL_MAX_SRC_CLASSES];
+    }
+    return t;
 }
 
-template <int K, int P>
-MSPL_DEVINL void reset_zk(float (&zk)[K][P]) {
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int p = 0; p < P; ++p) zk[k][p] = -INFINITY;
-}
+// Slow paths of the full-resolution kernels: re-read the pixel's logits from global memory.  Only coordinates are kept; the
+// pointers are formed inside the (rare) branch so that the common path pays nothing for them.
+template <int P>
+struct GlobalSlowPath {
+    const FuseParams& prm;
+    int s;
+    int64_t n, off;       // image, this thread's first pixel inside it
+    const uint8_t* lut;
+    MSPL_DEVINL float pmax(int p, float Mz) const {
+        const int64_t o = ((int64_t)n * prm.C[s]) * prm.hw + off + p;
+        return recompute_pmax(prm.main[s] + o, prm.aux[s] + o, prm.C[s], prm.hw, Mz);
+    }
+    MSPL_DEVINL int label(int p) const {
+        const int64_t o = ((int64_t)n * prm.C[s]) * prm.hw + off + p;
+        return recompute_label(prm.main[s] + o, prm.aux[s] + o, prm.C[s], prm.hw, lut);
+    }
+};
 
 // ======================================================================================================================
-// Direct-load kernel.  P: pixels per thread (vector width), CH: classes per chunk, KT: compile-time bound on the target
-// classes (prm.K <= KT; classes in [prm.K, KT) never receive votes or probability).
+// Direct-load kernel (fallback for unaligned / odd shapes).  One pixel per thread, CH: classes per chunk, KT: compile-time
+// bound on the target classes (prm.K <= KT; classes in [prm.K, KT) never receive votes or probability).
 // ======================================================================================================================
-template <int P, int CH, int KT, bool GK, bool TOP2, int THREADS, int MINB>
+template <int CH, int KT, bool GK, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(const __grid_constant__ FuseParams prm) {
+    constexpr int P = 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *s_hist, *s_cls;
-    uint8_t* s_lut;
-    tally_smem_init(prm, smem_raw, s_hist, s_cls, s_lut, THREADS);
+    const TallySmem ts = tally_smem_init(prm, smem_raw, THREADS);
     __syncthreads();
 
     const int S = prm.S;
     const float fS = 1.0f / (float)S;
     const int64_t hw = prm.hw;
-    const int64_t gpi = hw / P;                       // pixel groups per image
-    const int64_t n_groups = prm.n_img * gpi;
+    const int64_t n_groups = prm.n_img * hw;
     const int64_t n_tiles = (n_groups + THREADS - 1) / THREADS;
     Tally<KT> tally;
+    Px<P>* group = reinterpret_cast<Px<P>*>(ts.group) + threadIdx.x;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t g = tile * THREADS + threadIdx.x;
         const bool active = g < n_groups;
         g = active ? g : n_groups - 1;
-        const int64_t n = g / gpi;
-        const int64_t off = (g - n * gpi) * P;       // first pixel of the group inside its image
+        const int64_t n = g / hw;
+        const int64_t off = g - n * hw;
 
-        PixelFusion<P, KT, GK, TOP2> fus;
+        PixelFusion<P, KT, GK> fus;
         fus.reset();
         for (int s = 0; s < S; ++s) {
             const int C = prm.C[s];
             const float* pm = prm.main[s] + (n * C) * hw + off;
             const float* pa = prm.aux[s] + (n * C) * hw + off;
+            const uint8_t* row = ts.row + s * MSPL_MAX_SRC_CLASSES;
             SourceStats<P> st;
-            st.reset();
-            float zk[KT][P];
-            reset_zk<KT, P>(zk);
+            st.reset(group);
             for (int c0 = 0; c0 < C; c0 += CH) {
-                const int cn = min(CH, C - c0);
-                float m[CH][P], a[CH][P];
-                load_chunk<P, CH>(pm + c0 * hw, pa + c0 * hw, hw, cn, m, a);
-                fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                Px<P> m[CH], a[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    float mv[1] = {kPadLogit}, av[1] = {kPadLogit};
+                    if (c0 + j < C) {
+                        PixVec<1>::load(pm + (int64_t)row[c0 + j] * hw, mv);
+                        PixVec<1>::load(pa + (int64_t)row[c0 + j] * hw, av);
+                    }
+                    m[j] = Px<P>::make(mv);
+                    a[j] = Px<P>::make(av);
+                }
+                fold_chunk<P, CH>(st, m, a, c0 == 0, prm.order[s].seg[c0 / CH], THREADS);
             }
             float d[P];
-            fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d, pm, pa, C, hw);
+            fus.add_source(st, group, THREADS, prm.order[s].present, d, GlobalSlowPath<P>{prm, s, n, off, ts.lut + s * MSPL_MAX_SRC_CLASSES});
             if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
         }
         int label[P];
@@ -304,9 +342,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(cons
             if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
             if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
         }
-        tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
+        tally.template add<P>(prm, ts.hist, label, conf, fus.marg, off, active);
     }
-    tally.flush(prm, s_hist, s_cls, THREADS);
+    tally.flush(prm, ts.hist, ts.cls, THREADS);
 }
 
 // ======================================================================================================================
@@ -366,13 +404,20 @@ template <> MSPL_DEVINL void lds<4>(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
+// P pixels of one class row straight into the packed form
+template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
+    float v[P];
+    lds<P>(p, v);
+    return Px<P>::make(v);
+}
 
 }  // namespace tma
 
-// 1: the first chunk of a source skips the rescale of the (empty) accumulators, which makes the compiler peel that
-// iteration (two copies of the chunk body, ~38 KB of code); 0: one copy, the rescale runs on empty accumulators too.
+// 1: the first chunk of a source skips the rescale of the (empty) accumulators -- a branch around it whose merge costs ~20
+// register moves per chunk in the generated code; 0 (default): the rescale runs on the empty accumulators too (it evaluates
+// to exact zeros, see SourceStats::reset) and the chunk body is branch-free.
 #ifndef MSPL_PEEL_FIRST
-#define MSPL_PEEL_FIRST 1
+#define MSPL_PEEL_FIRST 0
 #endif
 
 template <int NCW, int P, int CH, int NSTAGE>
@@ -381,7 +426,9 @@ struct TmaCfg {
     static constexpr int kTilePix = NCW * 32 * P;
     static constexpr int kStageFloats = 2 * CH * kTilePix;
     static constexpr size_t kRingBytes = sizeof(float) * (size_t)kStageFloats * NSTAGE;
-    static size_t smem_bytes(int K) { return kRingBytes + 2 * NSTAGE * sizeof(uint64_t) + fuse_tally_smem_bytes(K) + 128; }
+    static size_t smem_bytes(int K, int KT) {
+        return kRingBytes + 2 * NSTAGE * sizeof(uint64_t) + fuse_tally_smem_bytes(K, KT, kThreads, P) + 128;
+    }
 };
 
 // (image, tile inside the image) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a 64-bit division per tile.
@@ -399,8 +446,9 @@ struct TileWalker {
 };
 
 // Producer warp of the TMA-staged kernels: walks this CTA's tiles in (tile, source, chunk) order and fills the ring.
+// s_row: per-source class visiting order ([S][256] bytes in shared memory), or nullptr for the original class order.
 template <int NCW, int P, int CH, int NSTAGE>
-MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t* full, uint64_t* empty, int lane) {
+MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t* full, uint64_t* empty, int lane, const uint8_t* s_row) {
     using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
     constexpr int TP = Cfg::kTilePix;
     const int S = prm.S;
@@ -438,7 +486,8 @@ MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t*
                 if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], 2 * cn * row_bytes);   // release: publishes the padding too
                 for (int j = lane; j < 2 * cn; j += 32) {
                     const int head = j >= cn, c = head ? j - cn : j;
-                    const float* src = (head ? pa : pm) + (int64_t)(c0 + c) * hw;
+                    const int cls = s_row ? (int)s_row[s * MSPL_MAX_SRC_CLASSES + c0 + c] : c0 + c;
+                    const float* src = (head ? pa : pm) + (int64_t)cls * hw;
                     tma::bulk_g2s(dst + (head * CH + c) * TP, src, row_bytes, &full[stage], policy);
                 }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -447,7 +496,7 @@ MSPL_DEVINL void tma_produce_tiles(const FuseParams& prm, float* ring, uint64_t*
     }
 }
 
-template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2>
+template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(const __grid_constant__ FuseParams prm) {
     using Cfg = TmaCfg<NCW, P, CH, NSTAGE>;
     constexpr int TP = Cfg::kTilePix;
@@ -455,9 +504,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kRingBytes);
     uint64_t* empty = full + NSTAGE;
-    uint32_t *s_hist, *s_cls;
-    uint8_t* s_lut;
-    tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, Cfg::kThreads);
+    const TallySmem ts = tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), Cfg::kThreads);
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             tma::mbar_init(&full[i], 1);
@@ -475,43 +522,43 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
     Tally<KT> tally;
 
     if (warp == NCW) {
-        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane);
+        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane, ts.row);
     } else {
         // ------------------------------- consumer warps -------------------------------
         const float fS = 1.0f / (float)S;
         int stage = 0;
         uint32_t phase = 0;
         const int px = (warp * 32 + lane) * P;          // this thread's first pixel inside the tile
+        Px<P>* group = reinterpret_cast<Px<P>*>(ts.group) + threadIdx.x;
         TileWalker walk(blockIdx.x, gridDim.x, tpi);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, walk.next()) {
             const int64_t n = walk.image;
             const int64_t off = walk.tile_in_image * TP + px;
             const bool active = off < hw;                 // partial last tile: the ring holds stale values past the image
-            PixelFusion<P, KT, GK, TOP2> fus;
+            PixelFusion<P, KT, GK> fus;
             fus.reset();
             for (int s = 0; s < S; ++s) {
                 const int C = prm.C[s];
                 SourceStats<P> st;
-                st.reset();
-                float zk[KT][P];
-                reset_zk<KT, P>(zk);
+                st.reset(group);
+                int chunk = 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += CH) {
-                    float m[CH][P], a[CH][P];
+                for (int c0 = 0; c0 < C; c0 += CH, ++chunk) {
+                    Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * Cfg::kStageFloats + px;
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + j * TP, m[j]);
+                    for (int j = 0; j < CH; ++j) m[j] = tma::lds_px<P>(src + j * TP);
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) tma::lds<P>(src + (CH + j) * TP, a[j]);
+                    for (int j = 0; j < CH; ++j) a[j] = tma::lds_px<P>(src + (CH + j) * TP);
                     __syncwarp();
                     if (lane == 0) tma::mbar_arrive(&empty[stage]);    // values are in registers: hand the slot back
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, MSPL_PEEL_FIRST ? c0 == 0 : false, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                    fold_chunk<P, CH>(st, m, a, MSPL_PEEL_FIRST ? c0 == 0 : false, prm.order[s].seg[chunk], Cfg::kThreads);
                 }
                 float d[P];
-                const int64_t goff = (n * C) * hw + (active ? off : 0);
-                fus.add_source(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d, prm.main[s] + goff, prm.aux[s] + goff, C, hw);
+                fus.add_source(st, group, Cfg::kThreads, prm.order[s].present, d,
+                               GlobalSlowPath<P>{prm, s, n, active ? off : 0, ts.lut + s * MSPL_MAX_SRC_CLASSES});
                 if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
             }
             int label[P];
@@ -523,17 +570,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                 if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
                 if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
             }
-            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
+            tally.template add<P>(prm, ts.hist, label, conf, fus.marg, off, active);
         }
     }
-    tally.flush(prm, s_hist, s_cls, Cfg::kThreads);
+    tally.flush(prm, ts.hist, ts.cls, Cfg::kThreads);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Labels-only variant: what the reference's generation loop actually keeps (uest_seg_multi_os.py:900-921 discards the KLD and
 // never forms a confidence).  With no confidence, uncertainty or histogram of confidences requested there is nothing to
 // exponentiate: per class and pixel the consumers do z = m + a/2 and a running first-argmax (4 instructions), so the kernel
-// is HBM-bound with a wide margin even at reduced clocks.  Same ring, same producer.
+// is HBM-bound with a wide margin even at reduced clocks.  Same ring, same producer (original class order).
 // ----------------------------------------------------------------------------------------------------------------------
 template <int NCW, int P, int CH, int NSTAGE, int KT>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(const __grid_constant__ FuseParams prm) {
@@ -543,9 +590,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(cons
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kRingBytes);
     uint64_t* empty = full + NSTAGE;
-    uint32_t *s_hist, *s_cls;
-    uint8_t* s_lut;
-    tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, Cfg::kThreads);
+    const TallySmem ts = tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), Cfg::kThreads);
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             tma::mbar_init(&full[i], 1);
@@ -561,7 +606,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Tally<KT> tally;
     if (warp == NCW) {
-        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane);
+        tma_produce_tiles<NCW, P, CH, NSTAGE>(prm, ring, full, empty, lane, nullptr);
     } else {
         int stage = 0;
         uint32_t phase = 0;
@@ -601,7 +646,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(cons
                         }
                 }
 #pragma unroll
-                for (int p = 0; p < P; ++p) votes[p] += 1u << (4 * s_lut[s * MSPL_MAX_SRC_CLASSES + amax[p]]);
+                for (int p = 0; p < P; ++p) votes[p] += 1u << (4 * ts.lut[s * MSPL_MAX_SRC_CLASSES + amax[p]]);
             }
             int label[P];
             float conf[P];
@@ -620,26 +665,99 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(cons
                 marg[p] = false;
             }
             if (active) store_labels<P>(prm.label + n * hw + off, label);
-            tally.template add<P>(prm, s_hist, label, conf, marg, off, active);
+            tally.template add<P>(prm, ts.hist, label, conf, marg, off, active);
         }
     }
-    tally.flush(prm, s_hist, s_cls, Cfg::kThreads);
+    tally.flush(prm, ts.hist, ts.cls, Cfg::kThreads);
 }
 
 // ======================================================================================================================
 // K1-lowres: the same fusion, reading the sources' logits at their native (pre-upsample) resolution and performing the
 // network's final bilinear align_corners=True interpolation in the consumer warps (next-row component).
 // HBM traffic drops from 8*sum(C) B/pixel to 4*sum(C)*(hm*wm + ha*wa)/(H*W) (1.25*sum(C) for the x2 / x4 heads of
-// ESPDNetUE); the kernel becomes instruction-bound.
+// ESPDNetUE); the kernel is instruction-bound.
 //   A tile is TP consecutive output pixels (row-major) of one image.  For every class of the chunk the producer copies
 //   the block of source rows the tile's output rows interpolate from (whole rows, one bulk copy per class and head).
-//   Arithmetic follows ATen's upsample_bilinear2d: src = dst * (in-1)/(out-1); i = (int)src; lambda = src - i;
-//   val = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
+//   Source coordinates and weights follow ATen's upsample_bilinear2d (src = dst * (in-1)/(out-1); i = (int)src;
+//   lambda = src - i); val = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), evaluated for the thread's two pixels at once
+//   with packed multiplies / fmas: per class, head and PAIR of pixels 8 shared-memory loads + 6 packed instructions.
+//   (A separable variant -- one warp-specialised vertical pass into a second shared-memory ring, then a 2-tap horizontal
+//   pass per pixel -- was built and measured in round 2: 4.45 ms per 200 images with two blender warps against 2.08 ms
+//   for the round-1 four-tap kernel; the vertical pass's address arithmetic and its extra hand-off cost more than the
+//   taps it saves.  Not kept.)
+//   MS / AS: compile-time class strides (floats) of the main / aux blocks inside a stage, or 0 to take them from the
+//   geometry at run time.  With fixed strides every tap of every class is `LDS [tap_register + immediate]`.
 // ======================================================================================================================
-// MS / AS: compile-time class strides (floats) of the main / aux blocks inside a stage, or 0 to take them from the
-// geometry at run time.  With fixed strides every tap of every class is `LDS [tap_register + immediate]`: the per-class
-// address arithmetic disappears from the interpolation loop.
-template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, bool TOP2, int MS = 0, int AS = 0>
+// Slow paths of K1-lowres: re-interpolate one pixel's logits from global memory with the fast path's own arithmetic.
+static __device__ __noinline__ float lowres_logit_global(const float* __restrict__ src, int hin, int win, float rh, float rw, int y, int x) {
+    const float hr = rh * (float)y, wr = rw * (float)x;
+    const int i0 = (int)hr, x0 = (int)wr;
+    const float h1 = hr - (float)i0, h0 = 1.0f - h1, w1 = wr - (float)x0, w0 = 1.0f - w1;
+    const int dy = (i0 < hin - 1) ? win : 0, dx = (x0 < win - 1) ? 1 : 0;
+    const float* p = src + (int64_t)i0 * win + x0;
+    const float top = fmaf(w1, __ldg(p + dx), __fmul_rn(w0, __ldg(p))), bot = fmaf(w1, __ldg(p + dy + dx), __fmul_rn(w0, __ldg(p + dy)));
+    return fmaf(h1, bot, __fmul_rn(h0, top));
+}
+template <int P>
+struct LowresSlowPath {
+    const float* gm;      // class 0 of this image's main / aux head
+    const float* ga;
+    int C, hm, wm, ha, wa;
+    float rhm, rwm, rha, rwa;
+    int yy[P], xx[P];
+    const uint8_t* lut;
+    MSPL_DEVINL float z(int c, int p) const {
+        return fmaf(0.5f, lowres_logit_global(ga + (int64_t)c * ha * wa, ha, wa, rha, rwa, yy[p], xx[p]),
+                    lowres_logit_global(gm + (int64_t)c * hm * wm, hm, wm, rhm, rwm, yy[p], xx[p]));
+    }
+    MSPL_DEVINL float pmax(int p, float Mz) const {
+        float s = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) s += exp_neg(z(c, p) - Mz);
+        return fminf(__frcp_rn(s), 1.0f);
+    }
+    MSPL_DEVINL int label(int p) const {
+        float best = -INFINITY;
+        int arg = 0;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const float v = z(c, p);
+            if (v > best) { best = v; arg = c; }
+        }
+        return lut[arg];
+    }
+};
+
+// One head's bilinear taps of a thread's P pixels: offsets of the four neighbours inside a stage's class block (relative to
+// the first staged source row) and the packed weights.
+template <int P>
+struct PackedTaps {
+    int o00[P], o01[P], o10[P], o11[P];
+    Px<P> w0, w1, h0, h1;
+    MSPL_DEVINL void set(const int (&yy)[P], const int (&xx)[P], int hin, int win, float rh, float rw, int first_row) {
+        float fw0[P], fw1[P], fh0[P], fh1[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const BilinearTap t = make_tap(yy[p], xx[p], hin, win, rh, rw, first_row);
+            o00[p] = t.o00; o01[p] = t.o00 + t.dx; o10[p] = t.o00 + t.dy; o11[p] = t.o00 + t.dy + t.dx;
+            fw0[p] = t.w0; fw1[p] = t.w1; fh0[p] = t.h0; fh1[p] = t.h1;
+        }
+        w0 = Px<P>::make(fw0); w1 = Px<P>::make(fw1); h0 = Px<P>::make(fh0); h1 = Px<P>::make(fh1);
+    }
+    MSPL_DEVINL Px<P> gather(const float* __restrict__ s, const int (&o)[P]) const {
+        float v[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) v[p] = s[o[p]];
+        return Px<P>::make(v);
+    }
+    MSPL_DEVINL Px<P> interpolate(const float* __restrict__ s) const {
+        const Px<P> top = fma(w1, gather(s, o01), w0 * gather(s, o00));
+        const Px<P> bot = fma(w1, gather(s, o11), w0 * gather(s, o10));
+        return fma(h1, bot, h0 * top);
+    }
+};
+
+template <int NCW, int P, int CH, int NSTAGE, int KT, bool GK, int MS = 0, int AS = 0>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(const __grid_constant__ FuseParams prm) {
     constexpr int kThreads = (NCW + 1) * 32;
     constexpr int TP = NCW * 32 * P;
@@ -652,9 +770,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
     const size_t ring_bytes = sizeof(float) * (size_t)stage_floats * NSTAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
     uint64_t* empty = full + NSTAGE;
-    uint32_t *s_hist, *s_cls;
-    uint8_t* s_lut;
-    tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), s_hist, s_cls, s_lut, kThreads);
+    const TallySmem ts = tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), kThreads);
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             tma::mbar_init(&full[i], 1);
@@ -708,8 +824,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                     if (lane == 0) tma::mbar_arrive_expect_tx(&full[stage], cn * (mbytes + abytes));
                     for (int j = lane; j < 2 * cn; j += 32) {
                         const int head = j >= cn, c = head ? j - cn : j;
-                        if (head) tma::bulk_g2s(dst + aux_base + c * aux_stride, pa + (int64_t)(c0 + c) * ha * wa, abytes, &full[stage], policy);
-                        else tma::bulk_g2s(dst + c * main_stride, pm + (int64_t)(c0 + c) * hm * wm, mbytes, &full[stage], policy);
+                        const int cls = ts.row[s * MSPL_MAX_SRC_CLASSES + c0 + c];
+                        if (head) tma::bulk_g2s(dst + aux_base + c * aux_stride, pa + (int64_t)cls * ha * wa, abytes, &full[stage], policy);
+                        else tma::bulk_g2s(dst + c * main_stride, pm + (int64_t)cls * hm * wm, mbytes, &full[stage], policy);
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -721,6 +838,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
         int stage = 0;
         uint32_t phase = 0;
         const int px = (warp * 32 + lane) * P;
+        Px<P>* group = reinterpret_cast<Px<P>*>(ts.group) + threadIdx.x;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t n = tile / tpi;
             const int64_t tile_off = (tile - n * tpi) * TP;
@@ -734,45 +852,39 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 yy[p] = (int)(o / W);
                 xx[p] = (int)(o - (int64_t)yy[p] * W);
             }
-            PixelFusion<P, KT, GK, TOP2> fus;
+            PixelFusion<P, KT, GK> fus;
             fus.reset();
             for (int s = 0; s < S; ++s) {
                 const int C = prm.C[s], hm = lr.hm[s], wm = lr.wm[s], ha = lr.ha[s], wa = lr.wa[s];
                 const float rhm = lowres_scale(hm, H), rwm = lowres_scale(wm, W);
                 const float rha = lowres_scale(ha, H), rwa = lowres_scale(wa, W);
-                const int m0 = (int)(rhm * (float)y_first), a0 = (int)(rha * (float)y_first);
-                BilinearTap tm[P], ta[P];
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    tm[p] = make_tap(yy[p], xx[p], hm, wm, rhm, rwm, m0);
-                    ta[p] = make_tap(yy[p], xx[p], ha, wa, rha, rwa, a0);
-                }
+                PackedTaps<P> tm, ta;
+                tm.set(yy, xx, hm, wm, rhm, rwm, (int)(rhm * (float)y_first));
+                ta.set(yy, xx, ha, wa, rha, rwa, (int)(rha * (float)y_first));
                 SourceStats<P> st;
-                st.reset();
-                float zk[KT][P];
-                reset_zk<KT, P>(zk);
+                st.reset(group);
+                int chunk = 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += CH) {
-                    float m[CH][P], a[CH][P];
+                for (int c0 = 0; c0 < C; c0 += CH, ++chunk) {
+                    Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * stage_floats;
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
-#pragma unroll
-                        for (int p = 0; p < P; ++p) {
-                            m[j][p] = bilinear(src + j * main_stride, tm[p]);
-                            a[j][p] = bilinear(src + aux_base + j * aux_stride, ta[p]);
-                        }
+                        m[j] = tm.interpolate(src + j * main_stride);
+                        a[j] = ta.interpolate(src + aux_base + j * aux_stride);
                     }
                     __syncwarp();
                     if (lane == 0) tma::mbar_arrive(&empty[stage]);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    fold_chunk<P, CH, TOP2, GK, KT>(st, m, a, c0, c0 == 0, s_lut + s * MSPL_MAX_SRC_CLASSES, zk);
+                    fold_chunk<P, CH>(st, m, a, MSPL_PEEL_FIRST ? c0 == 0 : false, prm.order[s].seg[chunk], kThreads);
                 }
                 float d[P];
-                // (the degenerate-pixel slow path would need the full-resolution logits this variant never materialises;
-                //  mspl_fuse_sources_lowres documents the |logit| <= 64 contract instead)
-                fus.add_source_lowres(st, zk, s_lut + s * MSPL_MAX_SRC_CLASSES, d);
+                LowresSlowPath<P> slow{prm.main[s] + (n * C) * hm * wm, prm.aux[s] + (n * C) * ha * wa, C, hm, wm, ha, wa,
+                                       rhm, rwm, rha, rwa, {}, {}, ts.lut + s * MSPL_MAX_SRC_CLASSES};
+#pragma unroll
+                for (int p = 0; p < P; ++p) { slow.yy[p] = yy[p]; slow.xx[p] = xx[p]; }
+                fus.add_source(st, group, kThreads, prm.order[s].present, d, slow);
                 if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
             }
             int label[P];
@@ -784,10 +896,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 if (prm.conf) PixVec<P>::store(prm.conf + o, conf);
                 if (prm.unc) PixVec<P>::store(prm.unc + o, unc);
             }
-            tally.template add<P>(prm, s_hist, label, conf, fus.marg, off, active);
+            tally.template add<P>(prm, ts.hist, label, conf, fus.marg, off, active);
         }
     }
-    tally.flush(prm, s_hist, s_cls, kThreads);
+    tally.flush(prm, ts.hist, ts.cls, kThreads);
 }
 
 }  // namespace mspl

@@ -1,6 +1,7 @@
-// Host-side launch helpers for the two K1 kernels (shared by libmspl_b200.so and tools/k1_sweep).
+// Host-side launch helpers for the K1 kernels (shared by libmspl_b200.so and tools/k1_sweep).
 #pragma once
 #include <algorithm>
+#include <cstring>
 
 #include "fuse_kernel.cuh"
 
@@ -20,10 +21,37 @@ inline DeviceInfo device_info() {
     return d;
 }
 
+// Class visiting order of every source for chunks of `chunk` classes (see ClassOrder in pixel_math.cuh): classes sorted by
+// (target class, class index); per chunk a byte with bit j = slot j ends its target group (chunk <= 8).
+// Needs prm.S, prm.C and prm.lut; returns false when a source has more chunks than ClassOrder::seg holds.
+inline bool build_class_order(FuseParams& prm, int chunk) {
+    if (chunk > 8) return false;
+    for (int s = 0; s < prm.S; ++s) {
+        ClassOrder& o = prm.order[s];
+        memset(&o, 0, sizeof(o));
+        const int C = prm.C[s];
+        if ((C + chunk - 1) / chunk > kMaxChunksPerSource) return false;
+        int i = 0;
+        for (int k = 0; k < MSPL_MAX_CLASSES; ++k)
+            for (int c = 0; c < C; ++c)
+                if (prm.lut[s][c] == k) {
+                    o.row[i++] = (uint8_t)c;
+                    o.present |= 1u << k;
+                }
+        if (i != C) return false;            // a table entry >= MSPL_MAX_CLASSES (callers validate entries < K)
+        for (i = 0; i < C; ++i) {
+            const int k = prm.lut[s][o.row[i]];
+            const bool last = (i == C - 1) || prm.lut[s][o.row[i + 1]] != k;
+            if (last) o.seg[i / chunk] |= (uint8_t)(1u << (i % chunk));
+        }
+    }
+    return true;
+}
+
 // Persistent grid: one wave of resident CTAs, each striding over the pixel tiles.
-template <int P, int THREADS, typename Kern>
-int launch_fuse_direct(Kern kern, const FuseParams& prm, cudaStream_t stream) {
-    const size_t smem = fuse_tally_smem_bytes(prm.K);
+template <int THREADS, typename Kern>
+int launch_fuse_direct(Kern kern, const FuseParams& prm, int KT, cudaStream_t stream) {
+    const size_t smem = fuse_tally_smem_bytes(prm.K, KT, THREADS, 1);
     const DeviceInfo di = device_info();
     int per_sm = 0;
     if (!di.ok || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -31,7 +59,7 @@ int launch_fuse_direct(Kern kern, const FuseParams& prm, cudaStream_t stream) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
-    const int64_t n_groups = prm.n_img * (prm.hw / P);
+    const int64_t n_groups = prm.n_img * prm.hw;
     const int64_t n_tiles = (n_groups + THREADS - 1) / THREADS;
     const int64_t cap = (int64_t)di.sms * per_sm;
     kern<<<(unsigned)(n_tiles < cap ? n_tiles : cap), THREADS, smem, stream>>>(prm);
@@ -40,10 +68,10 @@ int launch_fuse_direct(Kern kern, const FuseParams& prm, cudaStream_t stream) {
 
 // One CTA per SM (the shared-memory ring fills the SM), striding over the tiles.
 template <typename Cfg, typename Kern>
-int launch_fuse_tma(Kern kern, const FuseParams& prm, cudaStream_t stream) {
-    const size_t smem = Cfg::smem_bytes(prm.K);
+int launch_fuse_tma(Kern kern, const FuseParams& prm, int KT, cudaStream_t stream) {
+    const size_t smem = Cfg::smem_bytes(prm.K, KT);
     const DeviceInfo di = device_info();
-    if (!di.ok || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (!di.ok || smem > 227 * 1024 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return MSPL_ERR_CUDA;
     }
@@ -53,8 +81,7 @@ int launch_fuse_tma(Kern kern, const FuseParams& prm, cudaStream_t stream) {
 }
 
 // The bulk-copy path needs 16-byte aligned class rows (bases 16-byte aligned, pixels_per_image % 4 == 0).
-template <typename Cfg>
-bool tma_eligible(const FuseParams& prm) {
+inline bool tma_eligible(const FuseParams& prm) {
     if (prm.hw % 4 != 0) return false;
     for (int s = 0; s < prm.S; ++s)
         if (!aligned_to(prm.main[s], 16) || !aligned_to(prm.aux[s], 16) || (prm.kld[s] && !aligned_to(prm.kld[s], 16))) return false;
@@ -64,7 +91,8 @@ bool tma_eligible(const FuseParams& prm) {
 // ---- K1-lowres ------------------------------------------------------------------------------------------------------
 // Fills prm.lr's stage layout for tiles of `tile_pix` consecutive output pixels; returns the dynamic shared memory the
 // kernel needs with `stages` ring slots, or 0 if the geometry is unsupported (rows not 16-byte multiples).
-inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages, int fixed_main = 0, int fixed_aux = 0) {
+inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages, int KT, int nthreads, int P, int fixed_main = 0,
+                          int fixed_aux = 0) {
     LowresGeom& lr = prm.lr;
     const int rows_spanned = (int)std::min<int64_t>(lr.H, (tile_pix - 1) / lr.W + 2);
     int main_stride = 0, aux_stride = 0;
@@ -86,7 +114,8 @@ inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages, 
     lr.aux_cls_stride = aux_stride;
     lr.aux_base = chunk * main_stride;
     lr.stage_floats = chunk * (main_stride + aux_stride);
-    return sizeof(float) * (size_t)lr.stage_floats * stages + 2 * stages * sizeof(uint64_t) + fuse_tally_smem_bytes(prm.K) + 128;
+    return sizeof(float) * (size_t)lr.stage_floats * stages + 2 * stages * sizeof(uint64_t) +
+           fuse_tally_smem_bytes(prm.K, KT, nthreads, P) + 128;
 }
 
 template <int NCW, int P, typename Kern>

@@ -23,32 +23,34 @@ namespace mspl {
 #define MSPL_LOWRES_STAGES 4
 #endif
 
-// TMA-staged kernel configurations <consumer warps, pixels per thread, classes per chunk, ring stages>, picked from the
-// tools/k1_sweep runs on B200 (profiles/r01_k1_sweep_*.txt):
-//   vote with threshold == S ('all', or a single source): HBM-bound; 15 consumer + 1 producer warps = 16 warps, so the
-//     register file splits evenly (128 regs/thread); 960-pixel tiles, 4 x 38.4 KB stages            -> 99 % of the copy peak
-//   policies that need per-target-class probabilities ('half', int < S, 'prob'): ~25 % more instructions per pixel, so
-//     more consumer warps win; 19 + 1 = 20 warps (96 regs/thread), 1216-pixel tiles, 3 x 48.6 KB stages -> 80 %
-using TmaCfgVoteAll = TmaCfg<15, 2, MSPL_FUSE_CH, 4>;
-using TmaCfgPerClass = TmaCfg<19, 2, MSPL_FUSE_CH, 3>;
+// TMA-staged kernel configuration <consumer warps, pixels per thread, classes per chunk, ring stages>, picked from the
+// tools/k1_sweep runs on B200 (profiles/): 15 consumer + 1 producer warps = 16 warps, so the register file splits evenly
+// (128 regs/thread); 960-pixel tiles, 4 x 38.4 KB stages.  Since round 2 every policy runs this one shape: with the classes
+// visited grouped by target the per-target maxima cost nothing extra per class (pixel_math.cuh), so 'half' / 'prob' differ
+// from 'all' only in the per-source epilogue.  More than 5 target classes: 3 stages (their histogram and group slots need
+// the shared memory of the fourth).
+template <int KT> struct TmaCfgFor { using type = TmaCfg<15, 2, MSPL_FUSE_CH, 4>; static constexpr int kStages = 4; };
+template <> struct TmaCfgFor<8> { using type = TmaCfg<15, 2, MSPL_FUSE_CH, 3>; static constexpr int kStages = 3; };
 constexpr int kDirectThreads = 256;
 
 template <int KT>
-static int dispatch_fuse(const FuseParams& prm, int P, bool gk, cudaStream_t stream) {
+static int dispatch_fuse(FuseParams& prm, bool aligned, bool gk, cudaStream_t stream) {
     constexpr int CH = MSPL_FUSE_CH;
-    if (MSPL_USE_TMA && P == 4 && tma_eligible<TmaCfgVoteAll>(prm)) {
+    using Cfg = typename TmaCfgFor<KT>::type;
+    constexpr int NST = TmaCfgFor<KT>::kStages;
+    if (!build_class_order(prm, CH)) return MSPL_ERR_UNSUPPORTED;
+    if (MSPL_USE_TMA && aligned && tma_eligible(prm)) {
         // nothing but hard labels requested under a vote policy (the reference's own generation loop): no softmax at all
         const bool labels_only = prm.policy == MSPL_POLICY_VOTE && !prm.conf && !prm.unc && !prm.conf_hist && !prm.marginal;
         bool any_kld = false;
         for (int s = 0; s < prm.S; ++s) any_kld = any_kld || prm.kld[s] != nullptr;
-        if (labels_only && !any_kld)
-            return launch_fuse_tma<TmaCfgVoteAll>(fuse_labels_tma_kernel<15, 2, CH, 4, KT>, prm, stream);
-        if (gk) return launch_fuse_tma<TmaCfgPerClass>(fuse_sources_tma_kernel<19, 2, CH, 3, KT, true, true>, prm, stream);
-        return launch_fuse_tma<TmaCfgVoteAll>(fuse_sources_tma_kernel<15, 2, CH, 4, KT, false, true>, prm, stream);
+        if (labels_only && !any_kld) return launch_fuse_tma<Cfg>(fuse_labels_tma_kernel<15, 2, CH, NST, KT>, prm, KT, stream);
+        if (gk) return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<15, 2, CH, NST, KT, true>, prm, KT, stream);
+        return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<15, 2, CH, NST, KT, false>, prm, KT, stream);
     }
     // odd shapes / unaligned views: per-thread scalar streaming loads, same math
-    if (gk) return launch_fuse_direct<1, kDirectThreads>(fuse_sources_direct_kernel<1, CH, KT, true, true, kDirectThreads, 1>, prm, stream);
-    return launch_fuse_direct<1, kDirectThreads>(fuse_sources_direct_kernel<1, CH, KT, false, true, kDirectThreads, MSPL_FUSE_MINB>, prm, stream);
+    if (gk) return launch_fuse_direct<kDirectThreads>(fuse_sources_direct_kernel<CH, KT, true, kDirectThreads, 1>, prm, KT, stream);
+    return launch_fuse_direct<kDirectThreads>(fuse_sources_direct_kernel<CH, KT, false, kDirectThreads, MSPL_FUSE_MINB>, prm, KT, stream);
 }
 
 // merge_outputs (uest_seg_multi_os.py:695-718) on (S, npix) hard labels.
@@ -75,10 +77,10 @@ __global__ void __launch_bounds__(256) vote_labels_kernel(const uint8_t* __restr
 using namespace mspl;
 
 extern "C" const char* mspl_fuse_variant(void) {
-    static char name[224];
+    static char name[256];
     snprintf(name, sizeof(name),
-             "tma-bulk ring, CH=%d: vote-all <15 consumer warps, P=2, 4 stages>, per-class <19, P=2, 3 stages>; "
-             "direct-ldg P=1 fallback for unaligned shapes%s",
+             "tma-bulk ring, CH=%d, classes visited grouped by target, packed f32x2 math: <15 consumer warps, P=2, 4 stages> for "
+             "every policy; direct-ldg P=1 fallback for unaligned shapes%s",
              MSPL_FUSE_CH, MSPL_USE_TMA ? "" : " (TMA disabled at build time)");
     return name;
 }
@@ -130,7 +132,7 @@ extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logit
     // (under a vote policy they only ever feed conf, so a call without conf does not need them either)
     const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S && conf != nullptr);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return K <= 5 ? dispatch_fuse<5>(prm, P, gk, st) : dispatch_fuse<8>(prm, P, gk, st);
+    return K <= 5 ? dispatch_fuse<5>(prm, P == 4, gk, st) : dispatch_fuse<8>(prm, P == 4, gk, st);
 }
 
 extern "C" int mspl_fuse_sources_lowres(int num_sources, const float* const* main_logits, const float* const* aux_logits,
@@ -179,26 +181,29 @@ extern "C" int mspl_fuse_sources_lowres(int num_sources, const float* const* mai
     prm.class_hist = class_hist; prm.conf_hist = conf_hist; prm.marginal = marginal_count;
 
     constexpr int NCW = MSPL_LOWRES_NCW, P = 2, CH = MSPL_FUSE_CH, NST = MSPL_LOWRES_STAGES;
+    constexpr int kThreads = (NCW + 1) * 32;
     const bool gk = (policy == MSPL_POLICY_PROB) || (prm.vote_t < S && conf != nullptr);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    {   // common geometries (e.g. ESPDNetUE at 480x256: 3 rows x 240 / 3 rows x 120 floats per class) fit fixed class strides,
-        // which turn every interpolation tap into an immediate-offset shared-memory load
+    if (!build_class_order(prm, CH)) return MSPL_ERR_UNSUPPORTED;
+    if (K <= 5) {   // common geometries (e.g. ESPDNetUE at 480x256: 3 rows x 240 / 3 rows x 120 floats per class) fit fixed class
+                    // strides, which turn every interpolation tap into an immediate-offset shared-memory load
         constexpr int MS = 768, AS = 384;
         FuseParams fixed = prm;
-        const size_t fsmem = lowres_plan(fixed, NCW * 32 * P, CH, NST, MS, AS);
-        if (fsmem != 0 && fsmem <= 227 * 1024 && K <= 5) {
-            if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, true, MS, AS>, fixed, fsmem, st);
-            return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true, MS, AS>, fixed, fsmem, st);
+        const size_t fsmem = lowres_plan(fixed, NCW * 32 * P, CH, NST, 5, kThreads, P, MS, AS);
+        if (fsmem != 0 && fsmem <= 227 * 1024) {
+            if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, MS, AS>, fixed, fsmem, st);
+            return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, MS, AS>, fixed, fsmem, st);
         }
     }
-    const size_t smem = lowres_plan(prm, NCW * 32 * P, CH, NST);
+    const int KT = K <= 5 ? 5 : 8;
+    const size_t smem = lowres_plan(prm, NCW * 32 * P, CH, NST, KT, kThreads, P);
     if (smem == 0 || smem > 227 * 1024) return MSPL_ERR_UNSUPPORTED;    // caller upsamples and uses mspl_fuse_sources instead
     if (K <= 5) {
-        if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true, true>, prm, smem, st);
-        return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true>, prm, smem, st);
+        if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, true>, prm, smem, st);
+        return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false>, prm, smem, st);
     }
-    if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, true, true>, prm, smem, st);
-    return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, false, true>, prm, smem, st);
+    if (gk) return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, true>, prm, smem, st);
+    return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 8, false>, prm, smem, st);
 }
 
 extern "C" int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t num_pixels, int num_target_classes,

@@ -2,16 +2,24 @@
 //
 // For a pixel with class logits m_c (main head) and a_c (aux head), z_c = m_c + 0.5*a_c, the reference needs
 //   softmax(z)                  uest_seg_multi_os.py:687-689
-//   first-argmax_c              uest_seg_multi_os.py:904      (decided on z: softmax is monotone; ties -> lowest c)
+//   first-argmax_c -> LUT       uest_seg_multi_os.py:904-912  (decided on z: softmax is monotone; ties -> lowest c)
 //   KL(softmax(m)||softmax(a))  loss_fns/segmentation_loss.py:181-189
 // All of them follow from the running quantities below, updated one chunk of CH classes at a time (online
 // softmax: a chunk's maxima are folded in with ONE rescale per chunk, not one per class):
-//   Mm, Sm = sum e^{m-Mm}     Ma, Sa = sum e^{a-Ma}     Mz, Sz = sum e^{z-Mz}
-//   T  = sum e^{m-Mm} ((m-Mm) - (a-Ma))      z2 = second largest z      amax = first index of the largest z
+//   Mm, Sm = sum e^{m-Mm}     Ma, Sa = sum e^{a-Ma}     Sz = sum e^{z-Rz}     T = sum e^{m-Mm} ((m-Mm) - (a-Ma))
+//   g_k = max z over the source classes the label table maps to target class k
 // Then  KLD = T/Sm - log Sm + log Sa   (the reference's sum_c p1*(logp1 - logp2), with log_softmax written as
 // (x - max) - log(sum) exactly as ATen does, so no large maxima are ever added back),
-// max prob = 1/Sz,  top-2 margin = (1 - e^{z2-Mz})/Sz.
-// When the whole source fits one chunk this IS the two-sweep (max, then sums) softmax.
+// Mz = max_k g_k, label = the k attaining it, max prob = e^{Mz-Rz}/Sz, G_s[k] = e^{g_k-Rz}/Sz.
+//
+// Two things keep the instruction count per class and pixel low (the kernels are co-limited by issue slots):
+//   * a thread's P = 2 neighbouring pixels travel as ONE 64-bit register pair and every add / multiply / fma on them is a
+//     packed Blackwell instruction (FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot, IEEE results identical to the
+//     scalar forms); only the maxima and the MUFU exponentials are issued per lane;
+//   * the classes of a source are visited GROUPED BY TARGET CLASS (the loaders fetch class rows in that order, see
+//     ClassOrder): no arg-max index is tracked, only a running maximum of z that is committed to its target's slot at the
+//     (warp-uniform) group boundaries.  The reference's first-maximal-index rule only matters when two DIFFERENT targets tie
+//     exactly; that is detected from the committed maxima and resolved out of line in the original class order.
 #pragma once
 #include "common.cuh"
 
@@ -43,34 +51,123 @@ MSPL_DEVINL float max3(float a, float b, float c) {        // FMNMX3 (sm_100+)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-template <int N>
-MSPL_DEVINL float max_of(const float (&v)[N], float init) {
-    float r = init;
-    int j = 0;
-#pragma unroll
-    for (; j + 1 < N; j += 2) r = max3(r, v[j], v[j + 1]);
-    if (j < N) r = fmaxf(r, v[j]);
+
+// ---- P pixels of one thread as one value ------------------------------------------------------------------------------
+// Px<2>: two fp32 lanes in one 64-bit register pair, arithmetic through the packed f32x2 instructions (sm_100+).
+// Px<1>: plain float (the scalar fallback kernel for unaligned shapes).  Same IEEE results lane for lane.
+template <int P> struct Px;
+
+template <> struct Px<1> {
+    float v;
+    static MSPL_DEVINL Px splat(float x) { return Px{x}; }
+    static MSPL_DEVINL Px make(const float (&a)[1]) { return Px{a[0]}; }
+    MSPL_DEVINL void get(float (&a)[1]) const { a[0] = v; }
+};
+// (the _rn intrinsics are never contracted into fused multiply-adds, so the scalar kernel rounds exactly where the packed
+//  instructions do and both produce the same bits)
+MSPL_DEVINL Px<1> operator+(Px<1> a, Px<1> b) { return Px<1>{__fadd_rn(a.v, b.v)}; }
+MSPL_DEVINL Px<1> operator-(Px<1> a, Px<1> b) { return Px<1>{__fsub_rn(a.v, b.v)}; }
+MSPL_DEVINL Px<1> operator*(Px<1> a, Px<1> b) { return Px<1>{__fmul_rn(a.v, b.v)}; }
+MSPL_DEVINL Px<1> fma(Px<1> a, Px<1> b, Px<1> c) { return Px<1>{fmaf(a.v, b.v, c.v)}; }
+
+template <> struct Px<2> {
+    unsigned long long v;
+    static MSPL_DEVINL Px pack(float lo, float hi) {
+        Px r;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+        return r;
+    }
+    static MSPL_DEVINL Px splat(float x) { return pack(x, x); }
+    static MSPL_DEVINL Px make(const float (&a)[2]) { return pack(a[0], a[1]); }
+    MSPL_DEVINL void get(float (&a)[2]) const { asm("mov.b64 {%0, %1}, %2;" : "=f"(a[0]), "=f"(a[1]) : "l"(v)); }
+};
+MSPL_DEVINL Px<2> operator+(Px<2> a, Px<2> b) {
+    Px<2> r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+MSPL_DEVINL Px<2> operator-(Px<2> a, Px<2> b) {
+    Px<2> r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+MSPL_DEVINL Px<2> operator*(Px<2> a, Px<2> b) {
+    Px<2> r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+MSPL_DEVINL Px<2> fma(Px<2> a, Px<2> b, Px<2> c) {
+    Px<2> r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
     return r;
 }
 
+// lane-wise helpers (issued per lane: there is no packed FMNMX / MUFU)
+template <int P, typename F>
+MSPL_DEVINL Px<P> lanewise(Px<P> a, F f) {
+    float x[P];
+    a.get(x);
+#pragma unroll
+    for (int p = 0; p < P; ++p) x[p] = f(x[p]);
+    return Px<P>::make(x);
+}
+template <int P>
+MSPL_DEVINL Px<P> pmax(Px<P> a, Px<P> b) {
+    float x[P], y[P];
+    a.get(x); b.get(y);
+#pragma unroll
+    for (int p = 0; p < P; ++p) x[p] = fmaxf(x[p], y[p]);
+    return Px<P>::make(x);
+}
+template <int P>
+MSPL_DEVINL Px<P> pmax3(Px<P> a, Px<P> b, Px<P> c) {
+    float x[P], y[P], z[P];
+    a.get(x); b.get(y); c.get(z);
+#pragma unroll
+    for (int p = 0; p < P; ++p) x[p] = max3(x[p], y[p], z[p]);
+    return Px<P>::make(x);
+}
+template <int P, int N>
+MSPL_DEVINL Px<P> pmax_of(const Px<P> (&v)[N], Px<P> init) {
+    Px<P> r = init;
+    int j = 0;
+#pragma unroll
+    for (; j + 1 < N; j += 2) r = pmax3<P>(r, v[j], v[j + 1]);
+    if (j < N) r = pmax<P>(r, v[j]);
+    return r;
+}
+template <int P> MSPL_DEVINL Px<P> pex2(Px<P> a) { return lanewise<P>(a, [](float x) { return ex2_approx(x); }); }
+
+// ---- class visiting order of one source -----------------------------------------------------------------------------
+// Built on the host from the label table (build_class_order in fuse_launch.cuh): row[i] = the source class fetched i-th,
+// classes sorted by (target class, class index).  seg[chunk]: bit j = slot j of the chunk is the LAST class of its target
+// group.  `present` = bit k set when some class maps to target k; the groups are committed in ascending k, so the i-th
+// committed maximum belongs to the i-th set bit of `present`.
+constexpr int kMaxChunksPerSource = 64;       // >= ceil(MSPL_MAX_SRC_CLASSES / CH) for every CH >= 4
+struct ClassOrder {
+    uint8_t row[MSPL_MAX_SRC_CLASSES];
+    uint8_t seg[kMaxChunksPerSource];
+    uint32_t present;
+};
+
 // Running per-pixel statistics of one source.
 //   Mm, Sm = sum e^{m-Mm}     Ma, Sa = sum e^{a-Ma}     T = sum e^{m-Mm} ((m-Mm) - (a-Ma))
-//   Mz = max z, z2 = runner-up z, amax = first index of the largest z
-//   Sz = sum e^{z - Rz} with the reference point Rz = Mm + Ma/2 (>= Mz): e^{z-Rz} = e^{m-Mm} * e^{(a-Ma)/2}, so the z-softmax
-//        costs no exponential of its own (two MUFU.EX2 per class instead of three).
+//   Sz = sum e^{z - Rz} with the reference point Rz = Mm + Ma/2 (>= max z): e^{z-Rz} = e^{m-Mm} * e^{(a-Ma)/2}, so the
+//        z-softmax costs no exponential of its own (two MUFU.EX2 per class instead of three).
+//   run = max z over the classes of the target group being visited (committed to the group's slot at its last class)
+//   slot = where the next finished group's maximum goes: the groups of a source are committed in visiting order (ascending
+//          target class) to consecutive entries of the thread's column, `gstride` apart
 template <int P>
 struct SourceStats {
-    float Mm[P], Sm[P], Ma[P], Sa[P], Mz[P], Sz[P], T[P], z2[P];
-    int amax[P];
-    MSPL_DEVINL void reset() {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            // finite sentinel (not -inf): the rescale of an empty accumulator then evaluates to exactly 0 without NaNs, so
-            // kernels may run it unconditionally on a source's first chunk
-            Mm[p] = Ma[p] = Mz[p] = z2[p] = -1.0e30f;
-            Sm[p] = Sa[p] = Sz[p] = T[p] = 0.f;
-            amax[p] = 0;
-        }
+    Px<P> Mm, Sm, Ma, Sa, Sz, T, run;
+    Px<P>* slot;
+    MSPL_DEVINL void reset(Px<P>* group) {
+        // finite sentinel (not -inf) for the softmax maxima: the rescale of an empty accumulator then evaluates to exactly 0
+        // without NaNs, so kernels may run it unconditionally on a source's first chunk
+        Mm = Ma = Px<P>::splat(-1.0e30f);
+        Sm = Sa = Sz = T = Px<P>::splat(0.f);
+        run = Px<P>::splat(-INFINITY);
+        slot = group;
     }
 };
 
@@ -78,66 +175,49 @@ struct SourceStats {
 // max, its exponentials are exactly 0 and (m - Mm) - (a - Ma) stays finite (0) -- the math below needs no predicates.
 constexpr float kPadLogit = -1.0e30f;
 
-// Fold classes [c0, c0+CH) into the running stats.  m/a hold the chunk's logits; entries past the source's last class
-// are kPadLogit (see load_chunk).  `first` (warp-uniform): nothing accumulated yet, skip the rescale.
-// TOP2: also track the runner-up z (needed only for the near-tie report).
-// GK: also track zk[k][p], the running max of z over the classes that `lut` maps to target class k.
-template <int P, int CH, bool TOP2, bool GK, int K>
-MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const float (&m)[CH][P], const float (&a)[CH][P], int c0,
-                            bool first, const uint8_t* __restrict__ lut, float (&zk)[K][P]) {
+// Fold the CH classes of one chunk into the running stats.  m/a hold the chunk's logits in visiting order; entries past the
+// source's last class are kPadLogit.  `first` (warp-uniform): nothing accumulated yet, skip the rescale.  seg: the chunk's
+// ClassOrder word (bit j: slot j ends its target group).  Finished groups go to st.slot, gstride entries apart.
+template <int P, int CH>
+MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const Px<P> (&m)[CH], const Px<P> (&a)[CH], bool first, uint32_t seg, int gstride) {
+    const Px<P> half = Px<P>::splat(0.5f);
+    // sweep 1: z exactly as the reference forms it (0.5*a is exact in fp32, so the fused multiply-add rounds once, just
+    // like `pred + 0.5 * pred_aux`), folded into the running maximum of the current target group
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        float z[CH], mv[CH], av[CH];
-        float z1 = st.Mz[p], zr = st.z2[p];
-        int i1 = st.amax[p];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            mv[j] = m[j][p];
-            av[j] = a[j][p];
-            // z exactly as the reference forms it: 0.5*a is exact in fp32, so the fused multiply-add
-            // rounds once, just like `pred + 0.5 * pred_aux`.
-            z[j] = fmaf(0.5f, av[j], mv[j]);
-            if (TOP2) zr = fmaxf(zr, fminf(z1, z[j]));
-            i1 = (z[j] > z1) ? (c0 + j) : i1;      // strict >: lowest index wins ties, as np.argmax
-            z1 = fmaxf(z1, z[j]);
-        }
-        const float nMm = max_of<CH>(mv, st.Mm[p]), nMa = max_of<CH>(av, st.Ma[p]);
-        float sm = 0.f, sa = 0.f, sz = 0.f, t = 0.f;
-        if (!first) {   // rescale what earlier chunks accumulated to the new maxima
-            const float dm = st.Mm[p] - nMm, da = st.Ma[p] - nMa;
-            const float rm = exp_neg(dm), rh = exp_half_neg(da);
-            sm = st.Sm[p] * rm;
-            t = rm * fmaf(st.Sm[p], dm - da, st.T[p]);
-            sa = st.Sa[p] * (rh * rh);
-            sz = st.Sz[p] * (rm * rh);
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const float tm = mv[j] - nMm, ta = av[j] - nMa;
-            const float em = exp_neg(tm), h = exp_half_neg(ta);
-            sm += em;
-            t = fmaf(em, tm - ta, t);
-            sa = fmaf(h, h, sa);
-            sz = fmaf(em, h, sz);
-        }
-        st.Mm[p] = nMm; st.Ma[p] = nMa; st.Mz[p] = z1; st.z2[p] = zr; st.amax[p] = i1;
-        st.Sm[p] = sm; st.Sa[p] = sa; st.Sz[p] = sz; st.T[p] = t;
-    }
-    if (GK) {
-        // class-major: the table entry is warp-uniform, so one uniform branch per class selects the target class whose
-        // running max takes this class's z (padded classes read table slack and carry kPadLogit: harmless)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const int l = lut[c0 + j];
-#pragma unroll
-            for (int k = 1; k < K; ++k) {
-                if (l == k) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p) zk[k][p] = fmaxf(zk[k][p], fmaf(0.5f, a[j][p], m[j][p]));
-                }
-            }
+    for (int j = 0; j < CH; ++j) {
+        st.run = pmax<P>(st.run, fma(a[j], half, m[j]));
+        if ((seg >> j) & 1u) {              // warp-uniform: last class of its group
+            *st.slot = st.run;
+            st.slot += gstride;
+            st.run = Px<P>::splat(-INFINITY);
         }
     }
+    const Px<P> nMm = pmax_of<P, CH>(m, st.Mm), nMa = pmax_of<P, CH>(a, st.Ma);
+    Px<P> sm_old = Px<P>::splat(0.f), rm = sm_old, sm, sa = sm_old, sz = sm_old, t = sm_old;
+    const Px<P> l2e = Px<P>::splat(kLog2e), hl2e = Px<P>::splat(0.5f * kLog2e);
+    if (!first) {   // rescale what earlier chunks accumulated to the new maxima
+        const Px<P> dm = st.Mm - nMm, da = st.Ma - nMa;
+        const Px<P> rh = pex2<P>(da * hl2e);
+        rm = pex2<P>(dm * l2e);
+        sm_old = st.Sm;
+        t = rm * fma(st.Sm, dm - da, st.T);
+        sa = st.Sa * (rh * rh);
+        sz = st.Sz * (rm * rh);
+    }
+    // sweep 2: the exponentials and the four sums.  The rescaled old sum Sm*rm enters through an EXPLICIT fma with the first
+    // class's term: ptxas fuses a packed multiply into a following packed add whenever it sees the pair, so spelling it out
+    // keeps every variant of the kernels (packed / scalar, with / without the first-chunk branch) on the same bits.
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const Px<P> tm = m[j] - nMm, ta = a[j] - nMa;
+        const Px<P> em = pex2<P>(tm * l2e), h = pex2<P>(ta * hl2e);
+        sm = (j == 0) ? fma(sm_old, rm, em) : sm + em;
+        t = fma(em, tm - ta, t);
+        sa = fma(h, h, sa);
+        sz = fma(em, h, sz);
+    }
+    st.Mm = nMm; st.Ma = nMa;
+    st.Sm = sm; st.Sa = sa; st.Sz = sz; st.T = t;
 }
 
 // What the fusion needs from a finished source, per pixel.
@@ -167,50 +247,48 @@ constexpr float kMaxSharedExpGap = 16.f;
 #endif
 constexpr float kMaxSharedExpLogit = MSPL_MAX_EXP_LOGIT;
 
-template <int P>
-MSPL_DEVINL SourceResult finish_source(const SourceStats<P>& st, int p) {
+// Per-pixel scalars of a finished source (lane p of the packed stats) and the maximum Mz of its fused logits.
+struct SourceScalars { float Mm, Sm, Ma, Sa, Sz, T; };
+
+MSPL_DEVINL SourceResult finish_source(const SourceScalars& s, float Mz) {
     SourceResult r;
-    const float inv_sm = rcp_fast(st.Sm[p]);
-    r.kld = fmaf(st.T[p], inv_sm, log_fast(st.Sa[p] * inv_sm));
-    r.rz = fmaf(0.5f, st.Ma[p], st.Mm[p]);
-    r.inv_sz = rcp_fast(st.Sz[p]);
-    r.pmax = fminf(exp_neg(st.Mz[p] - r.rz) * r.inv_sz, 1.0f);     // numerator and its term of Sz round separately: clamp
-    r.degenerate = !(r.rz - st.Mz[p] <= kMaxSharedExpGap) || !(fabsf(st.Mz[p]) <= kMaxSharedExpLogit);     // also catches NaN
+    const float inv_sm = rcp_fast(s.Sm);
+    r.kld = fmaf(s.T, inv_sm, log_fast(s.Sa * inv_sm));
+    r.rz = fmaf(0.5f, s.Ma, s.Mm);
+    r.inv_sz = rcp_fast(s.Sz);
+    r.pmax = fminf(exp_neg(Mz - r.rz) * r.inv_sz, 1.0f);     // numerator and its term of Sz round separately: clamp
+    r.degenerate = !(r.rz - Mz <= kMaxSharedExpGap) || !(fabsf(Mz) <= kMaxSharedExpLogit);     // also catches NaN
     return r;
 }
 
-// Slow path for a degenerate pixel: recompute 1/sum_c e^{z_c - Mz} directly from global memory (rare; divergent).
-// Deliberately out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
+template <int P>
+MSPL_DEVINL void unpack_stats(const SourceStats<P>& st, SourceScalars (&s)[P]) {
+    float Mm[P], Sm[P], Ma[P], Sa[P], Sz[P], T[P];
+    st.Mm.get(Mm); st.Sm.get(Sm); st.Ma.get(Ma); st.Sa.get(Sa); st.Sz.get(Sz); st.T.get(T);
+#pragma unroll
+    for (int p = 0; p < P; ++p) s[p] = SourceScalars{Mm[p], Sm[p], Ma[p], Sa[p], Sz[p], T[p]};
+}
+
+// ---- out-of-line slow paths (rare, divergent): they must not bloat the hot loop's instruction footprint ----------------
+// Degenerate pixel: recompute 1/sum_c e^{z_c - Mz} directly from global memory.
 static __device__ __noinline__ float recompute_pmax(const float* __restrict__ pm, const float* __restrict__ pa, int C, int64_t hw, float Mz) {
     float s = 0.f;
 #pragma unroll 1
     for (int c = 0; c < C; ++c) s += exp_neg(fmaf(0.5f, __ldg(pa + c * hw), __ldg(pm + c * hw)) - Mz);
     return __frcp_rn(s);
 }
-
-template <int P>
-MSPL_DEVINL void fill_pad(float (&v)[P]) {
-#pragma unroll
-    for (int p = 0; p < P; ++p) v[p] = kPadLogit;
-}
-
-// Load P pixels of CH class planes of both heads (classes c0..c0+cn-1; cn warp-uniform); a tail chunk (cn < CH) is
-// padded with kPadLogit.  Full chunks take the predicate-free path.
-template <int P, int CH>
-MSPL_DEVINL void load_chunk(const float* __restrict__ pm, const float* __restrict__ pa, int64_t hw, int cn,
-                            float (&m)[CH][P], float (&a)[CH][P]) {
-    if (cn == CH) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) PixVec<P>::load(pm + j * hw, m[j]);
-#pragma unroll
-        for (int j = 0; j < CH; ++j) PixVec<P>::load(pa + j * hw, a[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            if (j < cn) { PixVec<P>::load(pm + j * hw, m[j]); PixVec<P>::load(pa + j * hw, a[j]); }
-            else { fill_pad<P>(m[j]); fill_pad<P>(a[j]); }
-        }
+// Two different target classes tie exactly for the maximum of z: the reference's label is the table entry of the FIRST maximal
+// class in the original class order (np.argmax, uest_seg_multi_os.py:904).
+static __device__ __noinline__ int recompute_label(const float* __restrict__ pm, const float* __restrict__ pa, int C, int64_t hw,
+                                                   const uint8_t* lut) {
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        const float z = fmaf(0.5f, __ldg(pa + c * hw), __ldg(pm + c * hw));
+        if (z > best) { best = z; arg = c; }       // strict >: lowest index wins ties
     }
+    return lut[arg];
 }
 
 }  // namespace mspl

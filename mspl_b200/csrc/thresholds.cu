@@ -9,16 +9,24 @@
 //    select over the candidates alone gives the exact threshold and cand_apply patches their labels.  6 B/pixel.
 //  * generic radix (mspl_radix_*): 3 full passes over (label, conf) on the order-preserving key + mspl_apply_thresholds,
 //    16 B/pixel; kept as the independent cross-check of the bracketed protocol and for callers with their own state.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mspl {
 
 struct RadixState {            // one per target class, caller-zeroed before pass 0
     unsigned long long rank;   // 1-based rank from the top still to be resolved inside the current prefix
     unsigned long long count;  // kept pixels of the class (n_k)
+    unsigned long long kept_above;   // candidate passes: keys seen so far that are certainly above the threshold
     uint32_t prefix;           // key bits resolved so far
-    uint32_t done;             // 1: threshold already final (floor(n_k*portion) == 0 -> 1.0)
+    uint32_t done;             // kInactive: takes no part in the passes (threshold final or never resolved);
+                               // kFixedOne: threshold is 1.0 (floor(n_k*portion) == 0), the candidate passes only COUNT the
+                               // keys >= key(1.0) by following that key's digits; 0: select by rank
 };
+constexpr uint32_t kInactive = 1, kFixedOne = 2;
 
 constexpr int kHistThreads = 256;
 
@@ -72,7 +80,7 @@ __global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(const uint8_t*
     if (threadIdx.x <= MSPL_MAX_CLASSES) {
         const int k = threadIdx.x;
         if (PASS == kLinearPass) s_prefix[k] = k < K ? 0u : 0xffffffffu;
-        else s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;    // no key prefix has all 32 bits set
+        else s_prefix[k] = (k < K && state[k].done != kInactive) ? state[k].prefix : 0xffffffffu;    // no key prefix has all 32 bits set
     }
     __syncthreads();
     // conf == +0 is by far the most common duplicate (every ignore-labelled pixel of the vote policies): those are counted
@@ -157,7 +165,8 @@ MSPL_DEVINL void suffix_counts(const unsigned long long* s_h, int per, unsigned 
 template <bool INIT>
 __global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* __restrict__ hist, int pass, double portion,
                                                            RadixState* __restrict__ state, float* __restrict__ thresh,
-                                                           unsigned long long* __restrict__ kept_count) {
+                                                           unsigned long long* __restrict__ kept_count,
+                                                           unsigned long long* __restrict__ final_hist, int ignore) {
     __shared__ unsigned long long s_h[MSPL_RADIX_BINS];
     __shared__ unsigned long long s_warp[8];
     __shared__ RadixState s_st;
@@ -181,7 +190,8 @@ __global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* _
         if (j > total) j = total;
         st.rank = j;
         st.prefix = 0;
-        st.done = (j == 0);
+        st.kept_above = 0;
+        st.done = (j == 0) ? kInactive : 0;
         if (threadIdx.x == 0) {
             if (st.done) {
                 thresh[k] = 1.0f;
@@ -190,17 +200,32 @@ __global__ void __launch_bounds__(256) radix_select_kernel(unsigned long long* _
             if (kept_count) kept_count[k] = total;
         }
     }
-    if (!st.done && above < st.rank && st.rank <= above + mine) {       // exactly one thread
+    if (st.done == kInactive) return;
+    // the digit this pass settles: by rank, or (kFixedOne) the digit of key(1.0); exactly one thread owns it
+    const bool fixed = st.done == kFixedOne;
+    const int fixed_d = (int)radix_digit(float_to_key(1.0f), pass);
+    const bool owner = fixed ? (fixed_d / per == (int)threadIdx.x) : (above < st.rank && st.rank <= above + mine);
+    if (owner) {
         unsigned long long acc = above;
         int d = threadIdx.x * per + per - 1;
         for (; d > threadIdx.x * per; --d) {
-            if (acc + s_h[d] >= st.rank) break;
+            if (fixed ? d == fixed_d : acc + s_h[d] >= st.rank) break;
             acc += s_h[d];
         }
-        st.rank -= acc;
+        if (!fixed) st.rank -= acc;
+        st.kept_above += acc;
         st.prefix = (st.prefix << bits) | (uint32_t)d;
         state[k] = st;
-        if (pass == 2) thresh[k] = key_to_float(st.prefix);
+        if (pass == 2) {
+            if (!fixed) thresh[k] = key_to_float(st.prefix);
+            // the candidates that reach the threshold: everything above the selected key plus its duplicates.  They had been
+            // counted as ignored; with the histograms all-reduced this patch is the GLOBAL one, identical on every rank.
+            const unsigned long long n = st.kept_above + s_h[d];
+            if (final_hist && n) {
+                atomicAdd(final_hist + k, n);
+                if (ignore >= 0) atomicAdd(final_hist + ignore, 0ull - n);
+            }
+        }
     }
 }
 
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
         // all be candidates
         if (threadIdx.x == 0) {
             RadixState st;
-            st.rank = 0; st.count = total; st.prefix = 0; st.done = 1;
+            st.rank = 0; st.count = total; st.kept_above = 0; st.prefix = 0; st.done = kInactive;
             state[k] = st;
             thresh[k] = INFINITY;
             bracket[k] = make_float2(INFINITY, INFINITY);
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
         // candidate patch keeps exactly those with conf >= 1.0
         if (threadIdx.x == 0) {
             RadixState st;
-            st.rank = 0; st.count = total; st.prefix = 0; st.done = 1;
+            st.rank = 0; st.count = total; st.kept_above = 0; st.prefix = 0; st.done = kFixedOne;   // passes only count conf >= 1.0
             state[k] = st;
             thresh[k] = 1.0f;
             bracket[k] = make_float2((float)(MSPL_RADIX_BINS - 1) * (1.0f / MSPL_RADIX_BINS), INFINITY);
@@ -320,7 +345,7 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
             acc += s_h[b];
         }
         RadixState st;
-        st.rank = j - acc; st.count = total; st.prefix = 0; st.done = 0;
+        st.rank = j - acc; st.count = total; st.kept_above = 0; st.prefix = 0; st.done = 0;
         state[k] = st;
         bracket[k] = make_float2(b == 0 ? -INFINITY : (float)b * (1.0f / MSPL_RADIX_BINS),
                                  b == MSPL_RADIX_BINS - 1 ? INFINITY : (float)(b + 1) * (1.0f / MSPL_RADIX_BINS));
@@ -583,7 +608,7 @@ __global__ void __launch_bounds__(kHistThreads) cand_hist_kernel(const uint8_t* 
     for (int i = threadIdx.x; i < nbins; i += kHistThreads) s_hist[i] = 0;
     if (threadIdx.x <= MSPL_MAX_CLASSES) {
         const int k = threadIdx.x;
-        s_prefix[k] = (k < K && !state[k].done) ? state[k].prefix : 0xffffffffu;
+        s_prefix[k] = (k < K && state[k].done != kInactive) ? state[k].prefix : 0xffffffffu;
     }
     __syncthreads();
     for (unsigned long long i = (unsigned long long)blockIdx.x * kHistThreads + threadIdx.x; i < n;
@@ -630,6 +655,150 @@ __global__ void __launch_bounds__(256) cand_apply_kernel(const uint8_t* __restri
         atomicAdd(final_hist + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
         if (ignore < K) atomicAdd(final_hist + ignore, 0ull - (unsigned long long)s_cls[threadIdx.x]);   // had been counted as ignored
     }
+}
+
+// ---- single-rank tail of the bracketed protocol in ONE launch ---------------------------------------------------------------
+// Replaces 3 x (cand_hist + cand_select) + cand_apply (7 launches of ~10 us for a few ten-thousand candidates) when no
+// all-reduce has to run between the passes.  One thread-block CLUSTER of kResolveCtas CTAs per class: each CTA gathers its
+// slice of the candidate list once, keeps the (key, index) pairs of its class in shared memory, and per radix pass
+//   local shared-memory histogram  ->  added into cluster rank 0's total through distributed shared memory
+//   ->  rank 0 selects the digit  ->  every CTA reads the verdict back over DSMEM
+// with three cluster barriers per pass; then each CTA patches the labels of its own candidates.  A CTA whose slice holds more
+// candidates of the class than its cache re-gathers them from global memory in every pass (correct, slower).
+constexpr int kResolveCtas = 8;             // cluster size (portable maximum)
+constexpr int kResolveThreads = 1024;
+constexpr int kResolveCap = 12288;          // cached (key, index) pairs per CTA: 96 KB
+
+struct ResolveVerdict { uint32_t digit, count_at; unsigned long long above; };
+
+__global__ void __launch_bounds__(kResolveThreads, 1) cand_resolve_kernel(const uint8_t* __restrict__ label, const float* __restrict__ conf,
+                                                                          const uint32_t* __restrict__ cand_index,
+                                                                          const unsigned long long* __restrict__ cand_count,
+                                                                          int64_t hw, int ignore, int ds_rate,
+                                                                          RadixState* __restrict__ state, float* __restrict__ thresh,
+                                                                          uint8_t* __restrict__ final_label,
+                                                                          uint8_t* __restrict__ ignore_mask,
+                                                                          unsigned long long* __restrict__ final_hist) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(rs_smem);                  // this CTA's histogram of the current pass
+    uint32_t* s_total = s_hist + MSPL_RADIX_BINS;                             // rank 0: the cluster's histogram
+    uint32_t* s_key = s_total + MSPL_RADIX_BINS;
+    uint32_t* s_idx = s_key + kResolveCap;
+    __shared__ uint32_t s_fill, s_kept;
+    __shared__ unsigned long long s_warp[kResolveThreads / 32];
+    __shared__ ResolveVerdict s_verdict;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int k = blockIdx.x / kResolveCtas;
+    const int t = threadIdx.x;
+    const RadixState st0 = state[k];
+    if (st0.done == kInactive) return;                    // uniform over the cluster: nothing to resolve for this class
+    const unsigned long long n = *cand_count;
+    // this CTA's slice of the candidate list
+    const unsigned long long per = (n + kResolveCtas - 1) / kResolveCtas;
+    const unsigned long long lo = per * rank < n ? per * rank : n, hi = lo + per < n ? lo + per : n;
+    if (t == 0) { s_fill = 0; s_kept = 0; }
+    __syncthreads();
+    // gather once: candidates of class k in the slice
+    for (unsigned long long i = lo + t; i < hi; i += kResolveThreads) {
+        const uint32_t idx = cand_index[i];
+        if (label[idx] == k) {
+            const uint32_t slot = atomicAdd(&s_fill, 1u);
+            if (slot < (uint32_t)kResolveCap) { s_key[slot] = float_to_key(conf[idx]); s_idx[slot] = idx; }
+        }
+    }
+    __syncthreads();
+    const uint32_t mine_n = s_fill;
+    const bool cached = mine_n <= (uint32_t)kResolveCap;
+    // visit (key, idx) of every candidate of class k in the slice
+    auto for_each = [&](auto&& f) {
+        if (cached) {
+            for (uint32_t i = t; i < mine_n; i += kResolveThreads) f(s_key[i], s_idx[i]);
+        } else {
+            for (unsigned long long i = lo + t; i < hi; i += kResolveThreads) {
+                const uint32_t idx = cand_index[i];
+                if (label[idx] == k) f(float_to_key(conf[idx]), idx);
+            }
+        }
+    };
+    const bool fixed = st0.done == kFixedOne;
+    const uint32_t key_one = float_to_key(1.0f);
+    uint32_t prefix = 0;
+    unsigned long long rank_left = st0.rank, kept_above = 0;
+    for (int pass = 0; pass < MSPL_RADIX_PASSES; ++pass) {
+        const int nb = pass == 2 ? 1024 : MSPL_RADIX_BINS;
+        const int bits = pass == 2 ? 10 : 11;
+        for (int i = t; i < MSPL_RADIX_BINS; i += kResolveThreads) { s_hist[i] = 0; s_total[i] = 0; }
+        cluster.sync();                                   // rank 0's total is zeroed before anyone adds to it
+        for_each([&](uint32_t key, uint32_t idx) {
+            const bool part = ds_rate <= 1 || ((int64_t)idx % hw) % ds_rate == 0;
+            if (part && radix_prefix(key, pass) == prefix) atomicAdd(&s_hist[radix_digit(key, pass)], 1u);
+        });
+        __syncthreads();
+        uint32_t* total0 = cluster.map_shared_rank(s_total, 0);
+        for (int i = t; i < nb; i += kResolveThreads)
+            if (s_hist[i]) atomicAdd(total0 + i, s_hist[i]);
+        cluster.sync();                                   // every CTA's counts have landed in rank 0
+        if (rank == 0) {
+            // suffix counts over the nb bins: thread t owns bins [t*per_t, (t+1)*per_t)
+            const int per_t = nb / kResolveThreads;       // 2 or 1
+            unsigned long long mine = 0;
+            for (int i = 0; i < per_t; ++i) mine += s_total[t * per_t + i];
+            unsigned long long incl = mine;
+            const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_down_sync(0xffffffffu, incl, o);
+                if (lane + o < 32) incl += v;
+            }
+            if (lane == 0) s_warp[warp] = incl;
+            if (t == 0) s_verdict = ResolveVerdict{0u, 0u, 0ull};
+            __syncthreads();
+            unsigned long long higher = 0;
+            for (int w2 = warp + 1; w2 < kResolveThreads / 32; ++w2) higher += s_warp[w2];
+            const unsigned long long above = higher + incl - mine;
+            const int fixed_d = (int)radix_digit(key_one, pass);
+            const bool owner = fixed ? (fixed_d / per_t == t) : (above < rank_left && rank_left <= above + mine);
+            if (owner) {
+                unsigned long long acc = above;
+                int d = t * per_t + per_t - 1;
+                for (; d > t * per_t; --d) {
+                    if (fixed ? d == fixed_d : acc + s_total[d] >= rank_left) break;
+                    acc += s_total[d];
+                }
+                s_verdict = ResolveVerdict{(uint32_t)d, s_total[d], acc};
+            }
+        }
+        cluster.sync();                                   // the verdict is published
+        const ResolveVerdict v = *cluster.map_shared_rank(&s_verdict, 0);
+        prefix = (prefix << bits) | v.digit;
+        if (!fixed) rank_left -= v.above;
+        kept_above += v.above;
+    }
+    const float th = fixed ? 1.0f : key_to_float(prefix);
+    if (rank == 0 && t == 0) {
+        RadixState st = st0;
+        st.prefix = prefix; st.rank = rank_left; st.kept_above = kept_above;
+        state[k] = st;
+        if (!fixed) thresh[k] = th;
+    }
+    // patch: the candidates that reach the threshold get their label back (they were written and counted as ignored)
+    uint32_t kept = 0;
+    for_each([&](uint32_t key, uint32_t idx) {
+        if (key_to_float(key) >= th) {
+            if (final_label) final_label[idx] = (uint8_t)k;
+            if (ignore_mask) ignore_mask[idx] = 0;
+            ++kept;
+        }
+    });
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if ((t & 31) == 0 && kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (t == 0 && final_hist && s_kept) {
+        atomicAdd(final_hist + k, (unsigned long long)s_kept);
+        if (ignore >= 0) atomicAdd(final_hist + ignore, 0ull - (unsigned long long)s_kept);
+    }
+    cluster.sync();                                       // no CTA may exit while others still read its shared memory
 }
 
 // Persistent grid of exactly the CTAs that can be resident at once (these kernels are latency-bound: a partial second
@@ -685,8 +854,10 @@ extern "C" int mspl_radix_select(unsigned long long* hist, int num_target_classe
     if (!(portion >= 0.0)) return MSPL_ERR_BAD_ARG;
     if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pass == 0) radix_select_kernel<true><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count);
-    else radix_select_kernel<false><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count);
+    if (pass == 0)
+        radix_select_kernel<true><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count, nullptr, -1);
+    else
+        radix_select_kernel<false><<<K, 256, 0, st>>>(hist, pass, portion, static_cast<RadixState*>(state), thresh, kept_count, nullptr, -1);
     return launch_status();
 }
 
@@ -808,12 +979,14 @@ extern "C" int mspl_cand_hist_pass(const uint8_t* label, const float* conf, cons
     return launch_status();
 }
 
-extern "C" int mspl_cand_select(unsigned long long* hist, int num_target_classes, int pass, void* state, float* thresh, void* stream) {
+extern "C" int mspl_cand_select(unsigned long long* hist, int num_target_classes, int pass, void* state, float* thresh,
+                                unsigned long long* final_hist, int ignore_label, void* stream) {
     const int K = num_target_classes;
     if (!hist || !state || !thresh || K < 1 || K > MSPL_MAX_CLASSES || pass < 0 || pass >= MSPL_RADIX_PASSES) return MSPL_ERR_BAD_ARG;
-    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4)) return MSPL_ERR_ALIGN;
+    if (final_hist && (ignore_label < 0 || ignore_label >= K)) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(hist, 8) || !aligned_to(state, 8) || !aligned_to(thresh, 4) || !aligned_to(final_hist, 8)) return MSPL_ERR_ALIGN;
     radix_select_kernel<false><<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, pass, 0.0, static_cast<RadixState*>(state),
-                                                                                 thresh, nullptr);
+                                                                                 thresh, nullptr, final_hist, ignore_label);
     return launch_status();
 }
 
@@ -829,5 +1002,41 @@ extern "C" int mspl_cand_apply(const uint8_t* label, const float* conf, const fl
         return MSPL_ERR_ALIGN;
     cand_apply_kernel<<<2 * kNumSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(label, conf, thresh, cand_index, cand_count, K,
                                                                                  ignore_label, final_label, ignore_mask, final_hist);
+    return launch_status();
+}
+
+extern "C" int mspl_cand_resolve(const uint8_t* label, const float* conf, const uint32_t* cand_index, const unsigned long long* cand_count,
+                                 int64_t pixels_per_image, int num_target_classes, int ignore_label, int ds_rate, void* state,
+                                 float* thresh, uint8_t* final_label, uint8_t* ignore_mask, unsigned long long* final_hist,
+                                 void* stream) {
+    const int K = num_target_classes;
+    if (!label || !conf || !cand_index || !cand_count || !state || !thresh || pixels_per_image < 1) return MSPL_ERR_BAD_ARG;
+    if (K < 1 || K > MSPL_MAX_CLASSES || ds_rate < 1 || ignore_label < -1 || ignore_label >= MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    if ((final_label || ignore_mask || final_hist) && (ignore_label < 0 || ignore_label >= K)) return MSPL_ERR_BAD_ARG;
+    if (!aligned_to(conf, 4) || !aligned_to(cand_index, 4) || !aligned_to(cand_count, 8) || !aligned_to(state, 8) ||
+        !aligned_to(thresh, 4) || !aligned_to(final_hist, 8))
+        return MSPL_ERR_ALIGN;
+    const size_t smem = sizeof(uint32_t) * (2 * (size_t)MSPL_RADIX_BINS + 2 * (size_t)kResolveCap);
+    if (cudaFuncSetAttribute(cand_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(K * kResolveCtas));
+    cfg.blockDim = dim3(kResolveThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kResolveCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, cand_resolve_kernel, label, conf, cand_index, cand_count, pixels_per_image, ignore_label, ds_rate,
+                           static_cast<RadixState*>(state), thresh, final_label, ignore_mask, final_hist) != cudaSuccess) {
+        cudaGetLastError();
+        return MSPL_ERR_CUDA;
+    }
     return launch_status();
 }

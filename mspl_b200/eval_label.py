@@ -25,8 +25,9 @@ def evaluate_pseudo_labels(model_list, os_data_list, val_loader, device='cuda', 
     luts = [SOURCE_TABLES[name] for name in os_data_list]
     for m in model_list:
         m.eval()
+        m.to(dev)      # as the reference's get_output does (:57)
     counts = torch.zeros((3, seg_classes), dtype=torch.int64, device=dev)
-    n_images = 0       # every get_iou call of the reference adds epsilon to the union once per image (batch_size=1, :149)
+    n_calls = 0        # every get_iou call of the reference adds its epsilon to the union once: once per LOADER batch (:201)
     pend_x, pend_t = [], []
 
     def flush():
@@ -46,7 +47,7 @@ def evaluate_pseudo_labels(model_list, os_data_list, val_loader, device='cuda', 
             if use_depth:
                 raise NotImplementedError("depth inputs are not wired into the batched evaluation")
             pend_x.append(image), pend_t.append(target)
-            n_images += image.shape[0]
+            n_calls += 1
             if sum(t.shape[0] for t in pend_x) >= batch_images:
                 flush()
                 pend_x, pend_t = [], []
@@ -54,8 +55,8 @@ def evaluate_pseudo_labels(model_list, os_data_list, val_loader, device='cuda', 
             flush()
     c = counts.cpu().numpy().astype(np.float64)
     inter = c[0]
-    # MIOU.get_iou: union = pred + mask - inter + 1e-6 (float32) per call; the meters sum the per-image values
-    union = c[1] + c[2] - c[0] + n_images * np.float64(np.float32(1e-6))
+    # MIOU.get_iou: union = pred + mask - inter + 1e-6 (float32) per call; the meters sum the per-call values
+    union = c[1] + c[2] - c[0] + n_calls * np.float64(np.float32(1e-6))
     iou = inter / (union + 1e-10) * 100
     miou = iou[[1, 2, 3]].mean()
     return (iou, miou, counts) if return_counts else (iou, miou)

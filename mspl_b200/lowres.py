@@ -9,40 +9,55 @@ and those two calls write 8*C bytes per pixel that the label-generation kernel i
 ``forward_lowres`` runs the model with ``torch.nn.functional.interpolate`` temporarily wrapped: calls that match that closing
 pattern (bilinear, align_corners=True, target size == the input image size) are recorded and answered with a zero-stride
 placeholder of the right shape; every other interpolate call (the decoder's internal upsampling) goes through untouched.
+The capture is only trusted when the model RETURNS exactly those two placeholders (same storage, zero strides); a model with a
+matching upsample in its interior, or whose modules are in training mode (the caller would have to run it twice on a miss,
+updating batch-norm statistics twice), takes the ordinary full-resolution path.  The patch is process-global, so it is held
+under a lock; names bound with ``from torch.nn.functional import interpolate`` bypass it (and then nothing is captured).
 The recorded tensors feed ``ops.fuse_sources_lowres``, which interpolates inside the fusion kernel.
 """
 import contextlib
+import threading
 
 import torch
 import torch.nn.functional as F
 
+_PATCH_LOCK = threading.Lock()      # the wrapper replaces a module attribute: one forward at a time
+
 
 @contextlib.contextmanager
-def _intercept_final_upsample(out_size, captured):
+def _intercept_final_upsample(out_size, captured, placeholders):
     original = F.interpolate
 
     def wrapper(input, size=None, scale_factor=None, mode='nearest', align_corners=None, **kwargs):
         want = tuple(int(v) for v in size) if isinstance(size, (tuple, list, torch.Size)) else None
         if mode == 'bilinear' and align_corners and want == tuple(out_size) and input.dim() == 4:
             captured.append(input)
-            return input.new_empty(1).expand(input.shape[0], input.shape[1], *want)     # never read by the caller
+            ph = input.new_empty(1).expand(input.shape[0], input.shape[1], *want)       # must never be read: checked below
+            placeholders.append(ph)
+            return ph
         return original(input, size=size, scale_factor=scale_factor, mode=mode, align_corners=align_corners, **kwargs)
 
-    F.interpolate = wrapper
-    try:
-        yield
-    finally:
-        F.interpolate = original
+    with _PATCH_LOCK:
+        F.interpolate = wrapper
+        try:
+            yield
+        finally:
+            F.interpolate = original
 
 
 def forward_lowres(model, x):
     """Run ``model(x)``; return ``(main_lowres, aux_lowres)`` if the model closed with exactly two matching upsample calls
     (main first, aux second, as ESPDNetUE does), else ``None`` -- the caller then uses the ordinary full-resolution path."""
-    captured = []
-    with _intercept_final_upsample(x.shape[-2:], captured):
+    captured, placeholders = [], []
+    with _intercept_final_upsample(x.shape[-2:], captured, placeholders):
         out = model(x)
     if len(captured) != 2 or not isinstance(out, (tuple, list)) or len(out) != 2:
         return None
+    # the two answers must have come back untouched as the model's outputs: if a matching upsample sat INSIDE the network its
+    # placeholder (uninitialised memory) flowed through later layers and nothing captured here can be trusted
+    for o, ph in zip(out, placeholders):
+        if not isinstance(o, torch.Tensor) or o.data_ptr() != ph.data_ptr() or o.shape != ph.shape or o.stride() != ph.stride():
+            return None
     main_lr, aux_lr = captured
     if main_lr.shape[1] != aux_lr.shape[1] or tuple(out[0].shape[-2:]) != tuple(x.shape[-2:]):
         return None

@@ -50,8 +50,8 @@ def vote_threshold(num_sources, thresh=None):
         return num_sources // 2 + 1
     if isinstance(thresh, str) and thresh == 'all':
         return num_sources
-    if isinstance(thresh, int) and not isinstance(thresh, bool) and thresh <= num_sources:
-        return thresh
+    if isinstance(thresh, int) and thresh <= num_sources:       # bool included, as the reference's isinstance(thresh, int)
+        return int(thresh)
     return num_sources // 2 + 1
 
 
@@ -138,7 +138,7 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
 
 def fuse_sources_lowres(mains, auxs, luts, out_size, policy='half', num_classes=5, ignore_label=4, ds_rate=1,
                         want_conf=True, want_unc=True, want_kld=False, want_conf_hist=True, count_marginal=True,
-                        class_hist=None, conf_hist=None, marginal=None):
+                        class_hist=None, conf_hist=None, marginal=None, label_out=None, conf_out=None, unc_out=None):
     """K1 with the networks' final bilinear upsample fused in: mains[s] is (N, C_s, hm, wm), auxs[s] is (N, C_s, ha, wa) --
     the tensors ESPDNetUE feeds to its closing ``F.interpolate(..., size=out_size, mode='bilinear', align_corners=True)``
     (model/segmentation/espdnet_ue.py:301-302) -- and the labels come out at ``out_size = (H, W)``.  Everything else is as
@@ -166,9 +166,16 @@ def fuse_sources_lowres(mains, auxs, luts, out_size, policy='half', num_classes=
         pol, vt = POLICY_PROB, 0
     else:
         pol, vt = POLICY_VOTE, vote_threshold(S, policy)
-    label = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    conf = torch.empty((n, h, w), dtype=torch.float32, device=dev) if (want_conf or want_conf_hist) else None
-    unc = torch.empty((n, h, w), dtype=torch.float32, device=dev) if want_unc else None
+    def _out(t, name, dtype, wanted):
+        if t is not None:
+            if _require_cuda(t, name, dtype).shape != (n, h, w) or t.device != dev:
+                raise ValueError("%s must be a (%d,%d,%d) tensor on %s" % (name, n, h, w, dev))
+            return t
+        return torch.empty((n, h, w), dtype=dtype, device=dev) if wanted else None
+
+    label = _out(label_out, "label_out", torch.uint8, True)
+    conf = _out(conf_out, "conf_out", torch.float32, want_conf or want_conf_hist)
+    unc = _out(unc_out, "unc_out", torch.float32, want_unc)
     kld = [torch.empty((n, h, w), dtype=torch.float32, device=dev) for _ in range(S)] if want_kld else None
     if class_hist is None:
         class_hist = torch.zeros(num_classes, dtype=torch.int64, device=dev)
@@ -176,6 +183,9 @@ def fuse_sources_lowres(mains, auxs, luts, out_size, policy='half', num_classes=
         conf_hist = torch.zeros((num_classes, RADIX_BINS), dtype=torch.int64, device=dev)
     if count_marginal and marginal is None:
         marginal = torch.zeros((), dtype=torch.int64, device=dev)
+    for t, nm in ((class_hist, "class_hist"), (conf_hist, "conf_hist"), (marginal, "marginal")):
+        if t is not None:
+            _require_cuda(t, nm, torch.int64)
     vp = ctypes.c_void_p
     main_ptrs = (vp * S)(*[m.data_ptr() for m in mains])
     aux_ptrs = (vp * S)(*[a.data_ptr() for a in auxs])
@@ -228,15 +238,18 @@ def softmax_kld(main, aux, want_prob=True, want_kld=True):
 
 
 def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_label=4, conf_hist=None, all_reduce=None,
-                     want_final=True, want_mask=False, final_hist=None):
+                     want_final=True, want_mask=False, final_hist=None, hist_reduced=False):
     """K2+K3, bracketed protocol: class-balanced thresholds AND the thresholded label map in ONE pass over (label, conf).
 
     label (N,H,W) u8, conf (N,H,W) f32.  conf_hist: the linear confidence histogram already accumulated by fuse_sources
-    (consumed: zeroed on return); if None it is computed here (one more 5 B/pixel pass).  all_reduce: optional callable
-    applied in place to each (K, 2048) int64 histogram (``lambda h: dist.all_reduce(h)``) so that every rank selects the
-    same bins -- thresholds are then identical for 1 or N GPUs.  No host synchronisation.
-    The ignore class is never selected, so its threshold is not resolved: thresh[ignore_label] = +inf (kept_count[ignore_label]
-    is still its pixel count).  ignore_label=None resolves every class; no map can be written then (thresholds only).
+    (consumed: zeroed on return); if None it is computed here (one more 5 B/pixel pass).
+    all_reduce: None for a single rank -- the candidate passes, their selects and the patch then run as ONE launch
+    (mspl_cand_resolve) -- or a callable applied in place to an int64 tensor (``lambda t: dist.all_reduce(t)``): every rank
+    then selects the same bins, thresholds are identical for 1 or N GPUs and the returned final_hist is the GLOBAL one on every
+    rank (derived from the all-reduced histograms, no collective of its own when ds_rate == 1).  hist_reduced: conf_hist has
+    already been all-reduced by the caller (the pipeline packs it with the other statistics into one collective).
+    No host synchronisation.  The ignore class is never selected, so its threshold is not resolved: thresh[ignore_label] = +inf
+    (kept_count[ignore_label] is still its pixel count).  ignore_label=None resolves every class; no map can be written then.
     Returns (thresh f32 (K,), kept_count i64 (K,), final u8 or None, mask u8 or None, final_hist i64 (K,) or None)."""
     label = _require_cuda(label, "label", torch.uint8)
     conf = _require_cuda(conf, "conf", torch.float32)
@@ -271,36 +284,52 @@ def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_
         _require_cuda(hist, "conf_hist", torch.int64)
     else:
         hist = torch.zeros((K, RADIX_BINS), dtype=torch.int64, device=dev)
+    single = all_reduce is None
     with torch.cuda.device(dev):
         st = _stream(dev)
         if conf_hist is None:
             _lib.check(lib.mspl_conf_hist(_ptr(label), _ptr(conf), npix, hw, K, _ptr(hist), int(ds_rate), st), "mspl_conf_hist")
-        # with ds_rate 1 the histogram covers every pixel, so the final class counts can be read off it (this rank's copy of
-        # it, taken before the all-reduce) instead of being counted per pixel by the classify pass
-        from_hist = outputs and int(ds_rate) == 1
-        local_hist = None
-        if all_reduce is not None:
-            if from_hist:
-                local_hist = hist.clone()
+        if not single and not (hist_reduced and conf_hist is not None):
             all_reduce(hist)
+        # with ds_rate 1 the histogram covers every pixel, so the final class counts are read off it (of all ranks' pixels once
+        # it is all-reduced) instead of being counted per pixel by the classify pass
+        from_hist = outputs and int(ds_rate) == 1
         _lib.check(lib.mspl_bracket_select(_ptr(hist), K, float(portion), ign, _ptr(state), _ptr(bracket), _ptr(thresh), _ptr(kept),
-                                           _ptr(local_hist), _ptr(final_hist if from_hist else None), st), "mspl_bracket_select")
+                                           None, _ptr(final_hist if from_hist else None), st), "mspl_bracket_select")
         _lib.check(lib.mspl_bracket_classify(_ptr(label), _ptr(conf), _ptr(bracket), npix, K, ign, _ptr(final), _ptr(mask),
                                              _ptr(final_hist if outputs and not from_hist else None), _ptr(cand_index),
                                              _ptr(cand_count), st), "mspl_bracket_classify")
-        for p in range(RADIX_PASSES):
-            _lib.check(lib.mspl_cand_hist_pass(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, p, _ptr(state),
-                                               _ptr(hist), int(ds_rate), st), "mspl_cand_hist_pass")
-            if all_reduce is not None:
+        if single:
+            _lib.check(lib.mspl_cand_resolve(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, ign, int(ds_rate),
+                                             _ptr(state), _ptr(thresh), _ptr(final), _ptr(mask), _ptr(final_hist if outputs else None),
+                                             st), "mspl_cand_resolve")
+        else:
+            for p in range(RADIX_PASSES):
+                _lib.check(lib.mspl_cand_hist_pass(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, p, _ptr(state),
+                                                   _ptr(hist), int(ds_rate), st), "mspl_cand_hist_pass")
                 all_reduce(hist)
-            _lib.check(lib.mspl_cand_select(_ptr(hist), K, p, _ptr(state), _ptr(thresh), st), "mspl_cand_select")
-        if outputs:
-            _lib.check(lib.mspl_cand_apply(_ptr(label), _ptr(conf), _ptr(thresh), _ptr(cand_index), _ptr(cand_count), K, ign,
-                                           _ptr(final), _ptr(mask), _ptr(final_hist), st), "mspl_cand_apply")
+                _lib.check(lib.mspl_cand_select(_ptr(hist), K, p, _ptr(state), _ptr(thresh), _ptr(final_hist if from_hist else None),
+                                                ign, st), "mspl_cand_select")
+            if outputs:
+                _lib.check(lib.mspl_cand_apply(_ptr(label), _ptr(conf), _ptr(thresh), _ptr(cand_index), _ptr(cand_count), K, ign,
+                                               _ptr(final), _ptr(mask), _ptr(None if from_hist else final_hist), st), "mspl_cand_apply")
+                if not from_hist:
+                    all_reduce(final_hist)      # ds_rate > 1: the classify pass counted this rank's pixels only
     return thresh, kept, final, mask, (final_hist if outputs else None)
 
 
-SELECT_AND_APPLY_LAUNCHES = 9      # bracket_select + classify + 3 x (cand_hist + cand_select) + cand_apply
+# kernels select_and_apply launches: single rank = bracket_select + classify + cand_resolve; with an all-reduce between the
+# passes = bracket_select + classify + 3 x (cand_hist + cand_select) + cand_apply
+SELECT_AND_APPLY_LAUNCHES = 3
+SELECT_AND_APPLY_LAUNCHES_SHARDED = 9
+
+
+def new_label_stats(num_classes, device):
+    """One int64 buffer holding every statistic K1 accumulates, so that N ranks exchange them in ONE all-reduce:
+    returns (buffer, conf_hist (K, 2048) view, class_hist (K,) view, marginal () view)."""
+    K = num_classes
+    buf = torch.zeros(K * RADIX_BINS + K + 1, dtype=torch.int64, device=device)
+    return buf, buf[:K * RADIX_BINS].view(K, RADIX_BINS), buf[K * RADIX_BINS:K * RADIX_BINS + K], buf[K * RADIX_BINS + K:].view(())
 
 
 def cb_thresholds(label, conf, portion=0.2, ds_rate=1, num_classes=5, conf_hist=None, all_reduce=None, ignore_label=None):

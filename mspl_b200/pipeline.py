@@ -2,12 +2,17 @@
 multi-GPU.  This is the post-network body of generate_pseudo_label_multi_model (uest_seg_multi_os.py:891-950)
 plus the [NEW] class-balanced thresholding stage, as one object whose steps enqueue without host syncs:
 
-    K1 fuse_sources (+ linear confidence histogram + class histogram)  ->  [all-reduce histograms]  ->  bracket select
-    ->  ONE pass over (label, conf): final label map, final class histogram, candidate list  ->  radix select on the
-    candidates ([all-reduce] x3)  ->  candidate patch  ->  class weights
+    K1 fuse_sources per batch (label, conf, unc maps; class histogram, linear confidence histogram, near-tie count, all three
+    accumulated in ONE int64 buffer)  ->  [ONE all-reduce of that buffer]  ->  bracket select  ->  ONE pass over
+    (label, conf): final label map, candidate list  ->  candidate radix select (one launch on a single rank; three
+    histogram all-reduces under N ranks)  ->  final class histogram, class weights
 
-Multi-GPU: one process per GPU; target images are sharded by contiguous index range; the only collective is an
-all-reduce(SUM) of small int64 histograms, so N-GPU results are bit-identical to 1-GPU results.
+The target set need not be resident at once: begin() allocates the shard's maps (5-9 B/pixel), fuse_batch() labels one batch
+of logits into its slice (the reference's loop over the target loader, :897-921), finish() runs the threshold stage over the
+whole shard.  run() is begin + one fuse_batch + finish.
+
+Multi-GPU: one process per GPU; target images are sharded by contiguous index range; the only collectives are all-reduce(SUM)
+of small int64 histograms, so N-GPU results are bit-identical to 1-GPU results.
 """
 from collections import namedtuple
 
@@ -39,6 +44,16 @@ def class_weights_from_histogram(class_hist, weighting='normal'):
     return torch.from_numpy(w).float()
 
 
+class ShardState:
+    """Maps and statistics of one rank's shard while its batches are being labelled (LabelGenerator.begin)."""
+    __slots__ = ("label", "conf", "unc", "stats", "conf_hist", "class_hist", "marginal", "filled")
+
+    def __init__(self, label, conf, unc, stats, conf_hist, class_hist, marginal):
+        self.label, self.conf, self.unc = label, conf, unc
+        self.stats, self.conf_hist, self.class_hist, self.marginal = stats, conf_hist, class_hist, marginal
+        self.filled = 0
+
+
 class LabelGenerator:
     """Fused multi-source pseudo-label generation with optional class-balanced thresholds.
 
@@ -60,7 +75,8 @@ class LabelGenerator:
         self.ops = ops if ops is not None else _cuda_ops
         self.group = group
         self.launches = 0          # kernels of libmspl_b200.so launched so far (bench.py reports this)
-        self.k1_events = None      # set to a list to collect (start, end) CUDA events around every K1 launch of run()
+        self.collectives = 0       # all-reduces issued so far
+        self.k1_events = None      # set to a list to collect (start, end) CUDA events around every K1 launch
 
     # -- distributed plumbing -----------------------------------------------------------------------------------
     def _world(self):
@@ -73,62 +89,95 @@ class LabelGenerator:
         if self._world() > 1:
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.collectives += 1
         return t
 
-    # -- device-resident job ------------------------------------------------------------------------------------
-    def run(self, mains, auxs, want_unc=True, want_mask=False):
-        """mains/auxs: this rank's shard, lists of (N_local, C_s, H, W) device tensors.  Returns a LabelJob whose
-        histograms / thresholds are GLOBAL (all-reduced) and whose maps are local."""
+    # -- streaming interface ------------------------------------------------------------------------------------
+    def begin(self, num_images, height, width, device, want_unc=True):
+        """Allocate this rank's maps for `num_images` target images and zeroed statistics."""
+        ops, K = self.ops, self.num_classes
+        shape = (num_images, height, width)
+        label = torch.empty(shape, dtype=torch.uint8, device=device)
+        conf = torch.empty(shape, dtype=torch.float32, device=device) if self.thresholds else None
+        unc = torch.empty(shape, dtype=torch.float32, device=device) if want_unc else None
+        stats, conf_hist, class_hist, marginal = ops.new_label_stats(K, device)
+        return ShardState(label, conf, unc, stats, conf_hist, class_hist, marginal)
+
+    def fuse_batch(self, shard, lo, mains, auxs, out_size=None):
+        """K1 on one batch of logits (lists of (n, C_s, H, W) tensors): labels images [lo, lo+n) of the shard.
+        out_size=(H, W): the lists hold the sources' heads BEFORE their closing bilinear upsample (main (n, C_s, hm, wm), aux
+        (n, C_s, ha, wa), model/segmentation/espdnet_ue.py:301-302) and K1-lowres interpolates on chip."""
         ops = self.ops
+        n = mains[0].shape[0]
         if self.k1_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        r = ops.fuse_sources(mains, auxs, self.luts, policy=self.policy, num_classes=self.num_classes,
-                             ignore_label=self.ignore_label, ds_rate=self.ds_rate, want_conf=self.thresholds,
-                             want_unc=want_unc, want_conf_hist=self.thresholds)
+        kw = dict(policy=self.policy, num_classes=self.num_classes, ignore_label=self.ignore_label, ds_rate=self.ds_rate,
+                  want_conf=self.thresholds, want_unc=shard.unc is not None, want_conf_hist=self.thresholds,
+                  class_hist=shard.class_hist, conf_hist=shard.conf_hist if self.thresholds else None, marginal=shard.marginal,
+                  label_out=shard.label[lo:lo + n], conf_out=shard.conf[lo:lo + n] if shard.conf is not None else None,
+                  unc_out=shard.unc[lo:lo + n] if shard.unc is not None else None)
+        if out_size is None:
+            ops.fuse_sources(mains, auxs, self.luts, **kw)
+        else:
+            ops.fuse_sources_lowres(mains, auxs, self.luts, out_size, **kw)
         if self.k1_events is not None:
             e1.record()
             self.k1_events.append((e0, e1))
         self.launches += 1
-        class_hist = self._all_reduce(r.class_hist)
-        marginal = self._all_reduce(r.marginal) if r.marginal is not None else None
+        shard.filled = max(shard.filled, lo + n)
+
+    def finish(self, shard, want_mask=False):
+        """Exchange the statistics (ONE all-reduce), resolve the thresholds, write the final maps.  Returns a LabelJob whose
+        histograms / thresholds are GLOBAL and whose maps are this rank's."""
+        ops = self.ops
+        sharded = self._world() > 1
+        self._all_reduce(shard.stats)       # class histogram + confidence histogram + near-tie count in one message
+        class_hist, marginal = shard.class_hist, shard.marginal
         if not self.thresholds:
-            return LabelJob(r.label, r.label, None, r.conf, r.unc, None, None, class_hist, class_hist, marginal)
+            return LabelJob(shard.label, shard.label, None, shard.conf, shard.unc, None, None, class_hist, class_hist, marginal)
         thresh, kept, final, mask, final_hist = ops.select_and_apply(
-            r.label, r.conf, self.portion, self.ds_rate, self.num_classes, self.ignore_label, conf_hist=r.conf_hist,
-            all_reduce=self._all_reduce if self._world() > 1 else None, want_final=True, want_mask=want_mask)
-        self.launches += ops.SELECT_AND_APPLY_LAUNCHES
-        final_hist = self._all_reduce(final_hist)
-        return LabelJob(r.label, final, mask, r.conf, r.unc, thresh, kept, class_hist, final_hist, marginal)
+            shard.label, shard.conf, self.portion, self.ds_rate, self.num_classes, self.ignore_label, conf_hist=shard.conf_hist,
+            all_reduce=self._all_reduce if sharded else None, want_final=True, want_mask=want_mask, hist_reduced=True)
+        self.launches += ops.SELECT_AND_APPLY_LAUNCHES_SHARDED if sharded else ops.SELECT_AND_APPLY_LAUNCHES
+        return LabelJob(shard.label, final, mask, shard.conf, shard.unc, thresh, kept, class_hist, final_hist, marginal)
+
+    # -- device-resident job ------------------------------------------------------------------------------------
+    def run(self, mains, auxs, want_unc=True, want_mask=False, cycles=1):
+        """mains/auxs: this rank's resident logits, lists of (N_pool, C_s, H, W) device tensors.  cycles > 1 labels a shard of
+        cycles * N_pool images whose image i is pool image (i mod N_pool) -- the benchmark's way of running a target set
+        larger than HBM holds as logits (the maps and statistics are those of the full shard)."""
+        n, _, h, w = mains[0].shape
+        shard = self.begin(n * cycles, h, w, mains[0].device, want_unc=want_unc)
+        for c in range(cycles):
+            self.fuse_batch(shard, c * n, mains, auxs)
+        return self.finish(shard, want_mask=want_mask)
 
     # -- host-resident job (end-to-end: H2D of every logit, D2H of the label maps) --------------------------------
-    def run_from_host(self, mains_host, auxs_host, device, chunk_images=16, out_host=None):
+    def run_from_host(self, mains_host, auxs_host, device, chunk_images=16, out_host=None, slots=3, out_size=None):
         """mains_host/auxs_host: lists of (N_local, C_s, H, W) fp32 CPU tensors (pinned for full copy speed).
-        Streams the logits to the device chunk by chunk on a copy stream while the previous chunk is fused, keeps only
-        label (1 B/pix) and conf (4 B/pix) on the device, then thresholds and copies the final uint8 maps back.
+        Streams the logits to the device chunk by chunk on a copy stream while earlier chunks are fused (`slots` device
+        buffers in flight), keeps only label (1 B/pix) and conf (4 B/pix) on the device, then thresholds and copies the final
+        uint8 maps back.  out_size=(H, W): the host tensors are the sources' pre-upsample heads (see fuse_batch).
         Returns (final label maps as a CPU uint8 tensor, LabelJob with device-side statistics)."""
-        ops = self.ops
         dev = torch.device(device)
         S = len(mains_host)
-        n, _, h, w = mains_host[0].shape
-        K = self.num_classes
-        label = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-        conf = torch.empty((n, h, w), dtype=torch.float32, device=dev)
-        class_hist = torch.zeros(K, dtype=torch.int64, device=dev)
-        conf_hist = torch.zeros((K, ops.RADIX_BINS), dtype=torch.int64, device=dev) if self.thresholds else None
-        marginal = torch.zeros((), dtype=torch.int64, device=dev)
+        n = mains_host[0].shape[0]
+        h, w = (int(out_size[0]), int(out_size[1])) if out_size is not None else mains_host[0].shape[2:]
+        shard = self.begin(n, h, w, dev, want_unc=False)
         compute = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
-        bufs = [[[torch.empty((chunk_images,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev) for t in mains_host]
-                 for _ in range(2)] for _ in range(2)]            # [slot][main|aux][source]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
+        bufs = [[[torch.empty((chunk_images,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev) for t in side]
+                 for side in (mains_host, auxs_host)] for _ in range(slots)]            # [slot][main|aux][source]
+        ready = [torch.cuda.Event() for _ in range(slots)]
+        freed = [torch.cuda.Event() for _ in range(slots)]
         starts = list(range(0, n, chunk_images))
 
-        def stage(i, slot):
+        def stage(i):
+            slot = i % slots
             lo, hi = starts[i], min(starts[i] + chunk_images, n)
             with torch.cuda.stream(copy):
-                if i >= 2:
+                if i >= slots:
                     copy.wait_event(freed[slot])
                 for s in range(S):
                     bufs[slot][0][s][:hi - lo].copy_(mains_host[s][lo:hi], non_blocking=True)
@@ -136,32 +185,19 @@ class LabelGenerator:
                 ready[slot].record(copy)
 
         copy.wait_stream(compute)
-        if starts:
-            stage(0, 0)
+        for i in range(min(slots - 1, len(starts))):
+            stage(i)
         for i, lo in enumerate(starts):
-            slot = i & 1
+            slot = i % slots
             hi = min(lo + chunk_images, n)
-            if i + 1 < len(starts):
-                stage(i + 1, slot ^ 1)
+            if i + slots - 1 < len(starts):
+                stage(i + slots - 1)
             compute.wait_event(ready[slot])
-            ops.fuse_sources([b[:hi - lo] for b in bufs[slot][0]], [b[:hi - lo] for b in bufs[slot][1]], self.luts,
-                                 policy=self.policy, num_classes=K, ignore_label=self.ignore_label, ds_rate=self.ds_rate,
-                                 want_unc=False, want_conf_hist=self.thresholds, class_hist=class_hist,
-                                 conf_hist=conf_hist, marginal=marginal, label_out=label[lo:hi], conf_out=conf[lo:hi])
-            self.launches += 1
+            self.fuse_batch(shard, lo, [b[:hi - lo] for b in bufs[slot][0]], [b[:hi - lo] for b in bufs[slot][1]], out_size=out_size)
             freed[slot].record(compute)
-        class_hist = self._all_reduce(class_hist)
-        if self.thresholds:
-            thresh, kept, final, _, final_hist = ops.select_and_apply(
-                label, conf, self.portion, self.ds_rate, K, self.ignore_label, conf_hist=conf_hist,
-                all_reduce=self._all_reduce if self._world() > 1 else None, want_final=True, want_mask=False)
-            self.launches += ops.SELECT_AND_APPLY_LAUNCHES
-            final_hist = self._all_reduce(final_hist)
-        else:
-            thresh = kept = None
-            final, final_hist = label, class_hist
+        job = self.finish(shard)
         if out_host is None:
             out_host = torch.empty((n, h, w), dtype=torch.uint8, pin_memory=True)
-        out_host.copy_(final, non_blocking=True)
+        out_host.copy_(job.final, non_blocking=True)
         compute.synchronize()          # a host-buffer API: the maps are in `out_host` when the call returns
-        return out_host, LabelJob(label, final, None, conf, None, thresh, kept, class_hist, final_hist, marginal)
+        return out_host, job

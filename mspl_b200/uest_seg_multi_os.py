@@ -181,7 +181,7 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
     world, rank = _dist_info(args)
     num_classes = args.classes
     use_depth = getattr(args, 'use_depth', False)
-    if policy not in ('half', 'all', 'prob') and not (isinstance(policy, int) and not isinstance(policy, bool)):
+    if policy not in ('half', 'all', 'prob') and not isinstance(policy, int):
         policy = None           # un-typed CLI strings fall through to 'half', as at uest_seg_multi_os.py:702-705
     use_cb = bool(getattr(args, 'cb_thresholds', False))
     portion = float(getattr(args, 'init_tgt_port', 0.2))
@@ -195,6 +195,10 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
     for m in model_list:
         m.train() if getattr(args, 'eval_training', False) else m.eval()
         m.to(dev)
+    # The reference forwards ONE image at a time (batch_size=1, :888-897).  With modules in training mode (--eval-training)
+    # batch norm normalises over the batch and updates its running statistics per forward, so batching the network would
+    # change the labels: forward image by image then and batch only the fusion kernel.
+    per_image_forward = any(mod.training for m in model_list for mod in m.modules())
 
     if logger is not None:
         logger.info('###### Start evaluating target domain train set in round {}! ######'.format(round_idx))
@@ -222,10 +226,28 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
                 depth_path_list.append(path_name.replace('color', 'depth'))
         writer.submit(label_u8, out_paths)
 
-    fuse_upsample = bool(getattr(args, 'fuse_upsample', False))
+    # (a forward_lowres miss runs the network a second time, which in training mode would update the statistics twice)
+    fuse_upsample = bool(getattr(args, 'fuse_upsample', False)) and not per_image_forward
+
+    def forward_heads(m, x):
+        if not per_image_forward or x.shape[0] == 1:
+            return _split_heads(m(x))
+        outs = [_split_heads(m(x[i:i + 1])) for i in range(x.shape[0])]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    def table_for(s, num_src_classes):
+        if luts[s] is not None:
+            return luts[s]
+        # a source without a table: the reference leaves its ids unconverted (:907-912) and merge_outputs never counts an id
+        # >= args.classes (:708-711); an identity table covers the ids that can vote
+        if num_src_classes > num_classes:
+            raise ValueError("source %d has no label table (os_data name unknown) and %d > %d classes: the reference leaves such "
+                             "ids unconverted, where those >= %d never win a vote; pass a table for it"
+                             % (s, num_src_classes, num_classes, num_classes))
+        return np.arange(num_src_classes)
 
     def flush(images, batch_names, batch_order):
-        x = torch.cat(images).to(dev, non_blocking=True)
+        x = torch.cat(images).to(dev, non_blocking=True)      # (one image size per call, like the reference's fixed crop)
         kw = dict(policy=policy, num_classes=num_classes, ignore_label=IGNORE_LABEL, ds_rate=ds_rate, want_conf=use_cb,
                   want_unc=False, want_conf_hist=use_cb, class_hist=None if use_cb else class_hist, conf_hist=conf_hist,
                   count_marginal=count_ties, marginal=marginal if count_ties else None)
@@ -236,16 +258,17 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
             if all(h is not None for h in heads):
                 try:
                     r = ops.fuse_sources_lowres([h[0].float().contiguous() for h in heads],
-                                                [h[1].float().contiguous() for h in heads], luts, x.shape[-2:], **kw)
+                                                [h[1].float().contiguous() for h in heads],
+                                                [table_for(s, h[0].shape[1]) for s, h in enumerate(heads)], x.shape[-2:], **kw)
                 except NotImplementedError:
                     r = None        # geometry the fused kernel does not cover: fall through to the full-resolution path
         if r is None:
             mains, auxs = [], []
             for m in model_list:
-                pred, pred_aux = _split_heads(m(x))
+                pred, pred_aux = forward_heads(m, x)
                 mains.append(pred.float().contiguous())
                 auxs.append(pred_aux.float().contiguous())
-            r = ops.fuse_sources(mains, auxs, luts, **kw)
+            r = ops.fuse_sources(mains, auxs, [table_for(s, t.shape[1]) for s, t in enumerate(mains)], **kw)
         if use_cb:      # labels wait on the device until the dataset-wide thresholds are known
             kept_labels.append(r.label), kept_confs.append(r.conf), names.append((batch_names, batch_order))
         else:
@@ -281,7 +304,8 @@ def _generate(model_list, luts, device, save_path, round_idx, args, logger, test
                 save_maps(final[pos:pos + len(batch_names)], batch_names, batch_order)
                 pos += len(batch_names)
         if world > 1:       # the dataset-wide class histogram (-> class weights) and the near-tie count
-            _all_reduce_sum(class_hist)
+            if not use_cb:      # (select_and_apply already returned the GLOBAL final histogram)
+                _all_reduce_sum(class_hist)
             if count_ties:
                 _all_reduce_sum(marginal)
 
@@ -320,8 +344,8 @@ def generate_pseudo_label_multi_model(model_list, os_data_list, device, save_pat
     ``<save_path>/tgt_train.lst``; returns (list path, class_weights) like the reference."""
     luts = []
     for os_data in os_data_list:
-        if os_data not in SOURCE_TABLES:     # the reference leaves such a source's ids unconverted (:907-912)
-            luts.append(np.arange(args.classes))
+        if os_data not in SOURCE_TABLES:     # the reference leaves such a source's ids unconverted (:907-912): see table_for
+            luts.append(None)
         else:
             luts.append(SOURCE_TABLES[os_data])
     return _generate(list(model_list), luts, device, save_path, round_idx, args, logger, testloader, batch_images,

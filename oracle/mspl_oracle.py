@@ -262,8 +262,8 @@ def fuse_sources(mains, auxs, luts, policy='half', seg_classes=NUM_GREENHOUSE_CL
       policy 'prob'               : label = first-argmax_k F ;  conf = max_k F
     Returns dict(label u8 (N,H,W), conf f32, unc f32, kld list of (N,H,W) f32, class_hist int64 (K,),
     marginal bool (N,H,W)).  ``marginal`` flags pixels where a different-but-legitimate fp32 rounding
-    may change the label: some source's top-2 softmax margin < 1e-6, or (policy 'prob') the top-2 margin
-    of F < 1e-6.
+    may change the label: for some source the softmax margin between the best class of its winning target and the
+    best class of any OTHER target is < 1e-6 (SURVEY.md 8 A4'), or (policy 'prob') the top-2 margin of F < 1e-6.
     """
     S = len(mains)
     K = seg_classes
@@ -287,8 +287,12 @@ def fuse_sources(mains, auxs, luts, policy='half', seg_classes=NUM_GREENHOUSE_CL
             if bool(sel.any()):
                 G[:, k] = P[:, sel].max(dim=1).values
         Fsum = Fsum + G
-        if P.shape[1] > 1:
-            top2 = torch.topk(P, 2, dim=1).values
+        # near-tie report: the best class of the winning TARGET against the best class of any other target (a near-tie between
+        # two source classes that map to the same target cannot change the label)
+        present = [k for k in range(K) if bool((lut_t == k).any())]
+        if len(present) > 1:
+            Gp = torch.stack([P[:, lut_t == k].max(dim=1).values for k in present], dim=1)
+            top2 = torch.topk(Gp, 2, dim=1).values
             marginal |= (top2[:, 0] - top2[:, 1]) < NEAR_TIE_MARGIN
     Fm = Fsum / S
     U = Usum / S

@@ -44,16 +44,31 @@ def fuse_sources(mains, auxs, luts, policy='half', num_classes=5, ignore_label=4
     marg = r["marginal"].sum()
     if marginal is not None:
         marg = marginal.add_(marg)
-    return FuseResult(r["label"], r["conf"], r["unc"], r["kld"] if want_kld else None, ch, hist, marg)
+    label, cf, unc = r["label"], r["conf"], r["unc"]
+    if label_out is not None:
+        label = label_out.copy_(label)
+    if conf_out is not None:
+        cf = conf_out.copy_(cf)
+    if unc_out is not None:
+        unc = unc_out.copy_(unc)
+    return FuseResult(label, cf, unc, r["kld"] if want_kld else None, ch, hist, marg)
 
 
-SELECT_AND_APPLY_LAUNCHES = 9
+SELECT_AND_APPLY_LAUNCHES = 3
+SELECT_AND_APPLY_LAUNCHES_SHARDED = 9
+
+
+def new_label_stats(num_classes, device):
+    K = num_classes
+    buf = torch.zeros(K * RADIX_BINS + K + 1, dtype=torch.int64, device=device)
+    return buf, buf[:K * RADIX_BINS].view(K, RADIX_BINS), buf[K * RADIX_BINS:K * RADIX_BINS + K], buf[K * RADIX_BINS + K:].view(())
 
 
 def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_label=4, conf_hist=None, all_reduce=None,
-                     want_final=True, want_mask=False, final_hist=None):
+                     want_final=True, want_mask=False, final_hist=None, hist_reduced=False):
     """The bracketed protocol written with torch ops (independent of the CUDA implementation): linear histogram ->
-    [all-reduce] -> bracket -> candidates -> 3 radix passes over the candidates ([all-reduce] each) -> thresholds."""
+    [all-reduce] -> bracket -> candidates -> 3 radix passes over the candidates ([all-reduce] each) -> thresholds.
+    Like the CUDA op, the returned final histogram is the GLOBAL one when an all_reduce is given."""
     h, w = label.shape[-2:]
     K = num_classes
     keep = (torch.arange(h * w) % ds_rate == 0).reshape(h, w).expand(label.shape)
@@ -61,7 +76,7 @@ def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_
     if conf_hist is None:
         conf_hist = torch.bincount(lab_all[keep] * RADIX_BINS + bins_all[keep], minlength=K * RADIX_BINS).reshape(K, RADIX_BINS)
     hist = conf_hist
-    if all_reduce is not None:
+    if all_reduce is not None and not hist_reduced:
         all_reduce(hist)
     kept = hist.sum(1)
     rank = torch.zeros(K, dtype=torch.int64)
@@ -104,6 +119,8 @@ def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_
     if want_final or want_mask or final_hist is not None:
         final, mask = O.apply_thresholds(label, conf, thresh, ignore_label)
         hist_out = torch.bincount(final.reshape(-1).long(), minlength=K)
+        if all_reduce is not None:
+            all_reduce(hist_out)
         if final_hist is not None:
             hist_out = final_hist.add_(hist_out)
     return thresh, kept, (final if want_final else None), (mask if want_mask else None), hist_out

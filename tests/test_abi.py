@@ -40,9 +40,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.mspl_abi_version() == 3
+    assert lib.mspl_abi_version() == 4
     assert lib.mspl_strerror(0) == b"ok" and b"misaligned" in lib.mspl_strerror(-2)
-    assert lib.mspl_radix_state_bytes(5) == 5 * 24
+    assert lib.mspl_radix_state_bytes(5) == 5 * 32
     assert lib.mspl_uw_ce_workspace_bytes() >= 16 + 2 * 8 * 148
     assert b"CH=" in lib.mspl_fuse_variant()
 

@@ -22,15 +22,29 @@ def test_strict_json_has_no_nan_or_infinity():
     assert json.loads(out) == {"a": [1.0, None, None, None], "b": {"c": [2, 3.5, None]}, "d": "inf", "e": None}
 
 
-def test_image_parallel_port_equals_sequential_loop():
+def test_image_parallel_arrangement_equals_sequential_loop():
+    """Both arrangements of the CPU arm (the reference's sequential loop; images dealt to worker threads) give the same class
+    weights, with the live reference's functions (when /root/reference or oracle/_ref is present) and with the oracle port."""
     mains, auxs = bench.make_logits_host(torch, 5, 24, 32, seed=3, pin=False)
-    luts = [O.LUTS[s] for s, _ in bench.SOURCES]
+    cpu = bench.CpuPath()
     for policy in ("all", "half"):
-        w_seq, lab_seq = bench.cpu_reference_step(O, mains, auxs, luts, policy)
+        w_seq = cpu.step(torch, np, mains, auxs, policy)
         with ThreadPoolExecutor(3) as pool:
-            w_par, lab_par = bench.cpu_reference_step_image_parallel(O, mains, auxs, luts, policy, pool, 3)
+            w_par = cpu.step(torch, np, mains, auxs, policy, pool, 3)
         assert torch.equal(w_seq, w_par)
-        assert np.array_equal(np.asarray(lab_seq), np.concatenate(lab_par))
+        _, class_array = O.multi_source_labels(mains, auxs, [O.LUTS[s] for s, _ in bench.SOURCES], policy)
+        assert torch.equal(w_seq, O.class_weights_from_histogram(class_array, 'normal'))     # reference arm == oracle port
+
+
+def test_shard_plan_covers_the_named_configs():
+    import argparse
+    a = argparse.Namespace(images_total=0)
+    assert bench.shard_plan(a, 1) == (2000, 2000, 1)              # configs[1]
+    assert bench.shard_plan(a, 2) == (10000, 2500, 4)             # configs[2]: 20,000 images over the ranks
+    assert bench.shard_plan(a, 4) == (5000, 2500, 2)
+    assert bench.shard_plan(a, 8) == (2500, 2500, 1)
+    a.images_total = 20000
+    assert bench.shard_plan(a, 1) == (20000, 2500, 8)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -45,7 +59,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True
     assert d["metric"] == "pseudo-labelled Mpix/s (3-source fusion)" and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
 

@@ -251,3 +251,76 @@ def test_generators_shard_over_ranks(tmp_path, use_cb):
         assert np.array_equal(np.array(Image.open(p1)), np.array(Image.open(p2)))
     for r in (0, 1):
         assert torch.equal(out[r][1], cw1.cpu())
+
+
+class BatchNormSource(torch.nn.Module):
+    """Like TinySource with a BatchNorm in front of the heads: in training mode its output depends on what else is in the batch."""
+
+    def __init__(self, classes, seed):
+        super().__init__()
+        self.bn = torch.nn.BatchNorm2d(3)
+        self.heads = TinySource(classes, seed)
+
+    def forward(self, x):
+        return self.heads(self.bn(x))
+
+
+def test_eval_training_forwards_image_by_image(tmp_path):
+    """--eval-training leaves the sources in train() mode (uest_seg_multi_os.py:873-878) and the reference forwards one image
+    at a time: batch norm then normalises each image by its own statistics.  The generator must not batch the network there
+    (it still batches the fusion kernel) -- labels equal the per-image train-mode forward, not the batched one."""
+    from mspl_b200 import uest_seg_multi_os as U
+    names = [n for n, _ in SOURCES]
+
+    def fresh():
+        return [BatchNormSource(c, 5 + i) for i, (_, c) in enumerate(SOURCES)]
+
+    images = [b[0] for b in _loader()]
+    mains, auxs = [], []
+    for m in fresh():
+        m.train()
+        with torch.no_grad():
+            outs = [m(x) for x in images]                         # one image per forward, as the reference
+        mains.append(torch.cat([o[0] for o in outs]).contiguous()), auxs.append(torch.cat([o[1] for o in outs]).contiguous())
+    luts = [O.LUTS[n] for n in names]
+    want, _ = O.multi_source_labels(mains, auxs, luts, 'half')
+    marg = O.fuse_sources(mains, auxs, luts, 'half')["marginal"].numpy()
+    lst, _ = U.generate_pseudo_label_multi_model(fresh(), names, 'cuda:0', str(tmp_path), 0, N, None, None,
+                                                 _args(merge_label_policy='half', eval_training=True), None, None, None,
+                                                 testloader=_loader(), batch_images=4)
+    n_batched_differs = 0
+    for i, ln in enumerate(open(lst)):
+        got = np.array(Image.open(ln.strip().split(',')[1]))
+        assert not ((got != want[i]) & ~marg[i]).any()
+    # the fixture is meaningful: a batched train-mode forward would have given different labels somewhere
+    bm, ba = [], []
+    for m in fresh():
+        m.train()
+        with torch.no_grad():
+            o = m(torch.cat(images))
+        bm.append(o[0].contiguous()), ba.append(o[1].contiguous())
+    batched, _ = O.multi_source_labels(bm, ba, luts, 'half')
+    n_batched_differs = int((np.asarray(batched) != np.asarray(want)).sum())
+    assert n_batched_differs > 0
+
+
+def test_source_without_table_votes_with_its_own_ids(tmp_path):
+    """An os_data name with no table: the reference leaves that source's ids unconverted (:907-912).  With no more classes than
+    the target it votes with its own ids; with more the generator refuses with an error that names the source."""
+    from mspl_b200 import uest_seg_multi_os as U
+    models = [TinySource(13, 5), TinySource(5, 6)]
+    images = torch.cat([b[0] for b in _loader()])
+    with torch.no_grad():
+        outs = [m(images) for m in models]
+    luts = [O.LUTS['camvid'], np.arange(5)]
+    want, _ = O.multi_source_labels([o[0] for o in outs], [o[1] for o in outs], luts, 'all')
+    marg = O.fuse_sources([o[0] for o in outs], [o[1] for o in outs], luts, 'all')["marginal"].numpy()
+    lst, _ = U.generate_pseudo_label_multi_model(models, ['camvid', 'somewhere_else'], 'cuda:0', str(tmp_path / "a"), 0, N, None, None,
+                                                 _args(merge_label_policy='all'), None, None, None, testloader=_loader(), batch_images=2)
+    for i, ln in enumerate(open(lst)):
+        got = np.array(Image.open(ln.strip().split(',')[1]))
+        assert not ((got != want[i]) & ~marg[i]).any()
+    with pytest.raises(ValueError, match="no label table"):
+        U.generate_pseudo_label_multi_model([TinySource(13, 5), TinySource(20, 6)], ['camvid', 'somewhere_else'], 'cuda:0',
+                                            str(tmp_path / "b"), 0, N, None, None, _args(merge_label_policy='all'), None, None, None,
+                                            testloader=_loader(), batch_images=2)

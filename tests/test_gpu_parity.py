@@ -378,7 +378,7 @@ def test_bracketed_protocol_sharded_raw_abi(ops, dev):
                            "cand_hist")
             all_reduce(ranks)
             for r in ranks:
-                _lib.check(lib.mspl_cand_select(p(r.hist), K, ps, p(r.state), p(r.thresh), st), "cand_select")
+                _lib.check(lib.mspl_cand_select(p(r.hist), K, ps, p(r.state), p(r.thresh), None, -1, st), "cand_select")
         for r in ranks:
             _lib.check(lib.mspl_cand_apply(p(r.lab), p(r.cf), p(r.thresh), p(r.cand), p(r.count), K, 4, p(r.final), None, p(r.fh), st),
                        "cand_apply")
@@ -1007,7 +1007,7 @@ def test_c_abi_error_codes(dev):
     assert rc == -3                                                          # more classes than the fused loss is built for
     assert lib.mspl_radix_select(None, 5, 0, 0.2, None, None, None, st) == -1
     assert lib.mspl_bracket_select(None, 5, 0.2, 4, None, None, None, None, None, None, st) == -1
-    assert lib.mspl_cand_select(None, 5, 0, None, None, st) == -1
+    assert lib.mspl_cand_select(None, 5, 0, None, None, None, -1, st) == -1
     lab8 = torch.zeros(64, dtype=torch.uint8, device=dev)
     cf = torch.zeros(64, device=dev)
     br = torch.zeros(10, device=dev)

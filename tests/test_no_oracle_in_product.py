@@ -76,12 +76,16 @@ def test_ops_reject_cpu_tensors():
 
 
 def test_only_the_checker_legs_of_the_entry_points_use_the_oracle():
-    """bench.py: the oracle appears only inside cpu_baseline() / run_reference(); __graft_entry__.py: only in build() (import
-    check) and smoke()."""
-    for fname, allowed in (("bench.py", {"cpu_baseline", "run_reference"}), ("__graft_entry__.py", {"build", "smoke"})):
+    """bench.py: the oracle appears only inside the CpuPath class (the CPU arm), which in turn is only instantiated by
+    cpu_baseline() / run_reference(); __graft_entry__.py: only in build() (checker build) and smoke()."""
+    for fname, allowed in (("bench.py", {"CpuPath"}), ("__graft_entry__.py", {"build", "smoke"})):
         tree = ast.parse(open(os.path.join(ROOT, fname)).read())
         for node in tree.body:
             uses = [n for n in ast.walk(node) if isinstance(n, ast.ImportFrom) and n.module and n.module.split(".")[0] == "oracle"]
             uses += [n for n in ast.walk(node) if isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names)]
             if uses:
-                assert isinstance(node, ast.FunctionDef) and node.name in allowed, (fname, getattr(node, "name", type(node).__name__))
+                assert isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in allowed, (fname, getattr(node, "name", type(node).__name__))
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and any(isinstance(n, ast.Name) and n.id == "CpuPath" for n in ast.walk(node)):
+            assert node.name in {"cpu_baseline", "run_reference"}, node.name

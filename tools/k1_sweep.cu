@@ -81,29 +81,34 @@ static void run_variant(const char* name, Bench& b, F launch) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
-#define DIRECT(P, CH, THREADS, MINB, GK, TOP2)                                                                                   \
-    if (want(#P "," #CH "," #THREADS "," #MINB, "direct"))                                                                      \
-    run_variant("direct P=" #P " CH=" #CH " thr=" #THREADS " minb=" #MINB " gk=" #GK " top2=" #TOP2, b, [&] {                  \
-        return launch_fuse_direct<P, THREADS>(fuse_sources_direct_kernel<P, CH, 5, GK, TOP2, THREADS, MINB>, b.prm, 0);         \
-    })
-#define TMA(NCW, P, CH, NST, GK, TOP2)                                                                                           \
+#define DIRECT(CH, THREADS, MINB, GK)                                                                                            \
+    if (want(#CH "," #THREADS "," #MINB, "direct")) {                                                                            \
+        build_class_order(b.prm, CH);                                                                                            \
+        run_variant("direct P=1 CH=" #CH " thr=" #THREADS " minb=" #MINB " gk=" #GK, b, [&] {                                  \
+            return launch_fuse_direct<THREADS>(fuse_sources_direct_kernel<CH, 5, GK, THREADS, MINB>, b.prm, 5, 0);               \
+        });                                                                                                                      \
+    }
+#define TMA(NCW, P, CH, NST, GK)                                                                                                 \
     if (want(#NCW "," #P "," #CH "," #NST, "tma")) {                                                                             \
         using Cfg = TmaCfg<NCW, P, CH, NST>;                                                                                     \
-        if (tma_eligible<Cfg>(b.prm))                                                                                            \
-            run_variant("tma ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST " gk=" #GK " top2=" #TOP2, b, [&] {                \
-                return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<NCW, P, CH, NST, 5, GK, TOP2>, b.prm, 0);                   \
+        build_class_order(b.prm, CH);                                                                                            \
+        if (tma_eligible(b.prm) && Cfg::smem_bytes(5, 5) <= 227 * 1024)                                                          \
+            run_variant("tma ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST " gk=" #GK, b, [&] {                               \
+                return launch_fuse_tma<Cfg>(fuse_sources_tma_kernel<NCW, P, CH, NST, 5, GK>, b.prm, 5, 0);                       \
             });                                                                                                                  \
+        else printf("tma ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST ": not eligible / smem %zu\n", Cfg::smem_bytes(5, 5));  \
     }
 
-#define LOWRES(NCW, P, CH, NST)                                                                                                  \
-    {                                                                                                                            \
+#define LOWRES(NCW, P, CH, NST, GK)                                                                                              \
+    if (want(#NCW "," #P "," #NST, "lowres")) {                                                                                  \
         FuseParams q = b.prm;                                                                                                    \
-        const size_t smem = lowres_plan(q, NCW * 32 * P, CH, NST);                                                               \
+        build_class_order(q, CH);                                                                                                \
+        const size_t smem = lowres_plan(q, NCW * 32 * P, CH, NST, 5, (NCW + 1) * 32, P, 768, 384);                               \
         if (smem && smem <= 227 * 1024)                                                                                          \
-            run_variant("lowres ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST, b, [&] {                                       \
-                return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, false, true>, q, smem, 0);     \
+            run_variant("lowres ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST " gk=" #GK, b, [&] {                            \
+                return launch_fuse_lowres<NCW, P>(fuse_sources_lowres_kernel<NCW, P, CH, NST, 5, GK, 768, 384>, q, smem, 0);     \
             });                                                                                                                  \
-        else printf("lowres ncw=" #NCW " P=" #P " stages=" #NST ": smem %zu does not fit\n", smem);                             \
+        else printf("lowres ncw=" #NCW " stages=" #NST ": smem %zu does not fit\n", smem);                                     \
     }
 
 static const char* g_filter = nullptr;
@@ -158,56 +163,33 @@ int main(int argc, char** argv) {
     if (lowres) {
         // main at H/2 x W/2 and aux at H/4 x W/4 occupy the front of the full-size buffers allocated above
         b.prm.lr.H = (int)H; b.prm.lr.W = (int)W;
-        LOWRES(15, 2, 5, 4);
-        LOWRES(19, 2, 5, 3);
-        LOWRES(19, 2, 5, 4);
-        LOWRES(23, 2, 5, 3);
-        LOWRES(11, 2, 5, 4);
-        LOWRES(15, 1, 5, 4);
-        LOWRES(23, 1, 5, 4);
-        LOWRES(31, 1, 5, 4);
-        LOWRES(15, 4, 5, 3);
+        if (!gk) {
+            LOWRES(15, 2, 5, 4, false);
+            LOWRES(15, 2, 5, 3, false);
+            LOWRES(19, 2, 5, 3, false);
+            LOWRES(11, 2, 5, 4, false);
+        } else {
+            LOWRES(15, 2, 5, 4, true);
+            LOWRES(19, 2, 5, 3, true);
+        }
         return 0;
     }
     if (!gk) {
-        DIRECT(4, 5, 256, 2, false, true);
-        DIRECT(4, 5, 256, 1, false, true);
-        DIRECT(4, 5, 128, 4, false, true);
-        DIRECT(4, 4, 256, 2, false, true);
-        DIRECT(2, 5, 256, 3, false, true);
-        DIRECT(2, 5, 256, 4, false, true);
-        DIRECT(2, 10, 256, 2, false, true);
-        DIRECT(1, 5, 256, 4, false, true);
-        DIRECT(1, 10, 256, 4, false, true);
-        DIRECT(4, 5, 256, 2, false, false);
-        TMA(8, 4, 5, 4, false, true);
-        TMA(8, 2, 5, 8, false, true);
-        TMA(16, 2, 5, 4, false, true);
-        TMA(16, 1, 5, 8, false, true);
-        TMA(12, 2, 5, 5, false, true);
-        TMA(8, 4, 4, 5, false, true);
-        TMA(16, 2, 4, 5, false, true);
-        TMA(8, 4, 10, 2, false, true);
-        TMA(16, 2, 10, 2, false, true);
-        TMA(15, 2, 5, 4, false, true);
-        TMA(19, 2, 5, 3, false, true);
-        TMA(20, 2, 5, 3, false, true);
-        TMA(24, 2, 5, 2, false, true);
-        TMA(24, 1, 5, 5, false, true);
-        TMA(30, 1, 5, 4, false, true);
-        TMA(16, 2, 5, 4, false, false);
-        TMA(8, 4, 5, 4, false, false);
+        DIRECT(5, 256, 2, false);
+        TMA(15, 2, 5, 4, false);
+        TMA(15, 2, 5, 3, false);
+        TMA(11, 2, 5, 5, false);
+        TMA(19, 2, 5, 3, false);
+        TMA(15, 2, 4, 5, false);
+        TMA(15, 2, 7, 3, false);
+        TMA(7, 2, 5, 8, false);
     } else {
-        DIRECT(4, 5, 256, 1, true, true);
-        DIRECT(2, 5, 256, 2, true, true);
-        DIRECT(1, 5, 256, 3, true, true);
-        TMA(8, 4, 5, 4, true, true);
-        TMA(16, 2, 5, 4, true, true);
-        TMA(15, 2, 5, 4, true, true);
-        TMA(19, 2, 5, 3, true, true);
-        TMA(12, 2, 5, 5, true, true);
-        TMA(11, 2, 5, 5, true, true);
-        TMA(16, 1, 5, 8, true, true);
+        DIRECT(5, 256, 1, true);
+        TMA(15, 2, 5, 4, true);
+        TMA(15, 2, 5, 3, true);
+        TMA(11, 2, 5, 5, true);
+        TMA(19, 2, 5, 3, true);
+        TMA(15, 2, 4, 5, true);
     }
     return 0;
 }
