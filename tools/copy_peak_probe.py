@@ -36,3 +36,39 @@ for gib in (2, 8, 16, 32, 40):
     del a, b
     torch.cuda.empty_cache()
 print(json.dumps(rows))
+
+
+def sustained(seconds=4.0, gib=8):
+    """The same copy back to back for `seconds`: GB/s of every copy in launch order next to nvidia-smi's SM clock / power /
+    throttle reasons -- what the HBM system delivers once the board's power limiter has settled (K1 runs inside 130-ms steps that
+    follow seconds of warm-up and data generation, not in a cold burst)."""
+    import subprocess
+    import time
+    n = gib * (1 << 30) // 4
+    a = torch.empty(n, dtype=torch.float32, device=dev).normal_()
+    b = torch.empty_like(a)
+    b.copy_(a)
+    torch.cuda.synchronize()
+    smi = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,clocks.mem,power.draw,clocks_event_reasons.sw_power_cap",
+                            "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+    events = []
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            events.append((e0, e1))
+        torch.cuda.synchronize()
+    smi.terminate()
+    rates = [2 * n * 4 / 1e6 / x.elapsed_time(y) for x, y in events]
+    k = max(1, len(rates) // 8)
+    buckets = [round(sum(rates[i:i + k]) / len(rates[i:i + k]), 1) for i in range(0, len(rates), k)]
+    lines = [ln.strip() for ln in smi.stdout.read().splitlines() if ln.strip()]
+    print(json.dumps({"sustained_copy_gib_each_way": gib, "seconds": seconds, "copies": len(rates),
+                      "gbs_first": round(rates[0], 1), "gbs_by_eighth_of_run": buckets, "gbs_last_quarter": round(sum(rates[-len(rates) // 4:]) / (len(rates) // 4), 1),
+                      "nvidia_smi_sm_mhz,mem_mhz,watts,sw_power_cap": lines[::max(1, len(lines) // 10)]}))
+
+
+sustained()
