@@ -109,14 +109,18 @@ struct PixelFusion {
                 best = fmaxf(best, g[k][p]);
             }
             SourceResult r = finish_source(sc[p], best);
-            if (r.degenerate) {
-                r.rz = best;
-                r.inv_sz = r.pmax = slow.pmax(p, best);
+            if (r.degenerate | (second == best)) {       // one rare, divergent region for both out-of-line recomputations
+                if (r.degenerate) {
+                    r.rz = best;
+                    r.inv_sz = r.pmax = slow.pmax(p, best);
+                }
+                if (second == best) lab = slow.label(p); // first maximal class in ORIGINAL order decides (np.argmax, :904)
             }
-            if (second == best) lab = slow.label(p);     // first maximal class in ORIGINAL order decides (np.argmax, :904)
             d[p] = r.kld;
             usum[p] += r.kld;
-            marg[p] |= (1.0f - exp_neg(second - best)) * r.pmax < kNearTieMargin;
+            // near-tie report: P_best - P_runner-up = pmax * (1 - e^{-(best - second)}) < 1e-6.  The gap that satisfies it is at
+            // most 1e-6 / pmax <= 2.6e-4 (pmax >= 1/256), where 1 - e^{-x} = x to a relative 1.3e-4: the exponential is not needed.
+            marg[p] |= (best - second) * r.pmax < kNearTieMargin;
             votes[p] += 1u << (4 * lab);
             last_lab[p] = lab;
             if (GK) {
@@ -369,16 +373,23 @@ MSPL_DEVINL void mbar_arrive(uint64_t* bar) {
 MSPL_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+// Wait for a phase of `bar`.  try_wait suspends the warp in hardware up to a time limit before it has to be re-issued; the
+// hint asks for a long suspension (the producer is HBM-bound: a stage takes ~1 us to fill), so that waiting warps do not burn
+// issue slots -- and board power, which is what caps this kernel's sustained rate -- on a spin loop (6 % of all executed
+// instructions without the hint, ncu source page of round 2).
+#ifndef MSPL_MBAR_SUSPEND_NS
+#define MSPL_MBAR_SUSPEND_NS 2000
+#endif
 MSPL_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)MSPL_MBAR_SUSPEND_NS)
         : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streaming data: L2 evict-first hint

@@ -376,7 +376,13 @@ __global__ void __launch_bounds__(256) bracket_select_kernel(unsigned long long*
     }
 }
 
-constexpr int kCandBuf = 768;                                  // per-warp staging entries
+#ifndef MSPL_CLASSIFY_UNR
+#define MSPL_CLASSIFY_UNR 6        // (label word, conf float4) groups a thread of the classify pass keeps in flight (4: 0.293 ms, 6: 0.285 ms, 8: 0.294 ms at 245.76 Mpix)
+#endif
+#ifndef MSPL_CLASSIFY_MINB
+#define MSPL_CLASSIFY_MINB 4
+#endif
+constexpr int kCandBuf = 256 + 128 * (MSPL_CLASSIFY_UNR > 4 ? MSPL_CLASSIFY_UNR : 4);   // per-warp staging entries (768 at UNR 4)
 
 // The one full pass of the bracketed protocol: settle every pixel outside its class's bracket, stage the candidates.
 // Candidates get the ignore label for now (and count as ignored); cand_apply patches the ones that reach the threshold.
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(256, 4) bracket_classify_kernel(const uint8_t*
 // generic kernel above, which matters because these passes are bound by the half-rate integer pipe, not by HBM.
 // Pixels of labels outside [0,K) are written as ignored.
 template <int UNR, bool COUNT>
-__global__ void __launch_bounds__(256, 4) bracket_classify_words_kernel(const uint32_t* __restrict__ label4,
+__global__ void __launch_bounds__(256, MSPL_CLASSIFY_MINB) bracket_classify_words_kernel(const uint32_t* __restrict__ label4,
                                                                       const float4* __restrict__ conf4,
                                                                       const float2* __restrict__ bracket, uint32_t n_groups, int K,
                                                                       int ignore, uint32_t* __restrict__ final4,
@@ -942,7 +948,7 @@ extern "C" int mspl_bracket_classify(const uint8_t* label, const float* conf, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2* br = reinterpret_cast<const float2*>(bracket);
     if (num_pixels % 4 == 0 && ok(4)) {
-        constexpr int kU = 4;
+        constexpr int kU = MSPL_CLASSIFY_UNR;
         const uint32_t n_groups = (uint32_t)(num_pixels / 4);
         auto launch = [&](auto kern) {
             const int64_t grid = resident_grid(kern, n_groups / kU + 1, 256, 0);
