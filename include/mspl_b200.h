@@ -35,7 +35,9 @@ extern "C" {
 #define MSPL_ABI_VERSION 4
 #define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
 #define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
-#define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14) */
+#define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14).  Eight is what the
+                                 * kernels' packed per-pixel state holds: votes in 8 x 4 bits, class counts in 8 x 8 bits, and a
+                                 * K x 2048-bin confidence histogram per CTA in shared memory (64 KB at K = 8) next to the ring */
 #define MSPL_RADIX_BINS 2048    /* bins of one histogram pass: linear conf bins, or 11 bits of the key */
 #define MSPL_RADIX_PASSES 3     /* 11 + 11 + 10 bits of the order-preserving fp32 key               */
 
@@ -91,6 +93,14 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
                       int ignore_label, int ds_rate, uint8_t* label, float* conf, float* unc,
                       float* const* kld_per_source, unsigned long long* class_hist,
                       unsigned long long* conf_hist, unsigned long long* marginal_count, void* stream);
+
+/* Host-only helper (no device work): the order in which K1 visits the classes of a source with label table `lut` -- sorted by
+ * (target class, class index), so that the kernel tracks one running maximum per target group instead of an arg-max index.
+ * row[i] = the source class visited i-th (num_classes bytes); seg[j] bit b = slot b of chunk j is the last class of its target
+ * group (ceil(num_classes / chunk) bytes); *present bit k = some class maps to target k.  Returns the chunk size (classes per
+ * shared-memory stage) the build uses, or a negative status. */
+MSPL_API int mspl_class_order(const uint8_t* lut, int num_classes, int num_target_classes, uint8_t* row, uint8_t* seg,
+                     uint32_t* present);
 
 /* ---- K1-lowres: K1 with the network's final upsample fused in (next-row component) ------------------
  * Same outputs and semantics as mspl_fuse_sources, but source s hands over its logits BEFORE the final

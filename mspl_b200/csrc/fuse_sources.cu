@@ -85,6 +85,26 @@ extern "C" const char* mspl_fuse_variant(void) {
     return name;
 }
 
+// Host-only: the class visiting order K1 derives from a label table (no device work; lets the host logic be tested on CPU).
+extern "C" int mspl_class_order(const uint8_t* lut, int num_classes, int num_target_classes, uint8_t* row, uint8_t* seg,
+                                uint32_t* present) {
+    if (!lut || !row || !seg || !present || num_classes < 1 || num_classes > MSPL_MAX_SRC_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (num_target_classes < 2 || num_target_classes > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    FuseParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.S = 1;
+    prm.C[0] = num_classes;
+    for (int c = 0; c < num_classes; ++c) {
+        if (lut[c] >= num_target_classes) return MSPL_ERR_BAD_ARG;
+        prm.lut[0][c] = lut[c];
+    }
+    if (!build_class_order(prm, MSPL_FUSE_CH)) return MSPL_ERR_UNSUPPORTED;
+    memcpy(row, prm.order[0].row, (size_t)num_classes);
+    memcpy(seg, prm.order[0].seg, (size_t)((num_classes + MSPL_FUSE_CH - 1) / MSPL_FUSE_CH));
+    *present = prm.order[0].present;
+    return MSPL_FUSE_CH;
+}
+
 extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
                                  const int* num_classes, const uint8_t* const* lut, int64_t num_images,
                                  int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,

@@ -95,3 +95,32 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
                            "-lmspl_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True)
     assert "CH=" in out
+
+
+def test_class_order_groups_classes_by_target(lib):
+    """Host logic of K1's grouped class order (no GPU): a permutation of the classes sorted by (target, class index), one
+    boundary bit per target group, the `present` mask -- for the reference's three tables and for awkward ones."""
+    import ctypes
+    import numpy as np
+    from mspl_b200.data_loader.segmentation.greenhouse import SOURCE_TABLES
+    tables = [np.asarray(t) for t in SOURCE_TABLES.values()]
+    tables += [np.array([2]), np.array([3, 0, 1, 0, 3, 1, 2, 2, 0, 1, 3]), np.arange(256) % 5, np.array([1] * 7)]
+    for lut in tables:
+        C = len(lut)
+        buf = (ctypes.c_ubyte * C)(*[int(v) for v in lut])
+        row = (ctypes.c_ubyte * C)()
+        seg = (ctypes.c_ubyte * 64)()
+        present = ctypes.c_uint32(0)
+        ch = lib.mspl_class_order(buf, C, 5, row, seg, ctypes.byref(present))
+        assert ch >= 4
+        order = np.array(list(row))
+        assert sorted(order.tolist()) == list(range(C))                                  # a permutation
+        tgt = lut[order]
+        assert np.array_equal(order, np.array(sorted(range(C), key=lambda c: (lut[c], c))))  # by (target, class index)
+        bits = [(seg[i // ch] >> (i % ch)) & 1 for i in range(C)]
+        want = [int(i == C - 1 or tgt[i + 1] != tgt[i]) for i in range(C)]
+        assert bits == want                                                               # one boundary per target group
+        assert present.value == sum(1 << int(k) for k in set(lut.tolist()))
+        assert sum(bits) == bin(present.value).count("1")
+    bad = (ctypes.c_ubyte * 3)(1, 2, 7)
+    assert lib.mspl_class_order(bad, 3, 5, (ctypes.c_ubyte * 3)(), (ctypes.c_ubyte * 64)(), ctypes.byref(ctypes.c_uint32())) == -1
