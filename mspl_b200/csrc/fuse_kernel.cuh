@@ -26,6 +26,7 @@ struct LowresGeom {
     int ha[MSPL_MAX_SOURCES], wa[MSPL_MAX_SOURCES];   // aux head resolution per source
     int main_cls_stride, aux_cls_stride, aux_base;    // float offsets inside one ring stage
     int stage_floats;
+    int same_geometry;                                // every source has the head sizes of source 0
 };
 
 struct FuseParams {
@@ -703,8 +704,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_labels_tma_kernel(cons
 static __device__ __noinline__ float lowres_logit_global(const float* __restrict__ src, int hin, int win, float rh, float rw, int y, int x) {
     const float hr = rh * (float)y, wr = rw * (float)x;
     const int i0 = (int)hr, x0 = (int)wr;
-    const float h1 = hr - (float)i0, h0 = 1.0f - h1, w1 = wr - (float)x0, w0 = 1.0f - w1;
     const int dy = (i0 < hin - 1) ? win : 0, dx = (x0 < win - 1) ? 1 : 0;
+    const float h1 = hr - (float)i0, h0 = 1.0f - h1;
+    const float w1 = dx ? wr - (float)x0 : 0.0f, w0 = dx ? 1.0f - (wr - (float)x0) : 1.0f;      // as PackedTaps::set
     const float* p = src + (int64_t)i0 * win + x0;
     const float top = fmaf(w1, __ldg(p + dx), __fmul_rn(w0, __ldg(p))), bot = fmaf(w1, __ldg(p + dy + dx), __fmul_rn(w0, __ldg(p + dy)));
     return fmaf(h1, bot, __fmul_rn(h0, top));
@@ -739,31 +741,39 @@ struct LowresSlowPath {
     }
 };
 
-// One head's bilinear taps of a thread's P pixels: offsets of the four neighbours inside a stage's class block (relative to
-// the first staged source row) and the packed weights.
+// One head's bilinear taps of a thread's P pixels inside a stage's class block (relative to the first staged source row).
+// Only TWO offsets per pixel are kept -- the upper-left neighbour and the one below it (clamped at the last source row as ATen
+// does) -- and the right-hand neighbours are read at +1 float through the load's immediate offset.  At the last source column
+// ATen reads the same element twice (w1p = 0); here the horizontal weights are forced to (1, 0) there, so the +1 read (one float
+// past the row: the next row, or finite slack inside the stage, which lowres_plan provides and the kernel zero-fills once) is
+// multiplied by an exact zero.  Four registers of offsets instead of eight per head keeps the taps resident across the chunk
+// loop -- with eight the compiler re-derived them from the pixel coordinates in every chunk (~70 instructions).
 template <int P>
 struct PackedTaps {
-    int o00[P], o01[P], o10[P], o11[P];
+    int o0[P], o1[P];
     Px<P> w0, w1, h0, h1;
     MSPL_DEVINL void set(const int (&yy)[P], const int (&xx)[P], int hin, int win, float rh, float rw, int first_row) {
         float fw0[P], fw1[P], fh0[P], fh1[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const BilinearTap t = make_tap(yy[p], xx[p], hin, win, rh, rw, first_row);
-            o00[p] = t.o00; o01[p] = t.o00 + t.dx; o10[p] = t.o00 + t.dy; o11[p] = t.o00 + t.dy + t.dx;
-            fw0[p] = t.w0; fw1[p] = t.w1; fh0[p] = t.h0; fh1[p] = t.h1;
+            o0[p] = t.o00;
+            o1[p] = t.o00 + t.dy;
+            const bool last_col = t.dx == 0;
+            fw0[p] = last_col ? 1.0f : t.w0; fw1[p] = last_col ? 0.0f : t.w1; fh0[p] = t.h0; fh1[p] = t.h1;
         }
         w0 = Px<P>::make(fw0); w1 = Px<P>::make(fw1); h0 = Px<P>::make(fh0); h1 = Px<P>::make(fh1);
     }
+    template <int D>
     MSPL_DEVINL Px<P> gather(const float* __restrict__ s, const int (&o)[P]) const {
         float v[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) v[p] = s[o[p]];
+        for (int p = 0; p < P; ++p) v[p] = s[o[p] + D];
         return Px<P>::make(v);
     }
     MSPL_DEVINL Px<P> interpolate(const float* __restrict__ s) const {
-        const Px<P> top = fma(w1, gather(s, o01), w0 * gather(s, o00));
-        const Px<P> bot = fma(w1, gather(s, o11), w0 * gather(s, o10));
+        const Px<P> top = fma(w1, gather<1>(s, o0), w0 * gather<0>(s, o0));
+        const Px<P> bot = fma(w1, gather<1>(s, o1), w0 * gather<0>(s, o1));
         return fma(h1, bot, h0 * top);
     }
 };
@@ -782,6 +792,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
     uint64_t* empty = full + NSTAGE;
     const TallySmem ts = tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), kThreads);
+    // the +1-float reads of PackedTaps may touch floats no copy ever wrote (slack between class blocks): make them finite once
+    for (int i = threadIdx.x; i < stage_floats * NSTAGE; i += kThreads) ring[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             tma::mbar_init(&full[i], 1);
@@ -789,6 +801,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // generic-proxy writes above must be ordered before the async-proxy (bulk copy) writes into the same shared memory
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     const int S = prm.S, H = lr.H, W = lr.W;
@@ -865,13 +879,15 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
             }
             PixelFusion<P, KT, GK> fus;
             fus.reset();
+            PackedTaps<P> tm, ta;
             for (int s = 0; s < S; ++s) {
                 const int C = prm.C[s], hm = lr.hm[s], wm = lr.wm[s], ha = lr.ha[s], wa = lr.wa[s];
                 const float rhm = lowres_scale(hm, H), rwm = lowres_scale(wm, W);
                 const float rha = lowres_scale(ha, H), rwa = lowres_scale(wa, W);
-                PackedTaps<P> tm, ta;
-                tm.set(yy, xx, hm, wm, rhm, rwm, (int)(rhm * (float)y_first));
-                ta.set(yy, xx, ha, wa, rha, rwa, (int)(rha * (float)y_first));
+                if (s == 0 || !lr.same_geometry) {      // sources of one architecture share their head sizes: taps once per tile
+                    tm.set(yy, xx, hm, wm, rhm, rwm, (int)(rhm * (float)y_first));
+                    ta.set(yy, xx, ha, wa, rha, rwa, (int)(rha * (float)y_first));
+                }
                 SourceStats<P> st;
                 st.reset(group);
                 int chunk = 0;

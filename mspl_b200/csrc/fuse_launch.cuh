@@ -106,14 +106,21 @@ inline size_t lowres_plan(FuseParams& prm, int tile_pix, int chunk, int stages, 
         aux_stride = std::max(aux_stride, rows(lr.ha[s]) * lr.wa[s]);
     }
     if (fixed_main > 0 && fixed_aux > 0) {          // compile-time strides requested: they must cover the geometry
-        if (main_stride > fixed_main || aux_stride > fixed_aux) return 0;
+        if (main_stride + 1 > fixed_main || aux_stride + 1 > fixed_aux) return 0;      // (+1: the taps' one-float overread)
         main_stride = fixed_main;
         aux_stride = fixed_aux;
+    }
+    else {                                           // the taps read one float past a row (PackedTaps): keep it inside the block
+        main_stride += 4;
+        aux_stride += 4;
     }
     lr.main_cls_stride = main_stride;
     lr.aux_cls_stride = aux_stride;
     lr.aux_base = chunk * main_stride;
     lr.stage_floats = chunk * (main_stride + aux_stride);
+    lr.same_geometry = 1;
+    for (int s = 1; s < prm.S; ++s)
+        if (lr.hm[s] != lr.hm[0] || lr.wm[s] != lr.wm[0] || lr.ha[s] != lr.ha[0] || lr.wa[s] != lr.wa[0]) lr.same_geometry = 0;
     return sizeof(float) * (size_t)lr.stage_floats * stages + 2 * stages * sizeof(uint64_t) +
            fuse_tally_smem_bytes(prm.K, KT, nthreads, P) + 128;
 }
