@@ -156,7 +156,9 @@ MSPL_API int mspl_vote_labels(const uint8_t* labels, int num_sources, int64_t nu
  *   mspl_cand_apply: candidates with conf >= thresh[label] get their label back (final_label, ignore_mask, final_hist).
  *   mspl_cand_resolve: the three candidate passes, their selects and mspl_cand_apply in ONE launch, for callers with no
  *     all-reduce to run in between (a single rank): one 8-CTA thread-block cluster per class, per-CTA candidate cache in
- *     shared memory, histograms combined over distributed shared memory.  final_hist gets this call's own patch.
+ *     shared memory, histograms combined over distributed shared memory.  final_hist gets this call's own patch.  Returns
+ *     MSPL_ERR_UNSUPPORTED (nothing launched) when the device cannot host an 8-CTA cluster of this kernel right now (e.g. a
+ *     partitioned GPU): run the three mspl_cand_hist_pass / mspl_cand_select rounds and mspl_cand_apply instead.
  *
  * (2) Generic radix -- 3 full passes over the order-preserving fp32 key (11+11+10 bits), 16 B/pixel with
  *   mspl_apply_thresholds: zero `hist` and `state`; for pass = 0, 1, 2: mspl_radix_hist_pass; [all-reduce hist];

@@ -1039,6 +1039,11 @@ extern "C" int mspl_cand_resolve(const uint8_t* label, const float* conf, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    int clusters = 0;       // e.g. a partitioned GPU without 8 free SMs in one GPC: the caller runs the multi-launch passes instead
+    if (cudaOccupancyMaxActiveClusters(&clusters, cand_resolve_kernel, &cfg) != cudaSuccess || clusters < 1) {
+        cudaGetLastError();
+        return MSPL_ERR_UNSUPPORTED;
+    }
     if (cudaLaunchKernelEx(&cfg, cand_resolve_kernel, label, conf, cand_index, cand_count, pixels_per_image, ignore_label, ds_rate,
                            static_cast<RadixState*>(state), thresh, final_label, ignore_mask, final_hist) != cudaSuccess) {
         cudaGetLastError();

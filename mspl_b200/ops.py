@@ -299,11 +299,15 @@ def select_and_apply(label, conf, portion=0.2, ds_rate=1, num_classes=5, ignore_
         _lib.check(lib.mspl_bracket_classify(_ptr(label), _ptr(conf), _ptr(bracket), npix, K, ign, _ptr(final), _ptr(mask),
                                              _ptr(final_hist if outputs and not from_hist else None), _ptr(cand_index),
                                              _ptr(cand_count), st), "mspl_bracket_classify")
+        resolved = False
         if single:
-            _lib.check(lib.mspl_cand_resolve(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, ign, int(ds_rate),
-                                             _ptr(state), _ptr(thresh), _ptr(final), _ptr(mask), _ptr(final_hist if outputs else None),
-                                             st), "mspl_cand_resolve")
-        else:
+            rc = lib.mspl_cand_resolve(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, ign, int(ds_rate),
+                                       _ptr(state), _ptr(thresh), _ptr(final), _ptr(mask), _ptr(final_hist if outputs else None), st)
+            if rc != -3:        # MSPL_ERR_UNSUPPORTED: no room for an 8-CTA cluster on this device -> the multi-launch passes below
+                _lib.check(rc, "mspl_cand_resolve")
+                resolved = True
+            all_reduce = lambda t: t
+        if not resolved:
             for p in range(RADIX_PASSES):
                 _lib.check(lib.mspl_cand_hist_pass(_ptr(label), _ptr(conf), _ptr(cand_index), _ptr(cand_count), hw, K, p, _ptr(state),
                                                    _ptr(hist), int(ds_rate), st), "mspl_cand_hist_pass")

@@ -124,3 +124,13 @@ def test_class_order_groups_classes_by_target(lib):
         assert sum(bits) == bin(present.value).count("1")
     bad = (ctypes.c_ubyte * 3)(1, 2, 7)
     assert lib.mspl_class_order(bad, 3, 5, (ctypes.c_ubyte * 3)(), (ctypes.c_ubyte * 64)(), ctypes.byref(ctypes.c_uint32())) == -1
+
+
+def test_vote_threshold_follows_merge_outputs_rule():
+    """merge_outputs' threshold rule (uest_seg_multi_os.py:697-705): None / 'half' / anything else -> S//2+1, 'all' -> S, an int
+    (bool included, as `isinstance(thresh, int)` accepts it) <= S -> itself."""
+    from mspl_b200.ops import vote_threshold
+    assert vote_threshold(3, None) == 2 and vote_threshold(3, 'half') == 2 and vote_threshold(3, 'all') == 3
+    assert vote_threshold(3, 1) == 1 and vote_threshold(3, 3) == 3 and vote_threshold(3, 4) == 2
+    assert vote_threshold(3, True) == 1 and vote_threshold(3, False) == 0
+    assert vote_threshold(3, '2') == 2 and vote_threshold(4, 'nonsense') == 3 and vote_threshold(1, None) == 1
