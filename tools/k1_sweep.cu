@@ -115,6 +115,17 @@ static void run_variant(const char* name, Bench& b, F launch) {
         else printf("tma ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST ": not eligible / smem %zu\n", Cfg::smem_bytes(5, 5));  \
     }
 
+#define LABELS(NCW, P, CH, NST)                                                                                                  \
+    if (want(#NCW "," #P "," #CH "," #NST, "labels")) {                                                                          \
+        using Cfg = TmaCfg<NCW, P, CH, NST>;                                                                                     \
+        FuseParams q = b.prm;                                                                                                    \
+        q.conf = nullptr; q.unc = nullptr; q.conf_hist = nullptr; q.marginal = nullptr;                                         \
+        build_class_order(q, CH);                                                                                                \
+        run_variant("labels-only ncw=" #NCW " P=" #P " CH=" #CH " stages=" #NST " (no softmax: z, arg-max, table, vote)", b, [&] { \
+            return launch_fuse_tma<Cfg>(fuse_labels_tma_kernel<NCW, P, CH, NST, 5>, q, 5, 0);                                    \
+        });                                                                                                                      \
+    }
+
 #define LOWRES(NCW, P, CH, NST, GK)                                                                                              \
     if (want(#NCW "," #P "," #NST, "lowres")) {                                                                                  \
         FuseParams q = b.prm;                                                                                                    \
@@ -194,6 +205,7 @@ int main(int argc, char** argv) {
         return 0;
     }
     if (!gk) {
+        LABELS(15, 2, 5, 4);
         DIRECT(5, 256, 2, false);
         TMA(15, 2, 5, 4, false);
         TMA(15, 2, 5, 3, false);
