@@ -43,7 +43,7 @@ POOL_IMAGES = 2500            # resident logits per rank: 93.4 GB at 480x256 (co
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("native", "reference"), default="native")
     ap.add_argument("--images-total", type=int, default=0,
