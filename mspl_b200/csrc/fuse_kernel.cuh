@@ -432,6 +432,13 @@ template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
 #define MSPL_PEEL_FIRST 0
 #endif
 
+// Unroll factor of the consumers' chunk loop (2 lets the running statistics ping-pong between two register sets instead of
+// being moved back at the end of every chunk: 164 instead of 171 instructions per chunk, 124 registers).
+#ifndef MSPL_CHUNK_UNROLL
+#define MSPL_CHUNK_UNROLL 1
+#endif
+constexpr int kChunkUnroll = MSPL_CHUNK_UNROLL;
+
 template <int NCW, int P, int CH, int NSTAGE>
 struct TmaCfg {
     static constexpr int kThreads = (NCW + 1) * 32;
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                 SourceStats<P> st;
                 st.reset(group);
                 int chunk = 0;
-#pragma unroll 1
+#pragma unroll kChunkUnroll
                 for (int c0 = 0; c0 < C; c0 += CH, ++chunk) {
                     Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
