@@ -61,76 +61,128 @@ inline size_t fuse_tally_smem_bytes(int K, int KT, int nthreads, int P) {
 // for the winning label and G_s[label] is simply that source's max probability.
 template <int P, int K, bool GK>
 struct PixelFusion {
-    float usum[P], csum[P], Fk[GK ? K : 1][P];
-    uint32_t votes[P];
-    int last_lab[P];        // label proposed by the most recent source (unanimity shortcut in finish())
-    bool marg[P];
+    Px<P> usum, csum, Fk[GK ? K : 1];
+    Px<P> mgap;             // min over the sources of (z_best - z_runner-up) * pmax: the near-tie report
+    uint32_t votes[P];      // 4 bits per target class
+    uint32_t last_vote[P];  // what the most recent source added (1 << 4*label): unanimity shortcut in finish()
+    bool marg[P];           // set by finish()
 
     MSPL_DEVINL void reset() {
+        usum = csum = Px<P>::splat(0.f);
+        mgap = Px<P>::splat(INFINITY);
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            usum[p] = csum[p] = 0.f;
-            votes[p] = 0;
-            marg[p] = false;
+        for (int k = 0; k < (GK ? K : 1); ++k) Fk[k] = Px<P>::splat(0.f);
 #pragma unroll
-            for (int k = 0; k < (GK ? K : 1); ++k) Fk[k][p] = 0.f;
-        }
+        for (int p = 0; p < P; ++p) votes[p] = 0;
     }
 
     // Fold one finished source in; d receives its KLD map values.  group: this thread's column of committed group maxima
-    // (g_k = max z over the source classes mapped to target k), present: targets the source's table maps to at all.
+    // (g = max z over the source classes mapped to one target; committed in ascending target order, one entry per target the
+    // source's table maps to at all).
     // slow: the kernel's out-of-line recomputations, slow.pmax(p, Mz) for a degenerate pixel and slow.label(p) for an exact
     // tie between two targets (only those touch global memory again).
     template <typename Slow>
-    MSPL_DEVINL void add_source(const SourceStats<P>& st, const Px<P>* group, int gstride, uint32_t present, float (&d)[P], Slow slow) {
-        SourceScalars sc[P];
-        unpack_stats<P>(st, sc);
-        float g[K][P];
-        const Px<P>* next = group;          // committed in ascending target order: one entry per target that is present
+    MSPL_DEVINL void add_source(const SourceStats<P>& st, const Px<P>* group, int gstride, const ClassOrder& order, float (&d)[P], Slow slow) {
+        // the source's proposal: the target whose group holds the largest z; the runner-up target gives the near-tie
+        // report and detects exact ties between targets (those are resolved out of line, so the scan order is free)
+        Px<P> gp[K];
+        float best[P], second[P];
+        uint32_t vote[P];
+        if (GK) {
+            // per-target probabilities are needed below: one value per TARGET, -inf for targets the table never maps to
+            const uint32_t present = order.present;
+            float g[K][P];
+            const Px<P>* next = group;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if ((present >> k) & 1u) {
-                next->get(g[k]);
-                next += gstride;
-            } else {
+            for (int k = 0; k < K; ++k) {
+                if ((present >> k) & 1u) {
+                    gp[k] = *next;
+                    next += gstride;
+                } else {
+                    gp[k] = Px<P>::splat(-INFINITY);
+                }
+                gp[k].get(g[k]);
+            }
 #pragma unroll
-                for (int p = 0; p < P; ++p) g[k][p] = -INFINITY;
+            for (int p = 0; p < P; ++p) {
+                best[p] = g[0][p];
+                second[p] = -INFINITY;
+                vote[p] = 1u;
+#pragma unroll
+                for (int k = 1; k < K; ++k) {
+                    second[p] = fmaxf(second[p], fminf(best[p], g[k][p]));
+                    vote[p] = (g[k][p] > best[p]) ? (1u << (4 * k)) : vote[p];
+                    best[p] = fmaxf(best[p], g[k][p]);
+                }
+            }
+        } else {
+            // only the winner matters: scan the committed groups themselves (ngroup <= K of them, a warp-uniform count) and
+            // take the winner's vote increment from the order's table.  All K entries of the column are loaded up front
+            // (those past ngroup are stale and never looked at), so the loads overlap instead of trailing the branches.
+            const int ngroup = (int)order.ngroup;
+#pragma unroll
+            for (int i = 0; i < K; ++i) gp[i] = Px<P>::load_shared_now(group + i * gstride);
+            gp[0].get(best);
+#pragma unroll
+            for (int p = 0; p < P; ++p) vote[p] = order.vote[0];
+#pragma unroll
+            for (int i = 1; i < K; ++i) {
+                if (i < ngroup) {
+                    float gi[P];
+                    gp[i].get(gi);
+                    const uint32_t vi = order.vote[i];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const float lo = fminf(best[p], gi[p]);
+                        second[p] = (i == 1) ? lo : fmaxf(second[p], lo);
+                        vote[p] = (gi[p] > best[p]) ? vi : vote[p];
+                        best[p] = fmaxf(best[p], gi[p]);
+                    }
+                } else if (i == 1) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) second[p] = -INFINITY;       // a single group: no runner-up
+                }
             }
         }
+        const Px<P> Mz = Px<P>::make(best);
+        SourceResult<P> r = finish_source<P>(st, Mz);
+        float gap[P];
+        r.gap.get(gap);
+        bool slow_any = false;
+#pragma unroll
+        for (int p = 0; p < P; ++p) slow_any |= degenerate_source(gap[p], best[p]) | (second[p] == best[p]);
+        if (slow_any) {       // ONE rare, divergent region for both out-of-line recomputations of all the thread's pixels
+            float rz[P], inv_sz[P], pm[P];
+            r.rz.get(rz); r.inv_sz.get(inv_sz); r.pmax.get(pm);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (degenerate_source(gap[p], best[p])) {
+                    rz[p] = best[p];
+                    inv_sz[p] = pm[p] = slow.pmax(p, best[p]);
+                }
+                // first maximal class in ORIGINAL order decides (np.argmax, :904)
+                if (second[p] == best[p]) vote[p] = 1u << (4 * slow.label(p));
+            }
+            r.rz = Px<P>::make(rz); r.inv_sz = Px<P>::make(inv_sz); r.pmax = Px<P>::make(pm);
+        }
+        r.kld.get(d);
+        usum = usum + r.kld;
+        // near-tie report: P_best - P_runner-up = pmax * (1 - e^{-(best - second)}) < 1e-6.  The gap that satisfies it is at
+        // most 1e-6 / pmax <= 2.6e-4 (pmax >= 1/256), where 1 - e^{-x} = x to a relative 1.3e-4: the exponential is not needed.
+        // (finish() compares the minimum over the sources; a NaN product -- both -inf -- never lowers it.)
+        mgap = pmin<P>(mgap, (Mz - Px<P>::make(second)) * r.pmax);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            // the source's proposal: the target whose group holds the largest z; the runner-up target gives the near-tie
-            // report and detects exact ties between targets
-            float best = g[0][p], second = -INFINITY;
-            int lab = 0;
+            votes[p] += vote[p];
+            last_vote[p] = vote[p];
+        }
+        if (GK) {
+            const Px<P> l2e = Px<P>::splat(kLog2e), one = Px<P>::splat(1.0f);
 #pragma unroll
-            for (int k = 1; k < K; ++k) {
-                second = fmaxf(second, fminf(best, g[k][p]));
-                lab = (g[k][p] > best) ? k : lab;
-                best = fmaxf(best, g[k][p]);
-            }
-            SourceResult r = finish_source(sc[p], best);
-            if (r.degenerate | (second == best)) {       // one rare, divergent region for both out-of-line recomputations
-                if (r.degenerate) {
-                    r.rz = best;
-                    r.inv_sz = r.pmax = slow.pmax(p, best);
-                }
-                if (second == best) lab = slow.label(p); // first maximal class in ORIGINAL order decides (np.argmax, :904)
-            }
-            d[p] = r.kld;
-            usum[p] += r.kld;
-            // near-tie report: P_best - P_runner-up = pmax * (1 - e^{-(best - second)}) < 1e-6.  The gap that satisfies it is at
-            // most 1e-6 / pmax <= 2.6e-4 (pmax >= 1/256), where 1 - e^{-x} = x to a relative 1.3e-4: the exponential is not needed.
-            marg[p] |= (best - second) * r.pmax < kNearTieMargin;
-            votes[p] += 1u << (4 * lab);
-            last_lab[p] = lab;
-            if (GK) {
-#pragma unroll
-                for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
-                    Fk[k][p] += fminf(exp_neg(g[k][p] - r.rz) * r.inv_sz, 1.0f);
-            } else {
-                csum[p] += r.pmax;
-            }
+            for (int k = 1; k < K; ++k)      // G[0] = 0 as transfer_output_to_greenhouse (uest_seg_multi_os.py:1340)
+                Fk[GK ? k : 0] = Fk[GK ? k : 0] + pmin<P>(pex2<P>((gp[k] - r.rz) * l2e) * r.inv_sz, one);
+        } else {
+            csum = csum + r.pmax;
         }
     }
 
@@ -138,15 +190,20 @@ struct PixelFusion {
     // definition states; far inside the 1e-5 tolerance) to keep IEEE division sequences out of the hot loop
     MSPL_DEVINL void finish(const FuseParams& prm, float inv_s, int (&label)[P], float (&conf)[P], float (&unc)[P]) {
         const int ignore = prm.ignore;
+        float us[P], cs[P], fk[GK ? K : 1][P], mg[P];
+        usum.get(us); csum.get(cs); mgap.get(mg);
+#pragma unroll
+        for (int k = 0; k < (GK ? K : 1); ++k) Fk[k].get(fk[k]);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            unc[p] = usum[p] * inv_s;
+            unc[p] = us[p] * inv_s;
+            marg[p] = mg[p] < kNearTieMargin;
             if (prm.policy == MSPL_POLICY_PROB) {
                 float best = -1.f, second = -1.f;
                 int bk = 0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float f = GK ? Fk[GK ? k : 0][p] * inv_s : 0.f;
+                    const float f = GK ? fk[GK ? k : 0][p] * inv_s : 0.f;
                     second = fmaxf(second, fminf(best, f));
                     bk = (f > best) ? k : bk;
                     best = fmaxf(best, f);
@@ -160,7 +217,7 @@ struct PixelFusion {
                 if (!GK && prm.vote_t == prm.S) {
                     // unanimity required ('all'): the label survives only if every source proposed it, so looking at the
                     // last proposal's count is enough -- no scan over the classes
-                    bk = last_lab[p];
+                    bk = (31 - __clz((int)last_vote[p])) >> 2;
                     bc = (votes[p] >> (4 * bk)) & 15u;
                 } else {
 #pragma unroll
@@ -172,12 +229,12 @@ struct PixelFusion {
                 label[p] = ((int)bc < prm.vote_t) ? ignore : bk;     // (:716)
                 // every source voted for `label`, so G_s[label] is that source's max probability -- except for target class 0,
                 // which transfer_output_to_greenhouse never fills (G[0] = 0, uest_seg_multi_os.py:1340)
-                float f = (label[p] == 0) ? 0.f : csum[p];
+                float f = (label[p] == 0) ? 0.f : cs[p];
                 if (GK) {
                     // F[label] by masking (a select chain over k gets turned into an indexed load of Fk from LOCAL memory)
                     uint32_t bits = 0;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) bits |= __float_as_uint(Fk[GK ? k : 0][p]) & (0u - (uint32_t)(label[p] == k));
+                    for (int k = 0; k < K; ++k) bits |= __float_as_uint(fk[GK ? k : 0][p]) & (0u - (uint32_t)(label[p] == k));
                     f = __uint_as_float(bits);
                 }
                 conf[p] = (label[p] == ignore) ? 0.f : f * inv_s;
@@ -335,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(cons
                 fold_chunk<P, CH>(st, m, a, c0 == 0, prm.order[s].seg[c0 / CH], THREADS);
             }
             float d[P];
-            fus.add_source(st, group, THREADS, prm.order[s].present, d, GlobalSlowPath<P>{prm, s, n, off, ts.lut + s * MSPL_MAX_SRC_CLASSES});
+            fus.add_source(st, group, THREADS, prm.order[s], d, GlobalSlowPath<P>{prm, s, n, off, ts.lut + s * MSPL_MAX_SRC_CLASSES});
             if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
         }
         int label[P];
@@ -425,9 +482,11 @@ template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
 
 }  // namespace tma
 
-// 1: the first chunk of a source skips the rescale of the (empty) accumulators -- a branch around it whose merge costs ~20
-// register moves per chunk in the generated code; 0 (default): the rescale runs on the empty accumulators too (it evaluates
-// to exact zeros, see SourceStats::reset) and the chunk body is branch-free.
+// 0: the rescale runs on the first chunk's empty accumulators too (it evaluates to exact zeros, see SourceStats::reset) and the
+// chunk body is branch-free; 1: the first chunk of a source skips it through a branch inside the loop, whose merge costs ~20
+// register moves per chunk in the generated code; 2: the first chunk is peeled OUT of the loop as a second, straight-line copy of
+// the body without the rescale (4 MUFU and 11 packed operations less for 3 of the benchmark's 8 chunks per pixel pair).  Same bits
+// in all three.
 #ifndef MSPL_PEEL_FIRST
 #define MSPL_PEEL_FIRST 0
 #endif
@@ -549,6 +608,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
         uint32_t phase = 0;
         const int px = (warp * 32 + lane) * P;          // this thread's first pixel inside the tile
         Px<P>* group = reinterpret_cast<Px<P>*>(ts.group) + threadIdx.x;
+        bool any_kld = false;
+        for (int s = 0; s < S; ++s) any_kld |= prm.kld[s] != nullptr;
         TileWalker walk(blockIdx.x, gridDim.x, tpi);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, walk.next()) {
             const int64_t n = walk.image;
@@ -557,12 +618,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
             PixelFusion<P, KT, GK> fus;
             fus.reset();
             for (int s = 0; s < S; ++s) {
-                const int C = prm.C[s];
+                const int nchunk = (int)prm.order[s].nchunk;
+                __builtin_assume(nchunk > 0);             // every source has a class: no zero-trip guard around the chunk loop
                 SourceStats<P> st;
                 st.reset(group);
-                int chunk = 0;
-#pragma unroll kChunkUnroll
-                for (int c0 = 0; c0 < C; c0 += CH, ++chunk) {
+                // one chunk: wait for its stage, copy the thread's values to registers, hand the stage back, fold
+                auto consume = [&](int chunk, bool first) {
                     Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * Cfg::kStageFloats + px;
@@ -573,12 +634,22 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
                     __syncwarp();
                     if (lane == 0) tma::mbar_arrive(&empty[stage]);    // values are in registers: hand the slot back
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    fold_chunk<P, CH>(st, m, a, MSPL_PEEL_FIRST ? c0 == 0 : false, prm.order[s].seg[chunk], Cfg::kThreads);
-                }
+                    fold_chunk<P, CH>(st, m, a, first, prm.order[s].seg[chunk], Cfg::kThreads);
+                };
+#if MSPL_PEEL_FIRST == 2
+                consume(0, true);           // straight-line copy of the body without the rescale of the (empty) accumulators
+#pragma unroll kChunkUnroll
+                for (int chunk = 1; chunk < nchunk; ++chunk) consume(chunk, false);
+#else
+#pragma unroll kChunkUnroll
+                for (int chunk = 0; chunk < nchunk; ++chunk) consume(chunk, MSPL_PEEL_FIRST ? chunk == 0 : false);
+#endif
                 float d[P];
-                fus.add_source(st, group, Cfg::kThreads, prm.order[s].present, d,
+                fus.add_source(st, group, Cfg::kThreads, prm.order[s], d,
                                GlobalSlowPath<P>{prm, s, n, active ? off : 0, ts.lut + s * MSPL_MAX_SRC_CLASSES});
-                if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+                if (any_kld) {     // per-source KLD maps are off in the label-generation job: one uniform test, hoisted
+                    if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
+                }
             }
             int label[P];
             float conf[P], unc[P];
@@ -918,7 +989,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                                        rhm, rwm, rha, rwa, {}, {}, ts.lut + s * MSPL_MAX_SRC_CLASSES};
 #pragma unroll
                 for (int p = 0; p < P; ++p) { slow.yy[p] = yy[p]; slow.xx[p] = xx[p]; }
-                fus.add_source(st, group, kThreads, prm.order[s].present, d, slow);
+                fus.add_source(st, group, kThreads, prm.order[s], d, slow);
                 if (prm.kld[s] != nullptr && active) PixVec<P>::store(prm.kld[s] + n * hw + off, d);
             }
             int label[P];

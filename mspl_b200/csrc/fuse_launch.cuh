@@ -31,6 +31,7 @@ inline bool build_class_order(FuseParams& prm, int chunk) {
         memset(&o, 0, sizeof(o));
         const int C = prm.C[s];
         if ((C + chunk - 1) / chunk > kMaxChunksPerSource) return false;
+        o.nchunk = (uint32_t)((C + chunk - 1) / chunk);
         int i = 0;
         for (int k = 0; k < MSPL_MAX_CLASSES; ++k)
             for (int c = 0; c < C; ++c)
@@ -39,6 +40,8 @@ inline bool build_class_order(FuseParams& prm, int chunk) {
                     o.present |= 1u << k;
                 }
         if (i != C) return false;            // a table entry >= MSPL_MAX_CLASSES (callers validate entries < K)
+        for (int k = 0; k < MSPL_MAX_CLASSES; ++k)
+            if ((o.present >> k) & 1u) o.vote[o.ngroup++] = 1u << (4 * k);
         for (i = 0; i < C; ++i) {
             const int k = prm.lut[s][o.row[i]];
             const bool last = (i == C - 1) || prm.lut[s][o.row[i + 1]] != k;

@@ -35,11 +35,13 @@ MSPL_DEVINL float exp_neg(float t) { return ex2_approx(t * kLog2e); }
 MSPL_DEVINL float exp_half_neg(float t) { return ex2_approx(t * (0.5f * kLog2e)); }   // e^{t/2}
 // natural log through MUFU.LG2 (absolute error <= 2^-22.6 * |log2 x| * ln 2: ~5e-7 at worst for the ratios of softmax sums it
 // is used on, inside the 2e-6 KLD floor), instead of the ~20-instruction branchy logf
-MSPL_DEVINL float log_fast(float x) {
+MSPL_DEVINL float lg2_approx(float x) {
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r * 0.6931471805599453f;
+    return r;
 }
+constexpr float kLn2 = 0.6931471805599453f;
+MSPL_DEVINL float log_fast(float x) { return lg2_approx(x) * kLn2; }
 // 1/x through MUFU.RCP alone (relative error <= 2^-23; the IEEE sequence adds a Newton step and a range check per call)
 MSPL_DEVINL float rcp_fast(float x) {
     float r;
@@ -62,6 +64,12 @@ template <> struct Px<1> {
     static MSPL_DEVINL Px splat(float x) { return Px{x}; }
     static MSPL_DEVINL Px make(const float (&a)[1]) { return Px{a[0]}; }
     MSPL_DEVINL void get(float (&a)[1]) const { a[0] = v; }
+    // load from shared memory HERE (a volatile access keeps its place: the compiler would otherwise sink it into a later branch)
+    static MSPL_DEVINL Px load_shared_now(const Px* p) {
+        Px r;
+        asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(r.v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return r;
+    }
 };
 // (the _rn intrinsics are never contracted into fused multiply-adds, so the scalar kernel rounds exactly where the packed
 //  instructions do and both produce the same bits)
@@ -80,6 +88,11 @@ template <> struct Px<2> {
     static MSPL_DEVINL Px splat(float x) { return pack(x, x); }
     static MSPL_DEVINL Px make(const float (&a)[2]) { return pack(a[0], a[1]); }
     MSPL_DEVINL void get(float (&a)[2]) const { asm("mov.b64 {%0, %1}, %2;" : "=f"(a[0]), "=f"(a[1]) : "l"(v)); }
+    static MSPL_DEVINL Px load_shared_now(const Px* p) {
+        Px r;
+        asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(r.v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return r;
+    }
 };
 MSPL_DEVINL Px<2> operator+(Px<2> a, Px<2> b) {
     Px<2> r;
@@ -120,6 +133,14 @@ MSPL_DEVINL Px<P> pmax(Px<P> a, Px<P> b) {
     return Px<P>::make(x);
 }
 template <int P>
+MSPL_DEVINL Px<P> pmin(Px<P> a, Px<P> b) {
+    float x[P], y[P];
+    a.get(x); b.get(y);
+#pragma unroll
+    for (int p = 0; p < P; ++p) x[p] = fminf(x[p], y[p]);
+    return Px<P>::make(x);
+}
+template <int P>
 MSPL_DEVINL Px<P> pmax3(Px<P> a, Px<P> b, Px<P> c) {
     float x[P], y[P], z[P];
     a.get(x); b.get(y); c.get(z);
@@ -148,6 +169,10 @@ struct ClassOrder {
     uint8_t row[MSPL_MAX_SRC_CLASSES];
     uint8_t seg[kMaxChunksPerSource];
     uint32_t present;
+    uint32_t nchunk;          // ceil(C / CH) for the chunk size the order was built for
+    uint32_t ngroup;          // number of target groups = popcount(present) (>= 1)
+    uint32_t vote[MSPL_MAX_CLASSES];   // vote[i] = 1 << 4*(target class of the i-th committed group): what a source adds to a
+                                       // pixel's packed vote counters (4 bits per target) when group i holds its largest z
 };
 
 // Running per-pixel statistics of one source.
@@ -220,14 +245,16 @@ MSPL_DEVINL void fold_chunk(SourceStats<P>& st, const Px<P> (&m)[CH], const Px<P
     st.Sm = sm; st.Sa = sa; st.Sz = sz; st.T = t;
 }
 
-// What the fusion needs from a finished source, per pixel.
+// What the fusion needs from a finished source, for the thread's P pixels at once (packed like the running statistics: the
+// adds / multiplies are one instruction for both pixels, only MUFU and min/max are issued per lane).
+template <int P>
 struct SourceResult {
-    float kld;      // KL(softmax(m) || softmax(a)) = T/Sm - log Sm + log Sa  (= sum_c p1 (logp1 - logp2), log_softmax taken as
+    Px<P> kld;      // KL(softmax(m) || softmax(a)) = T/Sm - log Sm + log Sa  (= sum_c p1 (logp1 - logp2), log_softmax taken as
                     // (x - max) - log(sum) like ATen, so no large maxima are ever added back)
-    float rz;       // Rz = Mm + Ma/2, the reference point of Sz
-    float inv_sz;   // 1 / Sz:  softmax(z)_c = e^{z_c - Rz} * inv_sz
-    float pmax;     // probability of the argmax class = e^{Mz - Rz} * inv_sz
-    bool degenerate;  // the two heads' maxima sit more than kMaxSharedExpGap logit units above Mz: caller takes the slow path
+    Px<P> rz;       // Rz = Mm + Ma/2, the reference point of Sz
+    Px<P> inv_sz;   // 1 / Sz:  softmax(z)_c = e^{z_c - Rz} * inv_sz
+    Px<P> pmax;     // probability of the argmax class = e^{Mz - Rz} * inv_sz
+    Px<P> gap;      // Mz - Rz (<= 0): the caller's degeneracy test reads it
 };
 
 // Largest Rz - Mz for which the shared exponentials are trusted.  e^{z-Rz} is formed as a product of two MUFU.EX2 results
@@ -247,27 +274,23 @@ constexpr float kMaxSharedExpGap = 16.f;
 #endif
 constexpr float kMaxSharedExpLogit = MSPL_MAX_EXP_LOGIT;
 
-// Per-pixel scalars of a finished source (lane p of the packed stats) and the maximum Mz of its fused logits.
-struct SourceScalars { float Mm, Sm, Ma, Sa, Sz, T; };
-
-MSPL_DEVINL SourceResult finish_source(const SourceScalars& s, float Mz) {
-    SourceResult r;
-    const float inv_sm = rcp_fast(s.Sm);
-    r.kld = fmaf(s.T, inv_sm, log_fast(s.Sa * inv_sm));
-    r.rz = fmaf(0.5f, s.Ma, s.Mm);
-    r.inv_sz = rcp_fast(s.Sz);
-    r.pmax = fminf(exp_neg(Mz - r.rz) * r.inv_sz, 1.0f);     // numerator and its term of Sz round separately: clamp
-    r.degenerate = !(r.rz - Mz <= kMaxSharedExpGap) || !(fabsf(Mz) <= kMaxSharedExpLogit);     // also catches NaN
+// Mz: the maximum of the source's fused logits, per pixel.
+template <int P>
+MSPL_DEVINL SourceResult<P> finish_source(const SourceStats<P>& st, Px<P> Mz) {
+    SourceResult<P> r;
+    const Px<P> inv_sm = lanewise<P>(st.Sm, [](float x) { return rcp_fast(x); });
+    const Px<P> lg2 = lanewise<P>(st.Sa * inv_sm, [](float x) { return lg2_approx(x); });
+    r.kld = fma(st.T, inv_sm, lg2 * Px<P>::splat(kLn2));
+    r.rz = fma(Px<P>::splat(0.5f), st.Ma, st.Mm);
+    r.inv_sz = lanewise<P>(st.Sz, [](float x) { return rcp_fast(x); });
+    r.gap = Mz - r.rz;
+    // numerator and its term of Sz round separately: clamp
+    r.pmax = pmin<P>(pex2<P>(r.gap * Px<P>::splat(kLog2e)) * r.inv_sz, Px<P>::splat(1.0f));
     return r;
 }
-
-template <int P>
-MSPL_DEVINL void unpack_stats(const SourceStats<P>& st, SourceScalars (&s)[P]) {
-    float Mm[P], Sm[P], Ma[P], Sa[P], Sz[P], T[P];
-    st.Mm.get(Mm); st.Sm.get(Sm); st.Ma.get(Ma); st.Sa.get(Sa); st.Sz.get(Sz); st.T.get(T);
-#pragma unroll
-    for (int p = 0; p < P; ++p) s[p] = SourceScalars{Mm[p], Sm[p], Ma[p], Sa[p], Sz[p], T[p]};
-}
+// the two heads' maxima sit more than kMaxSharedExpGap logit units above Mz, or |Mz| is beyond the trusted range: the caller
+// takes the slow path for this pixel (also catches NaN)
+MSPL_DEVINL bool degenerate_source(float gap, float Mz) { return !(gap >= -kMaxSharedExpGap) || !(fabsf(Mz) <= kMaxSharedExpLogit); }
 
 // ---- out-of-line slow paths (rare, divergent): they must not bloat the hot loop's instruction footprint ----------------
 // Degenerate pixel: recompute 1/sum_c e^{z_c - Mz} directly from global memory.
