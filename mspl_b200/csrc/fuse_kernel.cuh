@@ -490,6 +490,9 @@ template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
 #ifndef MSPL_PEEL_FIRST
 #define MSPL_PEEL_FIRST 0
 #endif
+#ifndef MSPL_LOWRES_PEEL_FIRST       // the same choice for the fused-upsample kernel
+#define MSPL_LOWRES_PEEL_FIRST MSPL_PEEL_FIRST
+#endif
 
 // Unroll factor of the consumers' chunk loop (2 lets the running statistics ping-pong between two register sets instead of
 // being moved back at the end of every chunk: 164 instead of 171 instructions per chunk, 124 registers).
@@ -968,9 +971,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 }
                 SourceStats<P> st;
                 st.reset(group);
-                int chunk = 0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += CH, ++chunk) {
+                const int nchunk = (int)prm.order[s].nchunk;
+                __builtin_assume(nchunk > 0);
+                auto consume = [&](int chunk, bool first) {
                     Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
                     const float* src = ring + (size_t)stage * stage_floats;
@@ -982,8 +985,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                     __syncwarp();
                     if (lane == 0) tma::mbar_arrive(&empty[stage]);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    fold_chunk<P, CH>(st, m, a, MSPL_PEEL_FIRST ? c0 == 0 : false, prm.order[s].seg[chunk], kThreads);
-                }
+                    fold_chunk<P, CH>(st, m, a, first, prm.order[s].seg[chunk], kThreads);
+                };
+#if MSPL_LOWRES_PEEL_FIRST == 2
+                consume(0, true);
+#pragma unroll 1
+                for (int chunk = 1; chunk < nchunk; ++chunk) consume(chunk, false);
+#else
+#pragma unroll 1
+                for (int chunk = 0; chunk < nchunk; ++chunk) consume(chunk, MSPL_LOWRES_PEEL_FIRST ? chunk == 0 : false);
+#endif
                 float d[P];
                 LowresSlowPath<P> slow{prm.main[s] + (n * C) * hm * wm, prm.aux[s] + (n * C) * ha * wa, C, hm, wm, ha, wa,
                                        rhm, rwm, rha, rwa, {}, {}, ts.lut + s * MSPL_MAX_SRC_CLASSES};
