@@ -490,9 +490,15 @@ template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
 #ifndef MSPL_PEEL_FIRST
 #define MSPL_PEEL_FIRST 0
 #endif
-#ifndef MSPL_LOWRES_PEEL_FIRST       // the same choice for the fused-upsample kernel
-#define MSPL_LOWRES_PEEL_FIRST MSPL_PEEL_FIRST
+// The same choice for the fused-upsample kernel, which is bound by instruction issue, not by HBM or board power: there the
+// peeled first chunk is worth 4.5 % (1.895 -> 1.810 ms per 200 images, same-box A/B, identical outputs).
+#ifndef MSPL_LOWRES_PEEL_FIRST
+#define MSPL_LOWRES_PEEL_FIRST 2
 #endif
+#ifndef MSPL_LOWRES_CHUNK_UNROLL
+#define MSPL_LOWRES_CHUNK_UNROLL 1
+#endif
+constexpr int kLowresChunkUnroll = MSPL_LOWRES_CHUNK_UNROLL;
 
 // Unroll factor of the consumers' chunk loop (2 lets the running statistics ping-pong between two register sets instead of
 // being moved back at the end of every chunk: 164 instead of 171 instructions per chunk, 124 registers).
@@ -829,10 +835,22 @@ struct LowresSlowPath {
 // past the row: the next row, or finite slack inside the stage, which lowres_plan provides and the kernel zero-fills once) is
 // multiplied by an exact zero.  Four registers of offsets instead of eight per head keeps the taps resident across the chunk
 // loop -- with eight the compiler re-derived them from the pixel coordinates in every chunk (~70 instructions).
+// MSPL_LOWRES_FOUR_WEIGHTS = 1 (default): the bilinear sample is evaluated as one chain over the four taps with the products of the
+// vertical and horizontal weights formed once per tile, W00*v00 + W01*v01 + W10*v10 + W11*v11 (1 packed multiply + 3 packed fmas per
+// class, head and pixel pair); 0: ATen's nesting h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11) (6 packed instructions).  The two
+// differ in the last ulp of the interpolated logit, like the kernel and ATen do anyway (the parity definition of this row, DESIGN.md
+// section 4, excuses exactly that); the kernel is bound by instruction issue, so the 20 instructions per chunk are worth ~5 %.
+#ifndef MSPL_LOWRES_FOUR_WEIGHTS
+#define MSPL_LOWRES_FOUR_WEIGHTS 1
+#endif
 template <int P>
 struct PackedTaps {
     int o0[P], o1[P];
+#if MSPL_LOWRES_FOUR_WEIGHTS
+    Px<P> w00, w01, w10, w11;
+#else
     Px<P> w0, w1, h0, h1;
+#endif
     MSPL_DEVINL void set(const int (&yy)[P], const int (&xx)[P], int hin, int win, float rh, float rw, int first_row) {
         float fw0[P], fw1[P], fh0[P], fh1[P];
 #pragma unroll
@@ -843,7 +861,12 @@ struct PackedTaps {
             const bool last_col = t.dx == 0;
             fw0[p] = last_col ? 1.0f : t.w0; fw1[p] = last_col ? 0.0f : t.w1; fh0[p] = t.h0; fh1[p] = t.h1;
         }
+#if MSPL_LOWRES_FOUR_WEIGHTS
+        const Px<P> w0 = Px<P>::make(fw0), w1 = Px<P>::make(fw1), h0 = Px<P>::make(fh0), h1 = Px<P>::make(fh1);
+        w00 = h0 * w0; w01 = h0 * w1; w10 = h1 * w0; w11 = h1 * w1;
+#else
         w0 = Px<P>::make(fw0); w1 = Px<P>::make(fw1); h0 = Px<P>::make(fh0); h1 = Px<P>::make(fh1);
+#endif
     }
     template <int D>
     MSPL_DEVINL Px<P> gather(const float* __restrict__ s, const int (&o)[P]) const {
@@ -853,9 +876,16 @@ struct PackedTaps {
         return Px<P>::make(v);
     }
     MSPL_DEVINL Px<P> interpolate(const float* __restrict__ s) const {
+#if MSPL_LOWRES_FOUR_WEIGHTS
+        Px<P> acc = w00 * gather<0>(s, o0);
+        acc = fma(w01, gather<1>(s, o0), acc);
+        acc = fma(w10, gather<0>(s, o1), acc);
+        return fma(w11, gather<1>(s, o1), acc);
+#else
         const Px<P> top = fma(w1, gather<1>(s, o0), w0 * gather<0>(s, o0));
         const Px<P> bot = fma(w1, gather<1>(s, o1), w0 * gather<0>(s, o1));
         return fma(h1, bot, h0 * top);
+#endif
     }
 };
 
@@ -989,10 +1019,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 };
 #if MSPL_LOWRES_PEEL_FIRST == 2
                 consume(0, true);
-#pragma unroll 1
+#pragma unroll kLowresChunkUnroll
                 for (int chunk = 1; chunk < nchunk; ++chunk) consume(chunk, false);
 #else
-#pragma unroll 1
+#pragma unroll kLowresChunkUnroll
                 for (int chunk = 0; chunk < nchunk; ++chunk) consume(chunk, MSPL_LOWRES_PEEL_FIRST ? chunk == 0 : false);
 #endif
                 float d[P];
