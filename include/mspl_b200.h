@@ -32,7 +32,7 @@ extern "C" {
 #define MSPL_API
 #endif
 
-#define MSPL_ABI_VERSION 4
+#define MSPL_ABI_VERSION 5
 #define MSPL_MAX_SOURCES 8      /* S: sources fused per call                                        */
 #define MSPL_MAX_SRC_CLASSES 256 /* C_s: the reference stores the argmax as uint8 (uest_seg_multi_os.py:904) */
 #define MSPL_MAX_CLASSES 8      /* K: target (greenhouse) classes; the reference has 5 (greenhouse.py:14).  Eight is what the
@@ -101,6 +101,12 @@ MSPL_API int mspl_fuse_sources(int num_sources, const float* const* main_logits,
  * shared-memory stage) the build uses, or a negative status. */
 MSPL_API int mspl_class_order(const uint8_t* lut, int num_classes, int num_target_classes, uint8_t* row, uint8_t* seg,
                      uint32_t* present);
+/* Host-only companion: what K1's per-source epilogue reads besides the order -- vote[i] = 1 << 4*(target class of the i-th target
+ * group in visiting order), the amount a source adds to a pixel's packed vote counters (4 bits per target, hence
+ * MSPL_MAX_SOURCES <= 15) when that group holds its largest fused logit (MSPL_MAX_CLASSES entries, unused ones 0), and *nchunk =
+ * the number of class chunks the kernel's inner loop runs for this source.  Returns the number of target groups (>= 1), or a
+ * negative status. */
+MSPL_API int mspl_class_order_votes(const uint8_t* lut, int num_classes, int num_target_classes, uint32_t* vote, uint32_t* nchunk);
 
 /* ---- K1-lowres: K1 with the network's final upsample fused in (next-row component) ------------------
  * Same outputs and semantics as mspl_fuse_sources, but source s hands over its logits BEFORE the final

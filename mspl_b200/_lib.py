@@ -23,6 +23,7 @@ SIGNATURES = {
     "mspl_fuse_sources_lowres": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mspl_class_order": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "mspl_class_order_votes": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     "mspl_vote_labels": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "mspl_radix_state_bytes": (c_sz, [c_int]),
     "mspl_conf_hist": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp]),

@@ -305,7 +305,9 @@ struct TallySmem {
     uint8_t* row;       // [S][256] class visiting order
     float* group;       // [KT][nthreads][P]
 };
-MSPL_DEVINL TallySmem tally_smem_init(const FuseParams& prm, unsigned char* smem, int nthreads) {
+// group_floats: size of the committed-maxima region ([KT][nthreads][P] floats), set to -inf so that no entry is ever read
+// uninitialised (the epilogue loads all KT entries of a thread's column and ignores those its source did not commit).
+MSPL_DEVINL TallySmem tally_smem_init(const FuseParams& prm, unsigned char* smem, int nthreads, int group_floats = 0) {
     TallySmem t;
     const int nbins = prm.K * MSPL_RADIX_BINS;
     t.hist = reinterpret_cast<uint32_t*>(smem);
@@ -316,6 +318,7 @@ MSPL_DEVINL TallySmem tally_smem_init(const FuseParams& prm, unsigned char* smem
     off = (off + 15) & ~(size_t)15;
     t.group = reinterpret_cast<float*>(smem + off);
     for (int i = threadIdx.x; i < nbins; i += nthreads) t.hist[i] = 0;
+    for (int i = threadIdx.x; i < group_floats; i += nthreads) t.group[i] = -INFINITY;
     if (threadIdx.x < 16) t.cls[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < prm.S * MSPL_MAX_SRC_CLASSES; i += nthreads) {
         t.lut[i] = prm.lut[i / MSPL_MAX_SRC_CLASSES][i % MSPL_MAX_SRC_CLASSES];
@@ -350,7 +353,7 @@ template <int CH, int KT, bool GK, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fuse_sources_direct_kernel(const __grid_constant__ FuseParams prm) {
     constexpr int P = 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TallySmem ts = tally_smem_init(prm, smem_raw, THREADS);
+    const TallySmem ts = tally_smem_init(prm, smem_raw, THREADS, KT * THREADS);
     __syncthreads();
 
     const int S = prm.S;
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_tma_kernel(con
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kRingBytes);
     uint64_t* empty = full + NSTAGE;
-    const TallySmem ts = tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), Cfg::kThreads);
+    const TallySmem ts = tally_smem_init(prm, smem_raw + Cfg::kRingBytes + 2 * NSTAGE * sizeof(uint64_t), Cfg::kThreads, KT * Cfg::kThreads * P);
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             tma::mbar_init(&full[i], 1);
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
     const size_t ring_bytes = sizeof(float) * (size_t)stage_floats * NSTAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
     uint64_t* empty = full + NSTAGE;
-    const TallySmem ts = tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), kThreads);
+    const TallySmem ts = tally_smem_init(prm, smem_raw + ring_bytes + 2 * NSTAGE * sizeof(uint64_t), kThreads, KT * kThreads * P);
     // the +1-float reads of PackedTaps may touch floats no copy ever wrote (slack between class blocks): make them finite once
     for (int i = threadIdx.x; i < stage_floats * NSTAGE; i += kThreads) ring[i] = 0.f;
     if (threadIdx.x == 0) {

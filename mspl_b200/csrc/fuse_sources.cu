@@ -105,6 +105,23 @@ extern "C" int mspl_class_order(const uint8_t* lut, int num_classes, int num_tar
     return MSPL_FUSE_CH;
 }
 
+extern "C" int mspl_class_order_votes(const uint8_t* lut, int num_classes, int num_target_classes, uint32_t* vote, uint32_t* nchunk) {
+    if (!lut || !vote || !nchunk || num_classes < 1 || num_classes > MSPL_MAX_SRC_CLASSES) return MSPL_ERR_BAD_ARG;
+    if (num_target_classes < 2 || num_target_classes > MSPL_MAX_CLASSES) return MSPL_ERR_BAD_ARG;
+    FuseParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.S = 1;
+    prm.C[0] = num_classes;
+    for (int c = 0; c < num_classes; ++c) {
+        if (lut[c] >= num_target_classes) return MSPL_ERR_BAD_ARG;
+        prm.lut[0][c] = lut[c];
+    }
+    if (!build_class_order(prm, MSPL_FUSE_CH)) return MSPL_ERR_UNSUPPORTED;
+    memcpy(vote, prm.order[0].vote, sizeof(prm.order[0].vote));
+    *nchunk = prm.order[0].nchunk;
+    return (int)prm.order[0].ngroup;
+}
+
 extern "C" int mspl_fuse_sources(int num_sources, const float* const* main_logits, const float* const* aux_logits,
                                  const int* num_classes, const uint8_t* const* lut, int64_t num_images,
                                  int64_t pixels_per_image, int num_target_classes, int policy, int vote_t,

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.mspl_abi_version() == 4
+    assert lib.mspl_abi_version() == 5
     assert lib.mspl_strerror(0) == b"ok" and b"misaligned" in lib.mspl_strerror(-2)
     assert lib.mspl_radix_state_bytes(5) == 5 * 32
     assert lib.mspl_uw_ce_workspace_bytes() >= 16 + 2 * 8 * 148
@@ -122,8 +122,16 @@ def test_class_order_groups_classes_by_target(lib):
         assert bits == want                                                               # one boundary per target group
         assert present.value == sum(1 << int(k) for k in set(lut.tolist()))
         assert sum(bits) == bin(present.value).count("1")
+        # the epilogue's companion table: one vote increment per target group in visiting (= ascending target) order
+        vote = (ctypes.c_uint32 * 8)()
+        nchunk = ctypes.c_uint32(0)
+        ngroup = lib.mspl_class_order_votes(buf, C, 5, vote, ctypes.byref(nchunk))
+        targets = sorted(set(int(k) for k in lut.tolist()))
+        assert ngroup == len(targets) and nchunk.value == -(-C // ch)
+        assert list(vote)[:ngroup] == [1 << (4 * k) for k in targets] and not any(list(vote)[ngroup:])
     bad = (ctypes.c_ubyte * 3)(1, 2, 7)
     assert lib.mspl_class_order(bad, 3, 5, (ctypes.c_ubyte * 3)(), (ctypes.c_ubyte * 64)(), ctypes.byref(ctypes.c_uint32())) == -1
+    assert lib.mspl_class_order_votes(bad, 3, 5, (ctypes.c_uint32 * 8)(), ctypes.byref(ctypes.c_uint32())) == -1
 
 
 def test_vote_threshold_follows_merge_outputs_rule():
