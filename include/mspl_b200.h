@@ -112,7 +112,9 @@ MSPL_API int mspl_class_order_votes(const uint8_t* lut, int num_classes, int num
  * Same outputs and semantics as mspl_fuse_sources, but source s hands over its logits BEFORE the final
  * F.interpolate(..., size=(out_h,out_w), mode='bilinear', align_corners=True) of model/segmentation/espdnet_ue.py:301-302:
  * main_logits[s] is (num_images, C_s, main_hw[2s], main_hw[2s+1]) and aux_logits[s] is (num_images, C_s, aux_hw[2s],
- * aux_hw[2s+1]); the kernel interpolates with ATen's upsample_bilinear2d arithmetic.  HBM traffic falls from
+ * aux_hw[2s+1]); the kernel interpolates with ATen's upsample_bilinear2d source coordinates and weights, summing the four
+ * taps in one fma chain (the interpolated logit can differ from ATen's nested form in the last ulp; the parity definition of this
+ * row excuses labels where the top-2 probability margin is < 1e-5).  HBM traffic falls from
  * 8*sum(C_s) to ~1.25*sum(C_s) bytes per output pixel for the x2 / x4 heads of ESPDNetUE.
  * Needs every row length (main/aux width) to be a multiple of 4 and out_h*out_w % 4 == 0; returns MSPL_ERR_UNSUPPORTED when
  * the tile's source rows do not fit in shared memory (very wide images): upsample and call mspl_fuse_sources instead.
