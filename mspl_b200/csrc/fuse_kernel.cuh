@@ -498,10 +498,15 @@ template <int P> MSPL_DEVINL Px<P> lds_px(const float* p) {
 #ifndef MSPL_LOWRES_PEEL_FIRST
 #define MSPL_LOWRES_PEEL_FIRST 2
 #endif
+// Unroll factor of its chunk loop, separately for the kernels without / with per-target probabilities (GK): 2 removes the
+// loop-carried register moves; measured +1.7 % time without GK (it spills there) and -0.4 % with GK (1.797 -> 1.790 ms per 200
+// images) -- not worth the code size, both stay at 1.
 #ifndef MSPL_LOWRES_CHUNK_UNROLL
 #define MSPL_LOWRES_CHUNK_UNROLL 1
 #endif
-constexpr int kLowresChunkUnroll = MSPL_LOWRES_CHUNK_UNROLL;
+#ifndef MSPL_LOWRES_CHUNK_UNROLL_GK
+#define MSPL_LOWRES_CHUNK_UNROLL_GK 1
+#endif
 
 // Unroll factor of the consumers' chunk loop (2 lets the running statistics ping-pong between two register sets instead of
 // being moved back at the end of every chunk: 164 instead of 171 instructions per chunk, 124 registers).
@@ -1006,6 +1011,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 st.reset(group);
                 const int nchunk = (int)prm.order[s].nchunk;
                 __builtin_assume(nchunk > 0);
+                constexpr int kUnroll = GK ? MSPL_LOWRES_CHUNK_UNROLL_GK : MSPL_LOWRES_CHUNK_UNROLL;
                 auto consume = [&](int chunk, bool first) {
                     Px<P> m[CH], a[CH];
                     tma::mbar_wait(&full[stage], phase);
@@ -1022,10 +1028,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) fuse_sources_lowres_kernel(
                 };
 #if MSPL_LOWRES_PEEL_FIRST == 2
                 consume(0, true);
-#pragma unroll kLowresChunkUnroll
+#pragma unroll kUnroll
                 for (int chunk = 1; chunk < nchunk; ++chunk) consume(chunk, false);
 #else
-#pragma unroll kLowresChunkUnroll
+#pragma unroll kUnroll
                 for (int chunk = 0; chunk < nchunk; ++chunk) consume(chunk, MSPL_LOWRES_PEEL_FIRST ? chunk == 0 : false);
 #endif
                 float d[P];
